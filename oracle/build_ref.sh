@@ -17,7 +17,12 @@ TMP=$(mktemp -d)
 trap 'rm -rf "$TMP"' EXIT
 ARCH="-gencode arch=compute_100a,code=sm_100a"
 NVCC="nvcc -std=c++14 -O2 -DNDEBUG $ARCH -Xcompiler -fPIC,-fopenmp -diag-suppress 20012,20011,20014,550,177,2361 -w"
-g++ -O2 -std=c++14 -fPIC -fpermissive -w $INC -I/usr/local/cuda/include -c "$SRC/scene.cpp" -o "$TMP/scene.o"
+# Scene::loadObj (scene.cpp:206-320) is declared int but falls off its end without a return; g++ >= 8
+# compiles that to a trap (ud2), so every MESH scene would abort.  Build scene.cpp from a temp copy whose
+# only change is a `return 1;` before that function's closing brace (the file's last line).
+sed '$ s/^}[[:space:]]*$/\treturn 1;\n}/' "$SRC/scene.cpp" > "$TMP/scene.cpp"
+[ "$(diff "$SRC/scene.cpp" "$TMP/scene.cpp" | grep -c '^[<>]')" = "1" ] || { echo "scene.cpp patch did not apply as expected" >&2; exit 1; }
+g++ -O2 -std=c++14 -fPIC -fpermissive -w $INC -I/usr/local/cuda/include -c "$TMP/scene.cpp" -o "$TMP/scene.o"
 g++ -O2 -std=c++14 -fPIC -fpermissive -w $INC -I/usr/local/cuda/include -c "$SRC/utilities.cpp" -o "$TMP/utilities.o"
 g++ -O2 -std=c++14 -fPIC -fpermissive -w $INC -I/usr/local/cuda/include -c "$HERE/ref_glue.cpp" -o "$TMP/glue.o"
 HOSTOBJ="$TMP/scene.o $TMP/utilities.o $TMP/glue.o"

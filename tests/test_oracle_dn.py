@@ -1,0 +1,47 @@
+"""CPU tests: the denoiser oracle (oracle/dn_oracle.py) against golden outputs of the reference's own
+AutoEncoder (tools/make_golden_dn.py), plus the weight container round trip."""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+from ai_path_tracer_denoiser_b200 import weights
+from oracle.dn_oracle import DenoiserOracle, synthetic_gbuffer
+
+# Same torch CPU kernels on the same image give identical bits; a different host may reorder the
+# convolution sums, so the stated tolerance is a few fp32 ulps of O(1) outputs.
+ATOL = 2e-5
+
+
+@pytest.mark.parametrize("name", ["dn_64x96", "dn_32x32"])
+def test_oracle_matches_reference_model_golden(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    O = DenoiserOracle(weights.synthetic_state_dict(1234))
+    for j in range(len(g["x"])):
+        y = O.forward(g["x"][j], reset=(j == 0))
+        assert np.abs(y - g["y"][j]).max() <= ATOL
+    assert np.abs(O.hidden[2][0].numpy() - g["hidden3"]).max() <= ATOL * 4
+
+
+def test_state_dict_layout_and_roundtrip(tmp_path):
+    sd = weights.synthetic_state_dict(1234)
+    assert len(sd) == 196
+    assert sum(v.size for k, v in sd.items() if k.endswith((".weight", ".bias"))) == 1508181
+    assert len(weights.conv_layers()) == 28
+    p = weights.save_weights(sd, str(tmp_path / "w.ptdw"))
+    back = weights.load_weights(p)
+    assert len(back) == 168                                                        # 196 minus 28 num_batches_tracked
+    for k, v in back.items():
+        assert v.tobytes() == sd[k].tobytes()
+
+
+def test_pad_crop_and_reset():
+    O = DenoiserOracle(weights.synthetic_state_dict(1234))
+    x = synthetic_gbuffer(40, 50, seed=3)
+    y0 = O.forward(x, reset=True)
+    y1 = O.forward(x, reset=False)
+    y2 = O.forward(x, reset=True)
+    assert y0.shape == (3, 40, 50)
+    assert np.array_equal(y0, y2) and not np.array_equal(y0, y1)                   # hidden state matters
+    assert O.hidden[0].shape == (1, 32, 64, 64) and O.hidden[5].shape == (1, 101, 2, 2)
