@@ -1,0 +1,666 @@
+// Host side of libptd.so: error channel, scene-file + OBJ ingest, camera maths, BVH build.
+//
+// Scene grammar and quirks follow Inference/src/scene.cpp:11-320 and utilities.cpp:45-92 of the reference
+// (SURVEY.md section 8f-1); the matrix algebra restates GLM 0.9.6.3's expression order
+// (gtc/matrix_transform.inl:40-134, detail/type_mat4x4.inl:37-92,686-704, gtc/matrix_inverse.inl:94-147) so
+// that the Geom records are bit-identical to what the reference's loader produces.  Nothing here is on the
+// per-frame path.  Compiled with -ffp-contract=off (x86-64 host code of the reference has no FMA either).
+#include <cfloat>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+#include <algorithm>
+#include "ptd_internal.h"
+
+// ---------------------------------------------------------------------------------------------------
+static thread_local char g_err[512] = "";
+void ptd_set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+extern "C" const char* ptd_last_error(void) { return g_err; }
+extern "C" int ptd_version(void) { return 100; }
+extern "C" int ptd_sizeof(int which) {
+    switch (which) {
+        case 0: return (int)sizeof(ptd_path_segment);
+        case 1: return (int)sizeof(ptd_intersection);
+        case 2: return (int)sizeof(ptd_geom);
+        case 3: return (int)sizeof(ptd_face);
+        case 4: return (int)sizeof(ptd_material);
+        case 5: return (int)sizeof(ptd_camera);
+        case 6: return (int)sizeof(ptd_aabb);
+    }
+    return -1;
+}
+
+// ---- GLM-shaped fp32 algebra (column-major mat4: m[c*4 + r]) ----------------------------------------
+#define PI_F 3.1415926535897932384626422832795028841971f   // utilities.h:13
+namespace {
+struct V4 { float x, y, z, w; };
+inline V4 mul(V4 a, float s) { return V4{a.x * s, a.y * s, a.z * s, a.w * s}; }
+inline V4 add(V4 a, V4 b) { return V4{a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w}; }
+inline V4 sub(V4 a, V4 b) { return V4{a.x - b.x, a.y - b.y, a.z - b.z, a.w - b.w}; }
+inline V4 mulv(V4 a, V4 b) { return V4{a.x * b.x, a.y * b.y, a.z * b.z, a.w * b.w}; }
+struct M4 {
+    float m[16];
+    V4 col(int c) const { return V4{m[c * 4], m[c * 4 + 1], m[c * 4 + 2], m[c * 4 + 3]}; }
+    void set(int c, V4 v) { m[c * 4] = v.x; m[c * 4 + 1] = v.y; m[c * 4 + 2] = v.z; m[c * 4 + 3] = v.w; }
+    float at(int c, int r) const { return m[c * 4 + r]; }
+};
+M4 identity() { M4 r; memset(r.m, 0, sizeof r.m); r.m[0] = r.m[5] = r.m[10] = r.m[15] = 1.f; return r; }
+
+inline ptd_vec3 v3(float x, float y, float z) { ptd_vec3 r = {x, y, z}; return r; }
+inline float dot3(ptd_vec3 a, ptd_vec3 b) { float tx = a.x * b.x, ty = a.y * b.y, tz = a.z * b.z; return tx + ty + tz; }
+inline ptd_vec3 norm3(ptd_vec3 a) { float s = 1.0f / sqrtf(dot3(a, a)); return v3(a.x * s, a.y * s, a.z * s); }
+inline ptd_vec3 cross3(ptd_vec3 x, ptd_vec3 y) {
+    return v3(x.y * y.z - y.y * x.z, x.z * y.x - y.z * x.x, x.x * y.y - y.x * x.y);
+}
+inline ptd_vec3 sub3(ptd_vec3 a, ptd_vec3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+inline ptd_vec3 add3(ptd_vec3 a, ptd_vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+inline float len3(ptd_vec3 a) { return sqrtf(dot3(a, a)); }
+
+M4 matmul(const M4& a, const M4& b) {                       // type_mat4x4.inl:686-704
+    M4 r;
+    for (int j = 0; j < 4; ++j)
+        r.set(j, add(add(add(mul(a.col(0), b.at(j, 0)), mul(a.col(1), b.at(j, 1))), mul(a.col(2), b.at(j, 2))), mul(a.col(3), b.at(j, 3))));
+    return r;
+}
+M4 translate(const M4& m, ptd_vec3 v) {                     // matrix_transform.inl:40-49
+    M4 r = m;
+    r.set(3, add(add(add(mul(m.col(0), v.x), mul(m.col(1), v.y)), mul(m.col(2), v.z)), m.col(3)));
+    return r;
+}
+M4 rotate(const M4& m, float angle, ptd_vec3 v) {           // matrix_transform.inl:52-85
+    const float a = angle, c = cosf(a), s = sinf(a);
+    ptd_vec3 axis = norm3(v);
+    ptd_vec3 temp = v3((1.f - c) * axis.x, (1.f - c) * axis.y, (1.f - c) * axis.z);
+    float R[3][3];
+    R[0][0] = c + temp.x * axis.x;
+    R[0][1] = 0 + temp.x * axis.y + s * axis.z;
+    R[0][2] = 0 + temp.x * axis.z - s * axis.y;
+    R[1][0] = 0 + temp.y * axis.x - s * axis.z;
+    R[1][1] = c + temp.y * axis.y;
+    R[1][2] = 0 + temp.y * axis.z + s * axis.x;
+    R[2][0] = 0 + temp.z * axis.x + s * axis.y;
+    R[2][1] = 0 + temp.z * axis.y - s * axis.x;
+    R[2][2] = c + temp.z * axis.z;
+    M4 r;
+    for (int j = 0; j < 3; ++j)
+        r.set(j, add(add(mul(m.col(0), R[j][0]), mul(m.col(1), R[j][1])), mul(m.col(2), R[j][2])));
+    r.set(3, m.col(3));
+    return r;
+}
+M4 scale(const M4& m, ptd_vec3 v) {                         // matrix_transform.inl:122-134
+    M4 r;
+    r.set(0, mul(m.col(0), v.x)); r.set(1, mul(m.col(1), v.y)); r.set(2, mul(m.col(2), v.z)); r.set(3, m.col(3));
+    return r;
+}
+M4 inverse(const M4& M) {                                   // type_mat4x4.inl:37-92
+#define m(c, r) M.at(c, r)
+    float Coef00 = m(2, 2) * m(3, 3) - m(3, 2) * m(2, 3), Coef02 = m(1, 2) * m(3, 3) - m(3, 2) * m(1, 3), Coef03 = m(1, 2) * m(2, 3) - m(2, 2) * m(1, 3);
+    float Coef04 = m(2, 1) * m(3, 3) - m(3, 1) * m(2, 3), Coef06 = m(1, 1) * m(3, 3) - m(3, 1) * m(1, 3), Coef07 = m(1, 1) * m(2, 3) - m(2, 1) * m(1, 3);
+    float Coef08 = m(2, 1) * m(3, 2) - m(3, 1) * m(2, 2), Coef10 = m(1, 1) * m(3, 2) - m(3, 1) * m(1, 2), Coef11 = m(1, 1) * m(2, 2) - m(2, 1) * m(1, 2);
+    float Coef12 = m(2, 0) * m(3, 3) - m(3, 0) * m(2, 3), Coef14 = m(1, 0) * m(3, 3) - m(3, 0) * m(1, 3), Coef15 = m(1, 0) * m(2, 3) - m(2, 0) * m(1, 3);
+    float Coef16 = m(2, 0) * m(3, 2) - m(3, 0) * m(2, 2), Coef18 = m(1, 0) * m(3, 2) - m(3, 0) * m(1, 2), Coef19 = m(1, 0) * m(2, 2) - m(2, 0) * m(1, 2);
+    float Coef20 = m(2, 0) * m(3, 1) - m(3, 0) * m(2, 1), Coef22 = m(1, 0) * m(3, 1) - m(3, 0) * m(1, 1), Coef23 = m(1, 0) * m(2, 1) - m(2, 0) * m(1, 1);
+    V4 Fac0{Coef00, Coef00, Coef02, Coef03}, Fac1{Coef04, Coef04, Coef06, Coef07}, Fac2{Coef08, Coef08, Coef10, Coef11};
+    V4 Fac3{Coef12, Coef12, Coef14, Coef15}, Fac4{Coef16, Coef16, Coef18, Coef19}, Fac5{Coef20, Coef20, Coef22, Coef23};
+    V4 Vec0{m(1, 0), m(0, 0), m(0, 0), m(0, 0)}, Vec1{m(1, 1), m(0, 1), m(0, 1), m(0, 1)};
+    V4 Vec2{m(1, 2), m(0, 2), m(0, 2), m(0, 2)}, Vec3{m(1, 3), m(0, 3), m(0, 3), m(0, 3)};
+#undef m
+    V4 Inv0 = add(sub(mulv(Vec1, Fac0), mulv(Vec2, Fac1)), mulv(Vec3, Fac2));
+    V4 Inv1 = add(sub(mulv(Vec0, Fac0), mulv(Vec2, Fac3)), mulv(Vec3, Fac4));
+    V4 Inv2 = add(sub(mulv(Vec0, Fac1), mulv(Vec1, Fac3)), mulv(Vec3, Fac5));
+    V4 Inv3 = add(sub(mulv(Vec0, Fac2), mulv(Vec1, Fac4)), mulv(Vec2, Fac5));
+    V4 SignA{+1, -1, +1, -1}, SignB{-1, +1, -1, +1};
+    M4 Inv;
+    Inv.set(0, mulv(Inv0, SignA)); Inv.set(1, mulv(Inv1, SignB)); Inv.set(2, mulv(Inv2, SignA)); Inv.set(3, mulv(Inv3, SignB));
+    V4 Row0{Inv.at(0, 0), Inv.at(1, 0), Inv.at(2, 0), Inv.at(3, 0)};
+    V4 Dot0 = mulv(M.col(0), Row0);
+    float Dot1 = (Dot0.x + Dot0.y) + (Dot0.z + Dot0.w);
+    float OneOverDeterminant = 1.0f / Dot1;
+    M4 r;
+    for (int c = 0; c < 4; ++c) r.set(c, mul(Inv.col(c), OneOverDeterminant));
+    return r;
+}
+M4 inverseTranspose(const M4& M) {                          // gtc/matrix_inverse.inl:94-147
+#define m(c, r) M.at(c, r)
+    float S00 = m(2, 2) * m(3, 3) - m(3, 2) * m(2, 3), S01 = m(2, 1) * m(3, 3) - m(3, 1) * m(2, 3), S02 = m(2, 1) * m(3, 2) - m(3, 1) * m(2, 2);
+    float S03 = m(2, 0) * m(3, 3) - m(3, 0) * m(2, 3), S04 = m(2, 0) * m(3, 2) - m(3, 0) * m(2, 2), S05 = m(2, 0) * m(3, 1) - m(3, 0) * m(2, 1);
+    float S06 = m(1, 2) * m(3, 3) - m(3, 2) * m(1, 3), S07 = m(1, 1) * m(3, 3) - m(3, 1) * m(1, 3), S08 = m(1, 1) * m(3, 2) - m(3, 1) * m(1, 2);
+    float S09 = m(1, 0) * m(3, 3) - m(3, 0) * m(1, 3), S10 = m(1, 0) * m(3, 2) - m(3, 0) * m(1, 2), S11 = m(1, 1) * m(3, 3) - m(3, 1) * m(1, 3);
+    float S12 = m(1, 0) * m(3, 1) - m(3, 0) * m(1, 1), S13 = m(1, 2) * m(2, 3) - m(2, 2) * m(1, 3), S14 = m(1, 1) * m(2, 3) - m(2, 1) * m(1, 3);
+    float S15 = m(1, 1) * m(2, 2) - m(2, 1) * m(1, 2), S16 = m(1, 0) * m(2, 3) - m(2, 0) * m(1, 3), S17 = m(1, 0) * m(2, 2) - m(2, 0) * m(1, 2);
+    float S18 = m(1, 0) * m(2, 1) - m(2, 0) * m(1, 1);
+    M4 I;
+    float* o = I.m;
+    o[0] = +(m(1, 1) * S00 - m(1, 2) * S01 + m(1, 3) * S02);
+    o[1] = -(m(1, 0) * S00 - m(1, 2) * S03 + m(1, 3) * S04);
+    o[2] = +(m(1, 0) * S01 - m(1, 1) * S03 + m(1, 3) * S05);
+    o[3] = -(m(1, 0) * S02 - m(1, 1) * S04 + m(1, 2) * S05);
+    o[4] = -(m(0, 1) * S00 - m(0, 2) * S01 + m(0, 3) * S02);
+    o[5] = +(m(0, 0) * S00 - m(0, 2) * S03 + m(0, 3) * S04);
+    o[6] = -(m(0, 0) * S01 - m(0, 1) * S03 + m(0, 3) * S05);
+    o[7] = +(m(0, 0) * S02 - m(0, 1) * S04 + m(0, 2) * S05);
+    o[8] = +(m(0, 1) * S06 - m(0, 2) * S07 + m(0, 3) * S08);
+    o[9] = -(m(0, 0) * S06 - m(0, 2) * S09 + m(0, 3) * S10);
+    o[10] = +(m(0, 0) * S11 - m(0, 1) * S09 + m(0, 3) * S12);
+    o[11] = -(m(0, 0) * S08 - m(0, 1) * S10 + m(0, 2) * S12);
+    o[12] = -(m(0, 1) * S13 - m(0, 2) * S14 + m(0, 3) * S15);
+    o[13] = +(m(0, 0) * S13 - m(0, 2) * S16 + m(0, 3) * S17);
+    o[14] = -(m(0, 0) * S14 - m(0, 1) * S16 + m(0, 3) * S18);
+    o[15] = +(m(0, 0) * S15 - m(0, 1) * S17 + m(0, 2) * S18);
+    float Determinant = +m(0, 0) * o[0] + m(0, 1) * o[1] + m(0, 2) * o[2] + m(0, 3) * o[3];
+#undef m
+    for (int i = 0; i < 16; ++i) o[i] /= Determinant;
+    return I;
+}
+M4 buildTransformationMatrix(ptd_vec3 t, ptd_vec3 r, ptd_vec3 s) {    // utilities.cpp:45-52
+    M4 T = translate(identity(), t);
+    M4 R = rotate(identity(), r.x * PI_F / 180, v3(1, 0, 0));
+    R = matmul(R, rotate(identity(), r.y * PI_F / 180, v3(0, 1, 0)));
+    R = matmul(R, rotate(identity(), r.z * PI_F / 180, v3(0, 0, 1)));
+    M4 S = scale(identity(), s);
+    return matmul(matmul(T, R), S);
+}
+
+// ---- text helpers (utilities.cpp:54-92) --------------------------------------------------------------
+bool safeGetline(std::istream& is, std::string& t) {
+    t.clear();
+    std::streambuf* sb = is.rdbuf();
+    if (!is.good()) return false;
+    for (;;) {
+        int c = sb->sbumpc();
+        switch (c) {
+            case '\n': return true;
+            case '\r': if (sb->sgetc() == '\n') sb->sbumpc(); return true;
+            case EOF: if (t.empty()) is.setstate(std::ios::eofbit); return true;
+            default: t += (char)c;
+        }
+    }
+}
+std::vector<std::string> tokenize(const std::string& s) {
+    std::istringstream ss(s);
+    std::vector<std::string> out;
+    std::string w;
+    while (ss >> w) out.push_back(w);
+    return out;
+}
+inline float tokf(const std::vector<std::string>& t, size_t i) { return i < t.size() ? (float)atof(t[i].c_str()) : 0.f; }
+inline int toki(const std::vector<std::string>& t, size_t i) { return i < t.size() ? atoi(t[i].c_str()) : 0; }
+inline ptd_vec3 tok3(const std::vector<std::string>& t) { return v3(tokf(t, 1), tokf(t, 2), tokf(t, 3)); }
+
+// ---- OBJ ingest: the subset of tinyobjloader the reference relies on (scene.cpp:259-317) --------------
+// Real numbers follow tinyobj's own digit-accumulating parser (tiny_obj_loader.h:805-929), not strtod, so
+// the float bits match: integer digits mantissa*10+d, fraction digits d*10^-k (table for k<8, pow beyond),
+// exponent through ldexp(mantissa*5^e, e).
+bool parse_real(const char*& p, float* out) {
+    while (*p == ' ' || *p == '\t') ++p;
+    const char* s = p;
+    const char* e = s;
+    while (*e && *e != ' ' && *e != '\t' && *e != '\r' && *e != '\n') ++e;
+    p = e;
+    if (s >= e) return false;
+    double mantissa = 0.0;
+    int exponent = 0, read = 0;
+    char sign = '+', exp_sign = '+';
+    const char* c = s;
+    bool lead_dot = false;
+    auto digit = [](char ch) { return ch >= '0' && ch <= '9'; };
+    if (*c == '+' || *c == '-') { sign = *c; ++c; if (c != e && *c == '.') lead_dot = true; }
+    else if (digit(*c)) {}
+    else if (*c == '.') lead_dot = true;
+    else return false;
+    if (!lead_dot) {
+        while (c != e && digit(*c)) { mantissa *= 10; mantissa += (int)(*c - '0'); ++c; ++read; }
+        if (read == 0) return false;
+    }
+    if (c != e && *c == '.') {
+        ++c; read = 1;
+        static const double lut[] = {1.0, 0.1, 0.01, 0.001, 0.0001, 0.00001, 0.000001, 0.0000001};
+        while (c != e && digit(*c)) {
+            mantissa += (int)(*c - '0') * (read < 8 ? lut[read] : std::pow(10.0, -read));
+            ++read; ++c;
+        }
+    }
+    if (c != e && (*c == 'e' || *c == 'E')) {
+        ++c;
+        if (c != e && (*c == '+' || *c == '-')) { exp_sign = *c; ++c; }
+        else if (c == e || !digit(*c)) return false;
+        read = 0;
+        while (c != e && digit(*c)) { exponent = exponent * 10 + (int)(*c - '0'); ++c; ++read; }
+        exponent *= (exp_sign == '+' ? 1 : -1);
+        if (read == 0) return false;
+    }
+    double r = (sign == '+' ? 1 : -1) * (exponent ? std::ldexp(mantissa * std::pow(5.0, exponent), exponent) : mantissa);
+    *out = (float)r;
+    return true;
+}
+struct ObjIdx { int v, vt, vn; };
+bool fix_index(int idx, int n, int* out) {               // tiny_obj_loader.h fixIndex: 1-based, negative = relative
+    if (idx > 0) { *out = idx - 1; return true; }
+    if (idx == 0) return false;
+    *out = n + idx;
+    return true;
+}
+bool parse_triple(const char*& p, int nv, int nt, int nn, ObjIdx* out) {
+    while (*p == ' ' || *p == '\t') ++p;
+    if (!*p || *p == '\r' || *p == '\n') return false;
+    out->v = out->vt = out->vn = -1;
+    if (!fix_index(atoi(p), nv, &out->v)) return false;
+    p += strcspn(p, "/ \t\r\n");
+    if (*p != '/') return true;
+    ++p;
+    if (*p == '/') {                                     // v//vn
+        ++p;
+        if (!fix_index(atoi(p), nn, &out->vn)) return false;
+        p += strcspn(p, "/ \t\r\n");
+        return true;
+    }
+    if (!fix_index(atoi(p), nt, &out->vt)) return false;  // v/vt[/vn]
+    p += strcspn(p, "/ \t\r\n");
+    if (*p != '/') return true;
+    ++p;
+    if (!fix_index(atoi(p), nn, &out->vn)) return false;
+    p += strcspn(p, "/ \t\r\n");
+    return true;
+}
+
+ptd_status load_obj(ptd_scene& sc, const std::string& path, int materialid, const M4& transform) {
+    std::ifstream f(path.c_str());
+    if (!f.is_open()) PTD_FAIL(PTD_ERR_IO, "cannot open OBJ file '%s'", path.c_str());
+    std::vector<float> V, N;
+    std::string line;
+    std::vector<ObjIdx> poly;
+    long lineno = 0;
+    while (safeGetline(f, line) && (f.good() || !line.empty())) {
+        ++lineno;
+        const char* p = line.c_str();
+        while (*p == ' ' || *p == '\t') ++p;
+        if (p[0] == 'v' && (p[1] == ' ' || p[1] == '\t')) {
+            p += 2;
+            float x = 0, y = 0, z = 0;
+            parse_real(p, &x); parse_real(p, &y); parse_real(p, &z);
+            V.push_back(x); V.push_back(y); V.push_back(z);
+        } else if (p[0] == 'v' && p[1] == 'n' && (p[2] == ' ' || p[2] == '\t')) {
+            p += 3;
+            float x = 0, y = 0, z = 0;
+            parse_real(p, &x); parse_real(p, &y); parse_real(p, &z);
+            N.push_back(x); N.push_back(y); N.push_back(z);
+        } else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t')) {
+            p += 2;
+            poly.clear();
+            ObjIdx ix;
+            while (parse_triple(p, (int)V.size() / 3, 0, (int)N.size() / 3, &ix)) poly.push_back(ix);
+            if (poly.size() < 3) continue;
+            for (size_t k = 2; k < poly.size(); ++k) {     // triangulate=true: fan (i0, i[k-1], i[k])
+                const ObjIdx tri[3] = {poly[0], poly[k - 1], poly[k]};
+                ptd_face face;
+                memset(&face, 0, sizeof face);
+                bool have_n = true;
+                for (int v = 0; v < 3; ++v) {
+                    if (tri[v].v < 0 || tri[v].v * 3 + 2 >= (int)V.size())
+                        PTD_FAIL(PTD_ERR_PARSE, "%s:%ld: vertex index out of range", path.c_str(), lineno);
+                    V4 pos{V[3 * tri[v].v], V[3 * tri[v].v + 1], V[3 * tri[v].v + 2], 1.f};
+                    // transform * vec4 (type_mat4x4.inl:617-628): (m0*v0 + m1*v1) + (m2*v2 + m3*v3)
+                    V4 t = add(add(mul(transform.col(0), pos.x), mul(transform.col(1), pos.y)),
+                               add(mul(transform.col(2), pos.z), mul(transform.col(3), pos.w)));
+                    face.v[v] = v3(t.x, t.y, t.z);
+                    if (sc.mesh_box.lb.x > t.x) sc.mesh_box.lb.x = t.x;      // scene.h:28-42
+                    if (sc.mesh_box.lb.y > t.y) sc.mesh_box.lb.y = t.y;
+                    if (sc.mesh_box.lb.z > t.z) sc.mesh_box.lb.z = t.z;
+                    if (sc.mesh_box.ub.x < t.x) sc.mesh_box.ub.x = t.x;
+                    if (sc.mesh_box.ub.y < t.y) sc.mesh_box.ub.y = t.y;
+                    if (sc.mesh_box.ub.z < t.z) sc.mesh_box.ub.z = t.z;
+                    if (tri[v].vn >= 0 && tri[v].vn * 3 + 2 < (int)N.size())
+                        face.n[v] = norm3(v3(N[3 * tri[v].vn], N[3 * tri[v].vn + 1], N[3 * tri[v].vn + 2]));   // scene.cpp:304-307 (untransformed)
+                    else
+                        have_n = false;
+                }
+                if (!have_n) {   // the reference reads out of bounds here; we fall back to its RECOMPUTE_NORMALS formula (scene.cpp:198-204)
+                    ptd_vec3 g = norm3(cross3(sub3(face.v[2], face.v[0]), sub3(face.v[1], face.v[0])));
+                    face.n[0] = face.n[1] = face.n[2] = g;
+                }
+                face.materialid = materialid;
+                sc.faces.push_back(face);
+            }
+        }
+    }
+    return PTD_OK;
+}
+
+std::string dirname_of(const std::string& p) {
+    size_t k = p.find_last_of('/');
+    return k == std::string::npos ? std::string(".") : p.substr(0, k);
+}
+}  // namespace
+
+// scene.cpp:142-152: derived camera fields (fov uses tan of the FULL fovy, sic)
+void ptd_camera_derive(ptd_camera& cam, float fovy) {
+    float yscaled = tanf(fovy * (PI_F / 180));
+    float xscaled = (yscaled * cam.res_x) / cam.res_y;
+    float fovx = (atanf(xscaled) * 180) / PI_F;
+    cam.fov_x = fovx;
+    cam.fov_y = fovy;
+    cam.pixelLength_x = 2 * xscaled / (float)cam.res_x;
+    cam.pixelLength_y = 2 * yscaled / (float)cam.res_y;
+}
+
+extern "C" ptd_status ptd_scene_load(const char* path, ptd_scene** out) {
+    if (!path || !out) PTD_FAIL(PTD_ERR_ARG, "ptd_scene_load: null argument");
+    *out = nullptr;
+    std::ifstream in(path);
+    if (!in.is_open()) PTD_FAIL(PTD_ERR_IO, "cannot open scene file '%s'", path);   // scene.cpp:16-19 throws here
+    ptd_scene* sc = new ptd_scene();
+    memset(&sc->mesh_box, 0, sizeof sc->mesh_box);
+    memset(&sc->camera, 0, sizeof sc->camera);
+    bool have_camera = false;
+    std::string line;
+    ptd_status rc = PTD_OK;
+    while (in.good() && rc == PTD_OK) {
+        safeGetline(in, line);
+        if (line.empty()) continue;
+        std::vector<std::string> tk = tokenize(line);
+        if (tk.empty()) continue;
+        if (tk[0] == "MATERIAL") {                                                    // scene.cpp:161-196
+            if (toki(tk, 1) != (int)sc->materials.size()) continue;                  // id mismatch: block skipped line by line
+            ptd_material m;
+            memset(&m, 0, sizeof m);
+            for (int i = 0; i < 7; ++i) {
+                safeGetline(in, line);
+                std::vector<std::string> t = tokenize(line);
+                if (t.empty()) continue;
+                if (t[0] == "RGB") m.color = tok3(t);
+                else if (t[0] == "SPECEX") m.specular_exponent = tokf(t, 1);
+                else if (t[0] == "SPECRGB") m.specular_color = tok3(t);
+                else if (t[0] == "REFL") m.hasReflective = tokf(t, 1);
+                else if (t[0] == "REFR") m.hasRefractive = tokf(t, 1);
+                else if (t[0] == "REFRIOR") m.indexOfRefraction = tokf(t, 1);
+                else if (t[0] == "EMITTANCE") m.emittance = tokf(t, 1);
+            }
+            sc->materials.push_back(m);
+        } else if (tk[0] == "OBJECT") {                                               // scene.cpp:44-100
+            if (toki(tk, 1) != (int)sc->geoms.size()) continue;
+            ptd_geom g;
+            memset(&g, 0, sizeof g);
+            g.type = -1;
+            safeGetline(in, line);
+            if (!line.empty() && in.good()) {
+                if (line == "sphere") g.type = PTD_SPHERE;                            // whole-line strcmp, scene.cpp:57-63
+                else if (line == "cube") g.type = PTD_CUBE;
+            }
+            safeGetline(in, line);
+            if (!line.empty() && in.good()) g.materialid = toki(tokenize(line), 1);
+            safeGetline(in, line);
+            while (!line.empty() && in.good()) {
+                std::vector<std::string> t = tokenize(line);
+                if (!t.empty()) {
+                    if (t[0] == "TRANS") g.translation = tok3(t);
+                    else if (t[0] == "ROTAT") g.rotation = tok3(t);
+                    else if (t[0] == "SCALE") g.scale = tok3(t);
+                    else if (t[0] == "VEL") g.vel = tok3(t);
+                }
+                safeGetline(in, line);
+            }
+            M4 T = buildTransformationMatrix(g.translation, g.rotation, g.scale);
+            M4 I = inverse(T), IT = inverseTranspose(T);
+            memcpy(g.transform, T.m, 64); memcpy(g.inverseTransform, I.m, 64); memcpy(g.invTranspose, IT.m, 64);
+            sc->geoms.push_back(g);
+        } else if (tk[0] == "CAMERA") {                                               // scene.cpp:102-159
+            ptd_camera& cam = sc->camera;
+            float fovy = 0.f;
+            for (int i = 0; i < 5; ++i) {
+                safeGetline(in, line);
+                std::vector<std::string> t = tokenize(line);
+                if (t.empty()) continue;
+                if (t[0] == "RES") { cam.res_x = toki(t, 1); cam.res_y = toki(t, 2); }
+                else if (t[0] == "FOVY") fovy = tokf(t, 1);
+                else if (t[0] == "ITERATIONS") sc->iterations = toki(t, 1);
+                else if (t[0] == "DEPTH") sc->trace_depth = toki(t, 1);
+                else if (t[0] == "FILE") sc->image_name = t.size() > 1 ? t[1] : "";
+            }
+            safeGetline(in, line);
+            while (!line.empty() && in.good()) {
+                std::vector<std::string> t = tokenize(line);
+                if (!t.empty()) {
+                    if (t[0] == "EYE") cam.position = tok3(t);
+                    else if (t[0] == "LOOKAT") cam.lookAt = tok3(t);
+                    else if (t[0] == "UP") cam.up = tok3(t);
+                }
+                safeGetline(in, line);
+            }
+            if (cam.res_x <= 0 || cam.res_y <= 0) { ptd_set_error("%s: CAMERA block without a valid RES line", path); rc = PTD_ERR_PARSE; break; }
+            sc->fovy_deg = fovy;
+            ptd_camera_derive(cam, fovy);
+            cam.right = norm3(cross3(cam.view, cam.up));      // computed from the still-zero view (scene.cpp:148 before :152) -> NaN; runCuda overwrites it
+            cam.view = norm3(sub3(cam.lookAt, cam.position));
+            have_camera = true;
+        } else if (tk[0] == "MESH") {                                                 // scene.cpp:206-320
+            if (toki(tk, 1) != 0) continue;                                           // "Max number of meshes == 1"
+            sc->mesh_box.lb = v3(FLT_MAX, FLT_MAX, FLT_MAX);
+            sc->mesh_box.ub = v3(FLT_MIN, FLT_MIN, FLT_MIN);                          // numeric_limits<float>::min(), sic (:216-218)
+            std::string obj;
+            safeGetline(in, line);
+            if (!line.empty() && in.good()) { std::vector<std::string> t = tokenize(line); if (t.size() > 1 && t[0] == "PATH") obj = t[1]; }
+            int materialid = 0;
+            safeGetline(in, line);
+            if (!line.empty() && in.good()) materialid = toki(tokenize(line), 1);
+            ptd_vec3 tr = v3(0, 0, 0), ro = v3(0, 0, 0), sca = v3(0, 0, 0);
+            safeGetline(in, line);
+            while (!line.empty() && in.good()) {
+                std::vector<std::string> t = tokenize(line);
+                if (!t.empty()) {
+                    if (t[0] == "TRANS") tr = tok3(t);
+                    else if (t[0] == "ROTAT") ro = tok3(t);
+                    else if (t[0] == "SCALE") sca = tok3(t);
+                }
+                safeGetline(in, line);
+            }
+            M4 T = buildTransformationMatrix(tr, ro, sca);
+            // the reference resolves PATH against the process cwd; we also try the scene file's directory
+            std::string p1 = obj, p2 = dirname_of(path) + "/" + obj;
+            std::ifstream probe(p1.c_str());
+            rc = load_obj(*sc, probe.is_open() ? p1 : p2, materialid, T);
+        }
+    }
+    if (rc == PTD_OK && !have_camera) { ptd_set_error("%s: no CAMERA block", path); rc = PTD_ERR_PARSE; }
+    if (rc != PTD_OK) { delete sc; return rc; }
+    *out = sc;
+    return PTD_OK;
+}
+
+extern "C" ptd_status ptd_scene_from_arrays(int ngeoms, const ptd_geom* geoms, int nmaterials, const ptd_material* materials,
+                                            int nfaces, const ptd_face* faces, const ptd_aabb* mesh_box, const ptd_camera* camera,
+                                            int trace_depth, int iterations, ptd_scene** out) {
+    if (!out || !camera || ngeoms < 0 || nmaterials < 0 || nfaces < 0 || (ngeoms && !geoms) || (nmaterials && !materials) || (nfaces && !faces))
+        PTD_FAIL(PTD_ERR_ARG, "ptd_scene_from_arrays: bad argument");
+    if (camera->res_x <= 0 || camera->res_y <= 0) PTD_FAIL(PTD_ERR_ARG, "ptd_scene_from_arrays: camera resolution %dx%d", camera->res_x, camera->res_y);
+    ptd_scene* sc = new ptd_scene();
+    sc->geoms.assign(geoms, geoms + ngeoms);
+    sc->materials.assign(materials, materials + nmaterials);
+    sc->faces.assign(faces, faces + nfaces);
+    if (mesh_box) sc->mesh_box = *mesh_box; else memset(&sc->mesh_box, 0, sizeof sc->mesh_box);
+    sc->camera = *camera;
+    sc->fovy_deg = camera->fov_y;
+    sc->trace_depth = trace_depth;
+    sc->iterations = iterations;
+    *out = sc;
+    return PTD_OK;
+}
+extern "C" void ptd_scene_free(ptd_scene* s) { delete s; }
+extern "C" ptd_status ptd_scene_counts(const ptd_scene* s, int out[5]) {
+    if (!s || !out) PTD_FAIL(PTD_ERR_ARG, "ptd_scene_counts: null argument");
+    out[0] = (int)s->geoms.size(); out[1] = (int)s->materials.size(); out[2] = (int)s->faces.size();
+    out[3] = s->trace_depth; out[4] = s->iterations;
+    return PTD_OK;
+}
+extern "C" const ptd_geom* ptd_scene_geoms(const ptd_scene* s) { return s && !s->geoms.empty() ? s->geoms.data() : nullptr; }
+extern "C" const ptd_material* ptd_scene_materials(const ptd_scene* s) { return s && !s->materials.empty() ? s->materials.data() : nullptr; }
+extern "C" const ptd_face* ptd_scene_faces(const ptd_scene* s) { return s && !s->faces.empty() ? s->faces.data() : nullptr; }
+extern "C" const ptd_aabb* ptd_scene_mesh_box(const ptd_scene* s) { return s ? &s->mesh_box : nullptr; }
+extern "C" ptd_camera* ptd_scene_camera(ptd_scene* s) { return s ? &s->camera : nullptr; }
+extern "C" ptd_status ptd_scene_set_resolution(ptd_scene* s, int w, int h) {
+    if (!s || w <= 0 || h <= 0) PTD_FAIL(PTD_ERR_ARG, "ptd_scene_set_resolution: bad argument");
+    s->camera.res_x = w; s->camera.res_y = h;
+    ptd_camera_derive(s->camera, s->fovy_deg);
+    return PTD_OK;
+}
+extern "C" ptd_status ptd_scene_set_depth(ptd_scene* s, int d) {
+    if (!s || d < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_scene_set_depth: bad argument");
+    s->trace_depth = d;
+    return PTD_OK;
+}
+
+// main.cpp:66-78
+extern "C" ptd_status ptd_camera_orbit_params(const ptd_camera* cam, float* zoom, float* phi, float* theta) {
+    if (!cam || !zoom || !phi || !theta) PTD_FAIL(PTD_ERR_ARG, "ptd_camera_orbit_params: null argument");
+    ptd_vec3 view = cam->view;
+    ptd_vec3 viewXZ = v3(view.x, 0.0f, view.z), viewZY = v3(0.0f, view.y, view.z);
+    *phi = acosf(dot3(norm3(viewXZ), v3(0, 0, -1)));
+    *theta = acosf(dot3(norm3(viewZY), v3(0, 1, 0)));
+    *zoom = len3(sub3(cam->position, cam->lookAt));
+    return PTD_OK;
+}
+// main.cpp:126-138 (cam.right is deliberately NOT normalised, like the reference)
+extern "C" ptd_status ptd_camera_orbit(ptd_camera* cam, float zoom, float phi, float theta) {
+    if (!cam) PTD_FAIL(PTD_ERR_ARG, "ptd_camera_orbit: null argument");
+    ptd_vec3 cp;
+    cp.x = zoom * sinf(phi) * sinf(theta);
+    cp.y = zoom * cosf(theta);
+    cp.z = zoom * cosf(phi) * sinf(theta);
+    ptd_vec3 n = norm3(cp);
+    cam->view = v3(-n.x, -n.y, -n.z);
+    ptd_vec3 v = cam->view, u = v3(0, 1, 0);
+    ptd_vec3 r = cross3(v, u);
+    cam->up = cross3(r, v);
+    cam->right = r;
+    cam->position = add3(cp, cam->lookAt);
+    return PTD_OK;
+}
+
+// ---- BVH build: binned SAH, host side, once per scene ---------------------------------------------------
+namespace {
+struct Box { float lo[3], hi[3]; };
+inline void box_reset(Box& b) { for (int a = 0; a < 3; ++a) { b.lo[a] = FLT_MAX; b.hi[a] = -FLT_MAX; } }
+inline void box_grow(Box& b, const float* p) { for (int a = 0; a < 3; ++a) { b.lo[a] = std::min(b.lo[a], p[a]); b.hi[a] = std::max(b.hi[a], p[a]); } }
+inline void box_merge(Box& b, const Box& o) { for (int a = 0; a < 3; ++a) { b.lo[a] = std::min(b.lo[a], o.lo[a]); b.hi[a] = std::max(b.hi[a], o.hi[a]); } }
+inline float box_area(const Box& b) {
+    float d[3] = {b.hi[0] - b.lo[0], b.hi[1] - b.lo[1], b.hi[2] - b.lo[2]};
+    if (d[0] < 0) return 0.f;
+    return 2.f * (d[0] * d[1] + d[1] * d[2] + d[2] * d[0]);
+}
+}  // namespace
+
+void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out) {
+    const int n = (int)faces.size();
+    out.nodes.clear(); out.tris.clear(); out.leaves = out.max_leaf = out.max_depth = 0;
+    if (n == 0) return;
+    std::vector<Box> tb(n);
+    std::vector<float> cen((size_t)n * 3);
+    Box all; box_reset(all);
+    for (int i = 0; i < n; ++i) {
+        box_reset(tb[i]);
+        for (int v = 0; v < 3; ++v) box_grow(tb[i], &faces[i].v[v].x);
+        for (int a = 0; a < 3; ++a) cen[(size_t)i * 3 + a] = 0.5f * (tb[i].lo[a] + tb[i].hi[a]);
+        box_merge(all, tb[i]);
+    }
+    // Conservative padding: a hit point computed in fp32 (and the slab test itself) may be off by a few ulps of the
+    // scene extent; every triangle box is grown by `pad` so traversal never culls a face brute force would hit.
+    float diag = sqrtf((all.hi[0] - all.lo[0]) * (all.hi[0] - all.lo[0]) + (all.hi[1] - all.lo[1]) * (all.hi[1] - all.lo[1]) +
+                       (all.hi[2] - all.lo[2]) * (all.hi[2] - all.lo[2]));
+    float maxabs = 0.f;
+    for (int a = 0; a < 3; ++a) maxabs = std::max(maxabs, std::max(fabsf(all.lo[a]), fabsf(all.hi[a])));
+    const float pad = 3e-5f * std::max(diag, maxabs) + 1e-6f;
+    for (int i = 0; i < n; ++i) for (int a = 0; a < 3; ++a) { tb[i].lo[a] -= pad; tb[i].hi[a] += pad; }
+
+    std::vector<int> idx(n);
+    for (int i = 0; i < n; ++i) idx[i] = i;
+    struct Task { int node, lo, hi, depth; };
+    std::vector<Task> stack;
+    out.nodes.reserve((size_t)n);
+    out.nodes.push_back(PtdBvhNode());
+    stack.push_back(Task{0, 0, n, 1});
+    const int NB = 16, MAX_LEAF = 4;
+    std::vector<int> order;
+    order.reserve(n);
+    while (!stack.empty()) {
+        Task t = stack.back();
+        stack.pop_back();
+        Box nb, cb;
+        box_reset(nb); box_reset(cb);
+        for (int i = t.lo; i < t.hi; ++i) { box_merge(nb, tb[idx[i]]); box_grow(cb, &cen[(size_t)idx[i] * 3]); }
+        PtdBvhNode& node = out.nodes[t.node];
+        for (int a = 0; a < 3; ++a) { node.bmin[a] = nb.lo[a]; node.bmax[a] = nb.hi[a]; }
+        const int cnt = t.hi - t.lo;
+        out.max_depth = std::max(out.max_depth, t.depth);
+        int split = -1;
+        if (cnt > MAX_LEAF) {
+            float best = FLT_MAX;
+            int best_axis = -1, best_bin = -1;
+            for (int a = 0; a < 3; ++a) {
+                float ext = cb.hi[a] - cb.lo[a];
+                if (!(ext > 0.f)) continue;
+                Box bb[NB]; int bc[NB];
+                for (int b = 0; b < NB; ++b) { box_reset(bb[b]); bc[b] = 0; }
+                float k = NB * (1.f - 1e-6f) / ext;
+                for (int i = t.lo; i < t.hi; ++i) {
+                    int b = std::min(NB - 1, std::max(0, (int)((cen[(size_t)idx[i] * 3 + a] - cb.lo[a]) * k)));
+                    box_merge(bb[b], tb[idx[i]]); bc[b]++;
+                }
+                float la[NB], ra[NB]; int lc[NB], rc[NB];
+                Box acc; box_reset(acc); int c = 0;
+                for (int b = 0; b < NB; ++b) { box_merge(acc, bb[b]); c += bc[b]; la[b] = box_area(acc); lc[b] = c; }
+                box_reset(acc); c = 0;
+                for (int b = NB - 1; b >= 0; --b) { box_merge(acc, bb[b]); c += bc[b]; ra[b] = box_area(acc); rc[b] = c; }
+                for (int b = 0; b < NB - 1; ++b) {
+                    if (lc[b] == 0 || rc[b + 1] == 0) continue;
+                    float cost = la[b] * lc[b] + ra[b + 1] * rc[b + 1];
+                    if (cost < best) { best = cost; best_axis = a; best_bin = b; }
+                }
+            }
+            if (best_axis >= 0) {
+                float ext = cb.hi[best_axis] - cb.lo[best_axis];
+                float k = NB * (1.f - 1e-6f) / ext;
+                int* first = idx.data() + t.lo;
+                int* last = idx.data() + t.hi;
+                int* mid = std::partition(first, last, [&](int i) {
+                    int b = std::min(NB - 1, std::max(0, (int)((cen[(size_t)i * 3 + best_axis] - cb.lo[best_axis]) * k)));
+                    return b <= best_bin;
+                });
+                split = (int)(mid - idx.data());
+                if (split == t.lo || split == t.hi) split = -1;
+            }
+            if (split < 0 && cnt > 16) {   // degenerate centroids: median split by index keeps leaves bounded
+                split = t.lo + cnt / 2;
+            }
+        }
+        if (split < 0) {
+            node.first = (int)order.size();
+            node.count = cnt;
+            for (int i = t.lo; i < t.hi; ++i) order.push_back(idx[i]);
+            std::sort(order.end() - cnt, order.end());    // ascending face index inside a leaf
+            out.leaves++;
+            out.max_leaf = std::max(out.max_leaf, cnt);
+        } else {
+            int l = (int)out.nodes.size();
+            out.nodes.push_back(PtdBvhNode());
+            out.nodes.push_back(PtdBvhNode());
+            out.nodes[t.node].first = l;
+            out.nodes[t.node].count = 0;
+            stack.push_back(Task{l + 1, split, t.hi, t.depth + 1});
+            stack.push_back(Task{l, t.lo, split, t.depth + 1});
+        }
+    }
+    out.tris.resize(order.size());
+    for (size_t k = 0; k < order.size(); ++k) {
+        const ptd_face& f = faces[order[k]];
+        PtdBvhTri& t = out.tris[k];
+        t.v0[0] = f.v[0].x; t.v0[1] = f.v[0].y; t.v0[2] = f.v[0].z; t.face = order[k];
+        t.v1[0] = f.v[1].x; t.v1[1] = f.v[1].y; t.v1[2] = f.v[1].z; t.material = f.materialid;
+        t.v2[0] = f.v[2].x; t.v2[1] = f.v[2].y; t.v2[2] = f.v[2].z; t.pad = 0;
+    }
+}

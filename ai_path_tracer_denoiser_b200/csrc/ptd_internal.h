@@ -1,0 +1,50 @@
+// Internal declarations shared by the host (C++) and device (CUDA) translation units of libptd.so.
+#pragma once
+#include <string>
+#include <vector>
+#include <cstdarg>
+#include <cstdio>
+#include "ptd.h"
+
+static_assert(sizeof(ptd_path_segment) == 44 && sizeof(ptd_intersection) == 36 && sizeof(ptd_geom) == 248 &&
+              sizeof(ptd_face) == 76 && sizeof(ptd_material) == 44 && sizeof(ptd_camera) == 84 && sizeof(ptd_aabb) == 24,
+              "record layouts must match Inference/src/sceneStructs.h");
+
+void ptd_set_error(const char* fmt, ...);
+#define PTD_FAIL(code, ...) do { ptd_set_error(__VA_ARGS__); return (code); } while (0)
+
+struct ptd_scene {
+    std::vector<ptd_geom> geoms;
+    std::vector<ptd_material> materials;
+    std::vector<ptd_face> faces;
+    ptd_aabb mesh_box;
+    ptd_camera camera;
+    float fovy_deg = 45.f;
+    int trace_depth = 8;
+    int iterations = 1;
+    std::string image_name;
+};
+
+// ---- BVH over the mesh faces (new work: the reference brute-forces every face, pathtrace.cu:258-269) ----
+// 32-byte node.  Interior: count == 0, left child = first, right child = first + 1.
+// Leaf: count > 0, triangles [first, first + count) of the leaf-ordered triangle array.
+struct PtdBvhNode {
+    float bmin[3]; int first;
+    float bmax[3]; int count;
+};
+// Leaf-ordered triangle record for traversal: vertex positions only (48 B); w of v0 holds the original face
+// index (the reference's array order decides ties, pathtrace.cu:261), w of v1 the material id.
+struct PtdBvhTri {
+    float v0[3]; int face;
+    float v1[3]; int material;
+    float v2[3]; int pad;
+};
+struct PtdBvh {
+    std::vector<PtdBvhNode> nodes;
+    std::vector<PtdBvhTri> tris;
+    int leaves = 0, max_leaf = 0, max_depth = 0;
+};
+void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out);
+
+// camera helpers shared with the CLI
+void ptd_camera_derive(ptd_camera& cam, float fovy_deg);

@@ -1,0 +1,138 @@
+/* ptd.h - C ABI of the B200-native path-trace + denoise hot paths.
+ *
+ * Drop-in boundary for Black-Phoenix/Ai-Path-Tracer-Denoiser's render loop (Inference/src/main.cpp:120-168):
+ *   HP-1  pathtraceInit / pathtrace / pathtraceFree           (Inference/src/pathtrace.h:6-8)
+ *   HP-2  network_prediction_faster_version(float* rgb)        (Inference/src/main.cpp:101-118),
+ *         i.e. torch::jit Module.forward([1,10,H,W]) -> [1,3,H,W] of training/recurrent_autoencoder_model.py
+ * plus the scene-file loader the north-star says to keep (Inference/src/scene.cpp:11-320).
+ *
+ * Conventions: plain C, POD pointers and sizes only; every function returns a ptd_status (0 = ok,
+ * negative = error, text via ptd_last_error()); nothing throws or exits across the boundary; handles
+ * are opaque and own all device memory; "dev" pointers are CUDA device pointers on the handle's
+ * device, `stream` is a cudaStream_t passed as void* (NULL = default stream).
+ * There is NO CPU fallback: every compute entry point fails with PTD_ERR_CUDA when no device exists.
+ */
+#ifndef PTD_H
+#define PTD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef int ptd_status;
+enum {
+    PTD_OK = 0,
+    PTD_ERR_ARG = -1,      /* bad argument / null handle                       */
+    PTD_ERR_IO = -2,       /* file missing or unreadable                        */
+    PTD_ERR_PARSE = -3,    /* scene / OBJ / weight file malformed               */
+    PTD_ERR_CUDA = -4,     /* CUDA runtime error or no device                   */
+    PTD_ERR_UNSUPPORTED = -5,
+    PTD_ERR_STATE = -6     /* call order (e.g. dump without trace enabled)      */
+};
+
+/* ---- record layouts: byte-identical to Inference/src/sceneStructs.h ------------------------------ */
+typedef struct { float x, y, z; } ptd_vec3;
+typedef struct { ptd_vec3 origin, direction; } ptd_ray;                                   /* :15-18        */
+typedef struct { int type, materialid; ptd_vec3 translation, rotation, scale;
+                 float transform[16], inverseTransform[16], invTranspose[16];             /* column major  */
+                 ptd_vec3 vel; } ptd_geom;                                                /* :20-30, 248 B */
+typedef struct { ptd_vec3 v[3]; ptd_vec3 n[3]; int materialid; } ptd_face;                /* :40-44,  76 B */
+typedef struct { ptd_vec3 color; float specular_exponent; ptd_vec3 specular_color;
+                 float hasReflective, hasRefractive, indexOfRefraction, emittance; } ptd_material; /* :46-56, 44 B */
+typedef struct { int res_x, res_y; ptd_vec3 position, lookAt, view, up, right;
+                 float fov_x, fov_y, pixelLength_x, pixelLength_y; } ptd_camera;          /* :58-67,  84 B */
+typedef struct { ptd_ray ray; ptd_vec3 color; int pixelIndex, remainingBounces; } ptd_path_segment; /* :77-82, 44 B */
+typedef struct { ptd_vec3 lb, ub; } ptd_aabb;                                             /* :84-87,  24 B */
+typedef struct { float t; ptd_vec3 surfaceNormal; int materialId; unsigned char is_inside, pad[3];
+                 ptd_vec3 intersect; } ptd_intersection;                                  /* :91-97,  36 B */
+enum { PTD_SPHERE = 0, PTD_CUBE = 1 };                                                    /* :10-13        */
+
+typedef struct ptd_scene ptd_scene;
+typedef struct ptd_pt ptd_pt;
+typedef struct ptd_dn ptd_dn;
+
+const char* ptd_last_error(void);          /* thread-local message of the last failing call */
+int ptd_version(void);
+int ptd_sizeof(int which);                 /* 0 path, 1 intersection, 2 geom, 3 face, 4 material, 5 camera, 6 aabb */
+int ptd_device_count(void);                /* 0 when no CUDA device / driver */
+
+/* ---- scene (replaces `new Scene(file)`, scene.cpp:11-42; same text grammar, OBJ mesh ingest) ----- */
+ptd_status ptd_scene_load(const char* scene_txt_path, ptd_scene** out);
+/* Build a scene from caller arrays (the exact sceneStructs.h records); arrays are copied. */
+ptd_status ptd_scene_from_arrays(int ngeoms, const ptd_geom* geoms, int nmaterials, const ptd_material* materials,
+                                 int nfaces, const ptd_face* faces, const ptd_aabb* mesh_box, const ptd_camera* camera,
+                                 int trace_depth, int iterations, ptd_scene** out);
+void ptd_scene_free(ptd_scene*);
+ptd_status ptd_scene_counts(const ptd_scene*, int out[5]);   /* geoms, materials, faces, traceDepth, iterations */
+const ptd_geom* ptd_scene_geoms(const ptd_scene*);
+const ptd_material* ptd_scene_materials(const ptd_scene*);
+const ptd_face* ptd_scene_faces(const ptd_scene*);
+const ptd_aabb* ptd_scene_mesh_box(const ptd_scene*);
+ptd_camera* ptd_scene_camera(ptd_scene*);                    /* mutable, like scene->state.camera */
+ptd_status ptd_scene_set_resolution(ptd_scene*, int width, int height);   /* re-derives fov.x / pixelLength (scene.cpp:142-150) */
+ptd_status ptd_scene_set_depth(ptd_scene*, int trace_depth);
+
+/* Orbit camera of the frame loop: main.cpp:66-78 (parameters) and main.cpp:126-138 (rebuild). */
+ptd_status ptd_camera_orbit_params(const ptd_camera*, float* zoom, float* phi, float* theta);
+ptd_status ptd_camera_orbit(ptd_camera*, float zoom, float phi, float theta);
+
+/* ---- HP-1 path tracer (replaces pathtraceInit / pathtrace / pathtraceFree) ----------------------- */
+enum {
+    PTD_PT_SORT_MATERIAL = 1u,    /* SORT_MATERIAL true  (pathtrace.cu:21, :508-510); default off as in the reference */
+    PTD_PT_TRACE = 2u,            /* keep per-bounce PathSegment / ShadeableIntersection arrays for ptd_pt_dump_*     */
+    PTD_PT_NO_BVH = 4u,           /* brute-force every face like the reference (pathtrace.cu:258-269); test aid        */
+    PTD_PT_KEEP_TERMINATED = 8u   /* also lay out terminated segments as thrust::partition leaves them (final dump)    */
+};
+/* Uploads the scene once (the reference re-uploads every frame, main.cpp:143-146) and builds the BVH. */
+ptd_status ptd_pt_create(const ptd_scene*, int device, unsigned flags, ptd_pt** out);
+void ptd_pt_destroy(ptd_pt*);
+/* One 1-spp iteration == pathtrace(pbo, frame, iter) (pathtrace.cu:422-528) for camera `cam` (NULL = the scene's).
+ * Writes the 10-plane fp32 G-buffer [10][H][W] (pathtrace.cu:81-94,295-304,379-387; x-mirrored like the
+ * reference) to device memory.  iter == 1 starts a new accumulation (what pathtraceInit's memsets do). Asynchronous. */
+ptd_status ptd_pt_render(ptd_pt*, const ptd_camera* cam, int iter, float* gbuffer_dev, void* stream);
+/* Same + blocking copy into the caller's host_tensor: the reference's pathtrace.cu:525 contract. */
+ptd_status ptd_pt_render_host(ptd_pt*, const ptd_camera* cam, int iter, float* host_tensor);
+/* RGBA8 view of image/iter (sendImageToPBO, pathtrace.cu:59-79) of the last render, device pointer. */
+ptd_status ptd_pt_export_rgba8(ptd_pt*, int iter, unsigned char* pbo_dev, void* stream);
+/* Introspection / parity taps (blocking). live_counts: paths entering each bounce (trace_depth ints). */
+ptd_status ptd_pt_live_counts(ptd_pt*, int* live_counts, int capacity, int* bounces_run);
+ptd_status ptd_pt_dump_paths(ptd_pt*, int bounce, ptd_path_segment* host, int capacity, int* n);          /* needs PTD_PT_TRACE */
+ptd_status ptd_pt_dump_intersections(ptd_pt*, int bounce, ptd_intersection* host, int capacity, int* n);  /* needs PTD_PT_TRACE */
+ptd_status ptd_pt_dump_final_paths(ptd_pt*, ptd_path_segment* host, int capacity);    /* needs PTD_PT_KEEP_TERMINATED */
+ptd_status ptd_pt_dump_image(ptd_pt*, float* host_rgb /* [P][3] */);
+ptd_status ptd_pt_bvh_stats(const ptd_pt*, int* nodes, int* leaves, int* max_leaf, int* max_depth);
+
+/* ---- HP-2 recurrent denoising autoencoder (replaces network_prediction_faster_version) ----------- */
+enum {
+    PTD_DN_FP32 = 0u,             /* fp32 FFMA convolutions (strict-parity path)                                   */
+    PTD_DN_TF32 = 1u              /* tcgen05 kind::tf32 tensor-core convolutions, fp32 accumulate in TMEM (default of the CLI) */
+};
+/* weights_path: "PTDW" flat dump of the model's state_dict (ai_path_tracer_denoiser_b200/weights.py).
+ * H, W: frame size (any; zero-padded bottom/right to a multiple of 32 internally, output cropped). */
+ptd_status ptd_dn_create(const char* weights_path, int H, int W, int device, unsigned flags, ptd_dn** out);
+void ptd_dn_destroy(ptd_dn*);
+/* forward(x, j): gbuffer_dev [10][H][W] fp32 planar -> rgb_dev [3][H][W] fp32 planar.  reset_hidden != 0 is
+ * j == 0 (recurrent_autoencoder_model.py:121-128: hidden states zeroed), else the state of the previous call is used. */
+ptd_status ptd_dn_forward(ptd_dn*, const float* gbuffer_dev, float* rgb_dev, int reset_hidden, void* stream);
+/* Host-pointer form == the reference call site (main.cpp:101-118: H2D of 40*P bytes, forward, D2H of 12*P). Blocking. */
+ptd_status ptd_dn_forward_host(ptd_dn*, const float* gbuffer_host, float* rgb_host, int reset_hidden);
+/* Row-strip mode for multi-GPU tiling: this handle owns padded rows [row0, row0+rows) of a
+ * Hp-row frame; rows multiple of 32.  Halo rows are exchanged by the caller-provided callback once per conv. */
+typedef void (*ptd_halo_fn)(void* user, int layer, float* send_up_dev, float* send_down_dev,
+                            float* recv_up_dev, float* recv_down_dev, size_t bytes, void* stream);
+ptd_status ptd_dn_create_strip(const char* weights_path, int H, int W, int row0, int rows, int device, unsigned flags,
+                               ptd_halo_fn halo, void* user, ptd_dn** out);
+ptd_status ptd_dn_padded_size(const ptd_dn*, int* Hp, int* Wp);
+/* Parity tap: copy a hidden state (level 0..5, NCHW fp32, padded size) to host. */
+ptd_status ptd_dn_dump_hidden(ptd_dn*, int level, float* host, size_t capacity_floats, int* C, int* H, int* W);
+/* Number of kernels one forward launches (for bench.py's gpu_launches). */
+int ptd_dn_launches_per_forward(const ptd_dn*);
+int ptd_pt_launches_last_render(const ptd_pt*);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PTD_H */

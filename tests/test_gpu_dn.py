@@ -1,0 +1,103 @@
+"""GPU parity tests of the denoiser hot path (HP-2), through the C ABI (libptd.so).
+
+Checkers: tests/golden/dn_*.npz (outputs of the reference's own AutoEncoder, tools/make_golden_dn.py) and
+oracle/dn_oracle.py (pinned against the same golden files) on further seeded inputs.
+Stated tolerances (outputs are O(1)):
+  PTD_DN_FP32  (FFMA convs)                 max-abs <= 1e-4, rel-L2 <= 1e-5   - fp32 re-association only
+  PTD_DN_TF32  (tcgen05 kind::tf32 convs)   max-abs <= 2e-2, rel-L2 <= 5e-3   - 10-bit-mantissa operands, fp32 accumulate
+                                            (what libtorch itself does for convs on Ampere+ with cudnn.allow_tf32 = True)
+"""
+import os
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN
+
+pytestmark = pytest.mark.gpu
+
+TOL = {"fp32": (1e-4, 1e-5), "tf32": (2e-2, 5e-3)}
+
+
+def _capi():
+    from ai_path_tracer_denoiser_b200 import capi
+    if capi.device_count() < 1:
+        pytest.fail("no CUDA device visible to libptd.so - the product has no CPU fallback")
+    return capi
+
+
+@pytest.fixture(scope="module")
+def wfile(tmp_path_factory):
+    from ai_path_tracer_denoiser_b200 import weights
+    return weights.save_weights(weights.synthetic_state_dict(1234), str(tmp_path_factory.mktemp("w") / "w.ptdw"))
+
+
+def _err(y, ref):
+    d = y.astype(np.float64) - ref.astype(np.float64)
+    return np.abs(d).max(), np.sqrt((d * d).sum() / max((ref.astype(np.float64) ** 2).sum(), 1e-30))
+
+
+def _mode(capi, mode):
+    return capi.DN_FP32 if mode == "fp32" else capi.DN_TF32
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("name", ["dn_64x96", "dn_32x32"])
+def test_matches_reference_model_golden(name, mode, wfile):
+    capi = _capi()
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    _, H, W = g["x"][0].shape
+    dn = capi.Denoiser(wfile, H, W, flags=_mode(capi, mode))
+    for j in range(len(g["x"])):
+        y = dn.forward_host(g["x"][j], reset=(j == 0))          # forward(x, j): hidden carried for j > 0
+        ma, rl = _err(y, g["y"][j])
+        assert ma <= TOL[mode][0] and rl <= TOL[mode][1], (j, ma, rl)
+    hid = dn.dump_hidden(2)
+    ma, rl = _err(hid, g["hidden3"][0] if g["hidden3"].ndim == 4 else g["hidden3"])
+    assert ma <= 4 * TOL[mode][0], ma
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_pad_crop_recurrence_and_reset_vs_oracle(mode, wfile):
+    """Non-/32 frame (zero pad bottom/right, crop; decision D3), 5-frame recurrence, then a reset."""
+    capi = _capi()
+    from ai_path_tracer_denoiser_b200 import weights
+    from oracle.dn_oracle import DenoiserOracle, synthetic_gbuffer
+    H, W = 72, 100
+    O = DenoiserOracle(weights.synthetic_state_dict(1234))
+    dn = capi.Denoiser(wfile, H, W, flags=_mode(capi, mode))
+    assert dn.padded_size() == (96, 128)
+    first = None
+    for j in range(5):
+        x = synthetic_gbuffer(H, W, seed=11, frame=j)
+        ref = O.forward(x, reset=(j == 0))
+        y = dn.forward_host(x, reset=(j == 0))
+        assert y.shape == (3, H, W)
+        ma, rl = _err(y, ref)
+        assert ma <= TOL[mode][0] and rl <= TOL[mode][1], (j, ma, rl)      # no growth through the recurrence
+        if j == 0:
+            first = y
+    again = dn.forward_host(synthetic_gbuffer(H, W, seed=11, frame=0), reset=True)
+    assert again.tobytes() == first.tobytes()                                # reset really zeroes the six hidden states
+    for lvl in range(6):
+        ma, _ = _err(dn.dump_hidden(lvl), O.hidden[lvl][0].numpy())
+        assert ma <= 4 * TOL[mode][0], (lvl, ma)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_full_size_720p_properties(mode, wfile):
+    """BASELINE size (720p -> 736x1280 padded): finite, deterministic, translation-consistent in the interior
+    (a frame shifted by 32 px gives the shifted output away from the borders: the net is fully convolutional)."""
+    capi = _capi()
+    from oracle.dn_oracle import synthetic_gbuffer
+    H, W = 720, 1280
+    dn = capi.Denoiser(wfile, H, W, flags=_mode(capi, mode))
+    x = synthetic_gbuffer(H, W, seed=3)
+    y1 = dn.forward_host(x, reset=True)
+    y2 = dn.forward_host(x, reset=True)
+    assert np.isfinite(y1).all() and y1.tobytes() == y2.tobytes()
+    xs = np.zeros_like(x)
+    xs[:, :, 32:] = x[:, :, :-32]
+    ys = dn.forward_host(xs, reset=True)
+    a, b = ys[:, 300:420, 32 + 300:32 + 900], y1[:, 300:420, 300:900]
+    assert np.abs(a - b).max() <= 2 * TOL[mode][0]
