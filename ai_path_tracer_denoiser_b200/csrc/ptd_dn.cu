@@ -143,7 +143,7 @@ __global__ void maxpool2_nhwc(const float* __restrict__ in, float* __restrict__ 
                                                     fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
 }
 // planar G-buffer [10][H][W] rows [row0, row0+rows) -> NHWC16 [rows_p][Wp][16], zero padded (decision D3)
-__global__ void pack_gbuffer(const float* __restrict__ g, int H, int W, int Hp, int Wp, float* __restrict__ out) {
+__global__ void pack_gbuffer(const float* __restrict__ g, int H, int W, int Hp, int Wp, float* __restrict__ out, int round_tf32) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= (size_t)Hp * Wp) return;
     const int x = (int)(i % Wp), y = (int)(i / Wp);
@@ -153,6 +153,10 @@ __global__ void pack_gbuffer(const float* __restrict__ g, int H, int W, int Hp, 
     if (x < W && y < H) {
 #pragma unroll
         for (int c = 0; c < 10; ++c) v[c] = g[(size_t)c * H * W + (size_t)y * W + x];
+        if (round_tf32) {
+#pragma unroll
+            for (int c = 0; c < 10; ++c) v[c] = tc::round_tf32(v[c]);
+        }
     }
     float4* d = reinterpret_cast<float4*>(out + i * 16);
     d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
@@ -344,6 +348,7 @@ extern "C" ptd_status ptd_dn_create(const char* weights_path, int H, int W, int 
             d.H = L.H; d.W = L.W; d.coutp = L.coutp; d.out = L.out; d.lrelu_first = s.lrelu_first;
             d.scale = L.d_scale; d.shift = L.d_shift; d.bias = L.d_bias;
             d.pool_out = (s.kind == DN_L2B && lvl < 5) ? pooled[lvl] : nullptr;
+            d.round_out = li + 1 < specs.size();
             rc = tc_plan_create(d, w9, cinp, L.tc, h->allocs);
             if (rc != PTD_OK) return fail(rc);
         }
@@ -370,7 +375,7 @@ extern "C" ptd_status ptd_dn_forward(ptd_dn* h, const float* gbuf, float* rgb, i
         for (int l = 0; l < 6; ++l) CUDA_TRY(cudaMemsetAsync(h->hidden[l], 0, h->hidden_bytes[l], st));
     {
         const size_t n = (size_t)h->Hp * h->Wp;
-        pack_gbuffer<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gbuf, h->H, h->W, h->Hp, h->Wp, h->d_in16);
+        pack_gbuffer<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gbuf, h->H, h->W, h->Hp, h->Wp, h->d_in16, h->flags == PTD_DN_TF32);
         ++launches;
     }
     size_t pool_i = 0;

@@ -159,8 +159,8 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_bounce(const PtKernelParams p) {
             color = V(1.0f, 1.0f, 1.0f);
             float jx = rng_uniform(rng, -0.5f, 0.5f);
             float jy = rng_uniform(rng, -0.5f, 0.5f);
-            v3 a = muls(muls(p.cam.right, p.cam.pixelLength_x), ((float)x - (float)p.cam.res_x * 0.5f + jx));
-            v3 b = muls(muls(p.cam.up, p.cam.pixelLength_y), ((float)y - (float)p.cam.res_y * 0.5f + jy));
+            v3 a = muls(muls(p.cam.right, p.cam.pixelLength_x), fadd(ffma((float)p.cam.res_x, -0.5f, (float)x), jx));
+            v3 b = muls(muls(p.cam.up, p.cam.pixelLength_y), fadd(ffma((float)p.cam.res_y, -0.5f, (float)y), jy));
             ray.d = normalize(sub(sub(p.cam.view, a), b));
             pixelIndex = idx;
             rb = p.trace_depth;
@@ -271,13 +271,12 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_bounce(const PtKernelParams p) {
             // finalGather (:393-402) + copy_data (:81-94): every segment terminates exactly once per iteration, so its
             // throughput is accumulated and the radiance planes are emitted here instead of in two extra passes over P.
             float* img = p.image + (size_t)pixelIndex * 3;
-            v3 acc = color;
-            if (p.iter != 1) acc = add(V(img[0], img[1], img[2]), color);
+            v3 acc = add(p.iter != 1 ? V(img[0], img[1], img[2]) : V(0.f, 0.f, 0.f), color);
             img[0] = acc.x; img[1] = acc.y; img[2] = acc.z;
             const float fi = (float)p.iter;
-            p.gbuf[mirrored] = acc.x / fi;
-            p.gbuf[(size_t)p.P + mirrored] = acc.y / fi;
-            p.gbuf[(size_t)p.P * 2 + mirrored] = acc.z / fi;
+            p.gbuf[mirrored] = __fdiv_rn(acc.x, fi);
+            p.gbuf[(size_t)p.P + mirrored] = __fdiv_rn(acc.y, fi);
+            p.gbuf[(size_t)p.P * 2 + mirrored] = __fdiv_rn(acc.z, fi);
         }
     }
 

@@ -77,11 +77,11 @@ def test_pad_crop_recurrence_and_reset_vs_oracle(mode, wfile):
         assert ma <= TOL[mode][0] and rl <= TOL[mode][1], (j, ma, rl)      # no growth through the recurrence
         if j == 0:
             first = y
-    again = dn.forward_host(synthetic_gbuffer(H, W, seed=11, frame=0), reset=True)
-    assert again.tobytes() == first.tobytes()                                # reset really zeroes the six hidden states
     for lvl in range(6):
         ma, _ = _err(dn.dump_hidden(lvl), O.hidden[lvl][0].numpy())
         assert ma <= 4 * TOL[mode][0], (lvl, ma)
+    again = dn.forward_host(synthetic_gbuffer(H, W, seed=11, frame=0), reset=True)
+    assert again.tobytes() == first.tobytes()                                # reset really zeroes the six hidden states
 
 
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
