@@ -33,7 +33,8 @@ ptd_scene_set_resolution ptd_scene_set_depth ptd_camera_orbit_params ptd_camera_
 ptd_pt_render ptd_pt_render_host ptd_pt_export_rgba8 ptd_pt_live_counts ptd_pt_dump_paths ptd_pt_dump_intersections
 ptd_pt_dump_final_paths ptd_pt_dump_image ptd_pt_bvh_stats ptd_dn_create ptd_dn_destroy ptd_dn_forward
 ptd_dn_forward_host ptd_dn_create_strip ptd_dn_padded_size ptd_dn_dump_hidden ptd_dn_launches_per_forward
-ptd_pt_launches_last_render""".split()
+ptd_pt_launches_last_render ptd_dn_profile ptd_dn_launch_times ptd_dn_launch_name ptd_pt_profile
+ptd_pt_launch_times""".split()
 
 
 class PtdError(RuntimeError):
@@ -85,6 +86,12 @@ def lib():
         L.ptd_dn_padded_size.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ptd_dn_dump_hidden.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ptd_dn_launches_per_forward.argtypes = [C.c_void_p]
+        L.ptd_dn_profile.argtypes = [C.c_void_p, C.c_int]
+        L.ptd_dn_launch_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.ptd_dn_launch_name.argtypes = [C.c_void_p, C.c_int]
+        L.ptd_dn_launch_name.restype = C.c_char_p
+        L.ptd_pt_profile.argtypes = [C.c_void_p, C.c_int]
+        L.ptd_pt_launch_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
         _lib = L
     return _lib
 
@@ -247,6 +254,15 @@ class PathTracer:
     def launches(self):
         return lib().ptd_pt_launches_last_render(self.h)
 
+    def profile(self, on=True):
+        check(lib().ptd_pt_profile(self.h, 1 if on else 0))
+
+    def launch_times(self):
+        ms = np.zeros(4096, np.float32)
+        n = C.c_int()
+        check(lib().ptd_pt_launch_times(self.h, ms.ctypes.data, ms.size, C.byref(n)))
+        return ms[:n.value].copy()
+
 
 class Denoiser:
     """network_prediction_faster_version (main.cpp:101-118) / AutoEncoder.forward(x, j) behind ptd_dn_*."""
@@ -286,3 +302,13 @@ class Denoiser:
 
     def launches(self):
         return lib().ptd_dn_launches_per_forward(self.h)
+
+    def profile(self, on=True):
+        check(lib().ptd_dn_profile(self.h, 1 if on else 0))
+
+    def launch_times(self):
+        """[(name, ms)] of the last profiled forward, in launch order."""
+        ms = np.zeros(256, np.float32)
+        n = C.c_int()
+        check(lib().ptd_dn_launch_times(self.h, ms.ctypes.data, ms.size, C.byref(n)))
+        return [(lib().ptd_dn_launch_name(self.h, i).decode(), float(ms[i])) for i in range(n.value)]

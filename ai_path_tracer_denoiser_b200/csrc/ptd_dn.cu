@@ -225,6 +225,10 @@ struct ptd_dn {
     std::vector<Pool> pools;        // pools[k] follows layer 3k+2
     float* d_final = nullptr;
     int launches = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;          // events[i], events[i+1] bracket launch i
+    std::vector<std::string> launch_names;
+    int timed_launches = 0;
 };
 
 extern "C" void ptd_dn_destroy(ptd_dn* h) {
@@ -232,6 +236,7 @@ extern "C" void ptd_dn_destroy(ptd_dn* h) {
     cudaSetDevice(h->device);
     for (auto& L : h->layers) tc_plan_destroy(L.tc);
     for (void* p : h->allocs) cudaFree(p);
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     delete h;
 }
 
@@ -371,12 +376,22 @@ extern "C" ptd_status ptd_dn_forward(ptd_dn* h, const float* gbuf, float* rgb, i
     cudaStream_t st = (cudaStream_t)stream_;
     CUDA_TRY(cudaSetDevice(h->device));
     int launches = 0;
+    int nmark = 0;
+    if (h->profiling) h->launch_names.clear();
+    auto mark = [&](const char* name) {                                 // event after the launch just issued (and one before the first)
+        if (!h->profiling) return;
+        if ((int)h->events.size() <= nmark) { cudaEvent_t e; cudaEventCreate(&e); h->events.push_back(e); }
+        cudaEventRecord(h->events[nmark++], st);
+        if (name) h->launch_names.push_back(name);
+    };
     if (reset_hidden)                                                   // forward(x, j == 0): model.py:121-128
         for (int l = 0; l < 6; ++l) CUDA_TRY(cudaMemsetAsync(h->hidden[l], 0, h->hidden_bytes[l], st));
     {
         const size_t n = (size_t)h->Hp * h->Wp;
+        mark(nullptr);
         pack_gbuffer<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gbuf, h->H, h->W, h->Hp, h->Wp, h->d_in16, h->flags == PTD_DN_TF32);
         ++launches;
+        mark("pack_gbuffer");
     }
     size_t pool_i = 0;
     for (size_t li = 0; li < h->layers.size(); ++li) {
@@ -394,12 +409,14 @@ extern "C" ptd_status ptd_dn_forward(ptd_dn* h, const float* gbuf, float* rgb, i
             conv3x3_fp32<<<grid, 128, 0, st>>>(a);
             ++launches;
         }
+        mark(L.spec.name.c_str());
         if (L.spec.kind == DN_L2B && L.spec.level < 5) {
             const ptd_dn::Pool& p = h->pools[pool_i++];
             if (!pooled_in_epilogue) {
                 const size_t n = (size_t)p.Ho * p.Wo * (p.cp / 4);
                 maxpool2_nhwc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.in, p.out, p.Ho, p.Wo, p.cp);
                 ++launches;
+                mark("maxpool2");
             }
         }
     }
@@ -407,8 +424,10 @@ extern "C" ptd_status ptd_dn_forward(ptd_dn* h, const float* gbuf, float* rgb, i
         const size_t n = (size_t)h->H * h->W;
         unpack_rgb<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->d_final, h->H, h->W, h->Wp, rgb);
         ++launches;
+        mark("unpack_rgb");
     }
     h->launches = launches;
+    if (h->profiling) h->timed_launches = nmark - 1;
     CUDA_TRY(cudaGetLastError());
     return PTD_OK;
 }
@@ -449,3 +468,22 @@ extern "C" ptd_status ptd_dn_dump_hidden(ptd_dn* h, int level, float* host, size
     return PTD_OK;
 }
 extern "C" int ptd_dn_launches_per_forward(const ptd_dn* h) { return h ? h->launches : 0; }
+extern "C" ptd_status ptd_dn_profile(ptd_dn* h, int enable) {
+    if (!h) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_profile: null handle");
+    h->profiling = enable != 0;
+    h->timed_launches = 0;
+    return PTD_OK;
+}
+extern "C" ptd_status ptd_dn_launch_times(ptd_dn* h, float* ms, int capacity, int* n) {
+    if (!h || !ms || !n) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_launch_times: null argument");
+    if (h->timed_launches <= 0) PTD_FAIL(PTD_ERR_STATE, "ptd_dn_launch_times: no profiled forward has run");
+    if (capacity < h->timed_launches) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_launch_times: capacity %d < %d", capacity, h->timed_launches);
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventSynchronize(h->events[h->timed_launches]));
+    for (int i = 0; i < h->timed_launches; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], h->events[i], h->events[i + 1]));
+    *n = h->timed_launches;
+    return PTD_OK;
+}
+extern "C" const char* ptd_dn_launch_name(const ptd_dn* h, int i) {
+    return (h && i >= 0 && i < (int)h->launch_names.size()) ? h->launch_names[i].c_str() : "";
+}

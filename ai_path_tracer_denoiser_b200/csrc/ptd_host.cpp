@@ -655,6 +655,41 @@ void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out) {
             stack.push_back(Task{l, t.lo, split, t.depth + 1});
         }
     }
+    // ---- flatten to the 64-byte two-children-per-fetch layout ----
+    {
+        std::vector<int> wide_index(out.nodes.size(), -1);
+        int nw = 0;
+        for (size_t i = 0; i < out.nodes.size(); ++i) if (out.nodes[i].count == 0) wide_index[i] = nw++;
+        auto child_code = [&](int ni) -> int {
+            const PtdBvhNode& c = out.nodes[ni];
+            if (c.count == 0) return wide_index[ni];
+            return ~((c.first << 4) | (c.count - 1));
+        };
+        if (nw == 0) {                      // the whole mesh is one leaf: synthetic root with an unreachable second child
+            PtdBvhWide w;
+            const PtdBvhNode& r = out.nodes[0];
+            w.f[0] = r.bmin[0]; w.f[1] = r.bmax[0]; w.f[2] = r.bmin[1]; w.f[3] = r.bmax[1];
+            w.f[4] = FLT_MAX; w.f[5] = -FLT_MAX; w.f[6] = FLT_MAX; w.f[7] = -FLT_MAX;
+            w.f[8] = r.bmin[2]; w.f[9] = r.bmax[2]; w.f[10] = FLT_MAX; w.f[11] = -FLT_MAX;
+            int c0 = child_code(0);
+            memcpy(&w.f[12], &c0, 4); memcpy(&w.f[13], &c0, 4); w.f[14] = w.f[15] = 0.f;
+            out.wide.push_back(w);
+        } else {
+            out.wide.resize(nw);
+            for (size_t i = 0; i < out.nodes.size(); ++i) {
+                if (out.nodes[i].count != 0) continue;
+                const int l = out.nodes[i].first, r = l + 1;
+                const PtdBvhNode& a = out.nodes[l];
+                const PtdBvhNode& b = out.nodes[r];
+                PtdBvhWide& w = out.wide[wide_index[i]];
+                w.f[0] = a.bmin[0]; w.f[1] = a.bmax[0]; w.f[2] = a.bmin[1]; w.f[3] = a.bmax[1];
+                w.f[4] = b.bmin[0]; w.f[5] = b.bmax[0]; w.f[6] = b.bmin[1]; w.f[7] = b.bmax[1];
+                w.f[8] = a.bmin[2]; w.f[9] = a.bmax[2]; w.f[10] = b.bmin[2]; w.f[11] = b.bmax[2];
+                int c0 = child_code(l), c1 = child_code(r);
+                memcpy(&w.f[12], &c0, 4); memcpy(&w.f[13], &c1, 4); w.f[14] = w.f[15] = 0.f;
+            }
+        }
+    }
     out.tris.resize(order.size());
     for (size_t k = 0; k < order.size(); ++k) {
         const ptd_face& f = faces[order[k]];
@@ -662,5 +697,29 @@ void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out) {
         t.v0[0] = f.v[0].x; t.v0[1] = f.v[0].y; t.v0[2] = f.v[0].z; t.face = order[k];
         t.v1[0] = f.v[1].x; t.v1[1] = f.v[1].y; t.v1[2] = f.v[1].z; t.material = f.materialid;
         t.v2[0] = f.v[2].x; t.v2[1] = f.v[2].y; t.v2[2] = f.v[2].z; t.pad = 0;
+    }
+}
+
+void ptd_geom_bounds(const std::vector<ptd_geom>& geoms, std::vector<ptd_aabb>& out) {
+    out.resize(geoms.size());
+    for (size_t g = 0; g < geoms.size(); ++g) {
+        const float* m = geoms[g].transform;
+        float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+        bool finite = true;
+        for (int k = 0; k < 8; ++k) {           // the unit cube [-.5,.5]^3 contains the radius-.5 sphere too
+            const float x = (k & 1) ? 0.5f : -0.5f, y = (k & 2) ? 0.5f : -0.5f, z = (k & 4) ? 0.5f : -0.5f;
+            for (int a = 0; a < 3; ++a) {
+                const float v = m[a] * x + m[4 + a] * y + m[8 + a] * z + m[12 + a];
+                if (!std::isfinite(v)) finite = false;
+                lo[a] = std::min(lo[a], v); hi[a] = std::max(hi[a], v);
+            }
+        }
+        float ext = 0.f;
+        for (int a = 0; a < 3; ++a) ext = std::max(ext, std::max(hi[a] - lo[a], std::max(fabsf(lo[a]), fabsf(hi[a]))));
+        const float pad = 1e-3f * ext + 1e-4f;   // the exact tests pull hit points back by 1e-4 and round in object space
+        for (int a = 0; a < 3; ++a) { lo[a] -= pad; hi[a] += pad; }
+        if (!finite) { for (int a = 0; a < 3; ++a) { lo[a] = -FLT_MAX; hi[a] = FLT_MAX; } }   // degenerate transform: never cull
+        out[g].lb.x = lo[0]; out[g].lb.y = lo[1]; out[g].lb.z = lo[2];
+        out[g].ub.x = hi[0]; out[g].ub.y = hi[1]; out[g].ub.z = hi[2];
     }
 }

@@ -39,12 +39,20 @@ struct PtdBvhTri {
     float v1[3]; int material;
     float v2[3]; int pad;
 };
+// Traversal layout (64 B per INTERIOR node, the classic while-while kernel layout): both children's boxes in one fetch.
+//   n0 = (c0.lo.x, c0.hi.x, c0.lo.y, c0.hi.y)   n1 = (c1.lo.x, c1.hi.x, c1.lo.y, c1.hi.y)
+//   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   n3 = (child0, child1, -, -) as ints
+// child >= 0: index of an interior node; child < 0: leaf, ~child = (first << 4) | (count - 1) into the leaf-ordered triangles.
+struct PtdBvhWide { float f[16]; };
 struct PtdBvh {
     std::vector<PtdBvhNode> nodes;
+    std::vector<PtdBvhWide> wide;
     std::vector<PtdBvhTri> tris;
     int leaves = 0, max_leaf = 0, max_depth = 0;
 };
 void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out);
+// Conservative (padded) world-space boxes of the cube / sphere geoms: a ray that misses one cannot hit the geom.
+void ptd_geom_bounds(const std::vector<ptd_geom>& geoms, std::vector<ptd_aabb>& out);
 
 // camera helpers shared with the CLI
 void ptd_camera_derive(ptd_camera& cam, float fovy_deg);

@@ -28,7 +28,7 @@
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ptd_set_error("%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return PTD_ERR_CUDA; } } while (0)
 
 struct PtKernelParams {
-    const ptd_geom* geoms; int ngeoms; int geoms_in_smem;
+    const ptd_geom* geoms; const ptd_aabb* geom_bounds; int ngeoms; int geoms_in_smem;
     const ptd_material* materials; int nmaterials;
     const ptd_face* faces; int nfaces;
     const float4* nodes; const float4* tris; int use_bvh;
@@ -47,16 +47,6 @@ struct PtKernelParams {
 using namespace ptm;
 
 // ---- mesh traversal -------------------------------------------------------------------------------------------
-// Slab test against a (padded) node box; returns entry distance or +inf when missed / beyond t_best.
-__device__ __forceinline__ float node_entry(const float4 lo, const float4 hi, const v3 o, const v3 inv, float t_best) {
-    float tx0 = (lo.x - o.x) * inv.x, tx1 = (hi.x - o.x) * inv.x;
-    float ty0 = (lo.y - o.y) * inv.y, ty1 = (hi.y - o.y) * inv.y;
-    float tz0 = (lo.z - o.z) * inv.z, tz1 = (hi.z - o.z) * inv.z;
-    float tn = fmaxf(fmaxf(fminf(tx0, tx1), fminf(ty0, ty1)), fmaxf(fminf(tz0, tz1), 0.0f));
-    float tf = fminf(fminf(fmaxf(tx0, tx1), fmaxf(ty0, ty1)), fmaxf(tz0, tz1));
-    return (tn <= tf && tn <= t_best) ? tn : __int_as_float(0x7f800000);
-}
-
 // Nearest face hit with the reference's semantics: candidates are accepted in ascending face order with a strict
 // `t_min > t` (pathtrace.cu:259-268), i.e. minimum t and, among equal t, the lowest face index; a geom hit with the
 // same t (best_face < 0) is never displaced.
@@ -66,52 +56,83 @@ __device__ __forceinline__ void consider_face(float t, int face, float bx, float
     }
 }
 
-__device__ __noinline__ void traverse_bvh(const float4* __restrict__ nodes, const float4* __restrict__ tris, const Ray ray,
-                                          float& t_min, int& best_face, float& bbx, float& bby, bool& hit_face) {
-    const v3 inv = V(1.0f / ray.d.x, 1.0f / ray.d.y, 1.0f / ray.d.z);
+// "while-while" traversal with a postponed leaf (Aila & Laine): all lanes of a warp walk interior nodes until every lane holds
+// a leaf, then all lanes run triangle tests, so the two divergent code paths stay converged.  One 64-byte fetch gives both
+// children's (padded) boxes.  The triangle test itself is the reference's exact expression tree; the BVH only decides WHICH
+// faces are tested, and subtrees are skipped only when their entry distance is strictly beyond the best t so far.
+#define PT_SENTINEL 0x76543210
+__device__ __forceinline__ void traverse_bvh(const float4* __restrict__ nodes, const float4* __restrict__ tris, const Ray ray,
+                                             float& t_min, int& best_face, float& bbx, float& bby, bool& hit_face) {
+    const float ooeps = 1e-30f;
+    const float idx = 1.0f / (fabsf(ray.d.x) > ooeps ? ray.d.x : copysignf(ooeps, ray.d.x));
+    const float idy = 1.0f / (fabsf(ray.d.y) > ooeps ? ray.d.y : copysignf(ooeps, ray.d.y));
+    const float idz = 1.0f / (fabsf(ray.d.z) > ooeps ? ray.d.z : copysignf(ooeps, ray.d.z));
+    const float oodx = ray.o.x * idx, oody = ray.o.y * idy, oodz = ray.o.z * idz;
     int stack[PT_STACK];
+    stack[0] = PT_SENTINEL;
     int sp = 0;
-    int node = 0;
-    {
-        float4 lo = __ldg(&nodes[0]), hi = __ldg(&nodes[1]);
-        if (node_entry(lo, hi, ray.o, inv, t_min) == __int_as_float(0x7f800000)) return;
-    }
-    for (;;) {
-        const float4 lo = __ldg(&nodes[2 * node]), hi = __ldg(&nodes[2 * node + 1]);
-        const int first = __float_as_int(lo.w), count = __float_as_int(hi.w);
-        if (count > 0) {
+    int node = 0, leaf = 0;
+    while (node != PT_SENTINEL) {
+        bool searching = true;
+        while (node >= 0 && node != PT_SENTINEL) {
+            const float4 n0 = __ldg(&nodes[4 * node]), n1 = __ldg(&nodes[4 * node + 1]), n2 = __ldg(&nodes[4 * node + 2]);
+            const float4 cn = __ldg(&nodes[4 * node + 3]);
+            // slabs; the 1e-5 relative slack keeps the (already padded) boxes conservative against the rounding of these products
+            const float c0lox = n0.x * idx - oodx, c0hix = n0.y * idx - oodx, c0loy = n0.z * idy - oody, c0hiy = n0.w * idy - oody;
+            const float c0loz = n2.x * idz - oodz, c0hiz = n2.y * idz - oodz;
+            const float c1lox = n1.x * idx - oodx, c1hix = n1.y * idx - oodx, c1loy = n1.z * idy - oody, c1hiy = n1.w * idy - oody;
+            const float c1loz = n2.z * idz - oodz, c1hiz = n2.w * idz - oodz;
+            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
+            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fmaxf(c0loz, c0hiz));
+            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
+            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fmaxf(c1loz, c1hiz));
+            const float tlim = t_min * 1.00001f;
+            const bool h0 = c0min * 0.99999f <= c0max * 1.00001f && c0min * 0.99999f <= tlim;
+            const bool h1 = c1min * 0.99999f <= c1max * 1.00001f && c1min * 0.99999f <= tlim;
+            const int child0 = __float_as_int(cn.x), child1 = __float_as_int(cn.y);
+            if (!h0 && !h1) {
+                node = stack[sp--];
+            } else {
+                node = h0 ? child0 : child1;
+                if (h0 && h1) {
+                    int other = child1;
+                    if (c1min < c0min) { other = node; node = child1; }
+                    stack[++sp] = other;
+                }
+            }
+            if (node < 0 && leaf >= 0) {            // first leaf found: postpone it and keep walking
+                searching = false;
+                leaf = node;
+                node = stack[sp--];
+            }
+            if (!__any_sync(__activemask(), searching)) break;
+        }
+        while (leaf < 0) {
+            const int code = ~leaf, first = code >> 4, count = (code & 15) + 1;
             for (int i = 0; i < count; ++i) {
                 const float4 a = __ldg(&tris[3 * (first + i)]), b = __ldg(&tris[3 * (first + i) + 1]), c = __ldg(&tris[3 * (first + i) + 2]);
                 float bx, by;
-                float t = triangleParam(V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), ray, bx, by);
+                const float t = triangleParam(V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), ray, bx, by);
                 consider_face(t, __float_as_int(a.w), bx, by, t_min, best_face, bbx, bby, hit_face);
             }
-        } else {
-            const float4 llo = __ldg(&nodes[2 * first]), lhi = __ldg(&nodes[2 * first + 1]);
-            const float4 rlo = __ldg(&nodes[2 * first + 2]), rhi = __ldg(&nodes[2 * first + 3]);
-            const float tl = node_entry(llo, lhi, ray.o, inv, t_min);
-            const float tr = node_entry(rlo, rhi, ray.o, inv, t_min);
-            const float INF = __int_as_float(0x7f800000);
-            if (tl != INF || tr != INF) {
-                if (tl != INF && tr != INF) {
-                    const bool left_first = tl <= tr;
-                    if (sp < PT_STACK) stack[sp++] = left_first ? first + 1 : first;
-                    node = left_first ? first : first + 1;
-                } else {
-                    node = (tl != INF) ? first : first + 1;
-                }
-                continue;
-            }
+            leaf = node;
+            if (node < 0) node = stack[sp--];
         }
-        // pop, skipping subtrees that can no longer contain a nearer (or equal, lower-index) hit
-        bool found = false;
-        while (sp > 0) {
-            node = stack[--sp];
-            const float4 plo = __ldg(&nodes[2 * node]), phi = __ldg(&nodes[2 * node + 1]);
-            if (node_entry(plo, phi, ray.o, inv, t_min) != __int_as_float(0x7f800000)) { found = true; break; }
-        }
-        if (!found) return;
     }
+}
+
+// conservative slab test against a geom's padded world box: false only when the ray certainly misses the geom
+__device__ __forceinline__ bool ray_may_hit_box(const Ray& ray, const ptd_aabb& b) {
+    const float ooeps = 1e-30f;
+    const float idx = 1.0f / (fabsf(ray.d.x) > ooeps ? ray.d.x : copysignf(ooeps, ray.d.x));
+    const float idy = 1.0f / (fabsf(ray.d.y) > ooeps ? ray.d.y : copysignf(ooeps, ray.d.y));
+    const float idz = 1.0f / (fabsf(ray.d.z) > ooeps ? ray.d.z : copysignf(ooeps, ray.d.z));
+    const float x0 = (b.lb.x - ray.o.x) * idx, x1 = (b.ub.x - ray.o.x) * idx;
+    const float y0 = (b.lb.y - ray.o.y) * idy, y1 = (b.ub.y - ray.o.y) * idy;
+    const float z0 = (b.lb.z - ray.o.z) * idz, z1 = (b.ub.z - ray.o.z) * idz;
+    const float tn = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
+    const float tf = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fmaxf(z0, z1));
+    return !(tn * 0.9999f > tf * 1.0001f);          // NaN compares false -> "may hit"
 }
 
 // ---- block-wide helpers -------------------------------------------------------------------------------------------
@@ -138,6 +159,9 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_bounce(const PtKernelParams p) {
         const uint32_t* g = reinterpret_cast<const uint32_t*>(p.geoms);
         uint32_t* d = reinterpret_cast<uint32_t*>(s_geoms);
         for (int i = tid; i < p.ngeoms * 62; i += PT_BLOCK) d[i] = __ldg(&g[i]);
+        const uint32_t* gb = reinterpret_cast<const uint32_t*>(p.geom_bounds);
+        uint32_t* db = reinterpret_cast<uint32_t*>(s_geoms + p.ngeoms);
+        for (int i = tid; i < p.ngeoms * 6; i += PT_BLOCK) db[i] = __ldg(&gb[i]);
     }
     __syncthreads();
     const int tile = s_tile;
@@ -147,6 +171,7 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_bounce(const PtKernelParams p) {
     const int idx = base + tid;
     const bool active = tid < valid;
     const ptd_geom* geoms = p.geoms_in_smem ? s_geoms : p.geoms;
+    const ptd_aabb* gbounds = p.geoms_in_smem ? reinterpret_cast<const ptd_aabb*>(s_geoms + p.ngeoms) : p.geom_bounds;
 
     // ---- 1. this tile's path segments ---------------------------------------------------------------------
     Ray ray; v3 color; int pixelIndex = 0, rb = 0;
@@ -198,6 +223,7 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_bounce(const PtKernelParams p) {
         bool outside = true;
         for (int g = 0; g < p.ngeoms; ++g) {
             const ptd_geom* ge = &geoms[g];
+            if (!ray_may_hit_box(ray, gbounds[g])) continue;                  // a certain miss leaves t, outside untouched in the reference too
             float t = 0.f;
             if (ge->type == PTD_CUBE) t = boxIntersectionTest(ge, ray, tip, tn, outside);
             else if (ge->type == PTD_SPHERE) t = sphereIntersectionTest(ge, ray, tip, tn, outside);
@@ -392,7 +418,7 @@ struct ptd_pt {
     int W = 0, H = 0, P = 0, depth = 0, ngeoms = 0, nmaterials = 0, nfaces = 0, ntiles = 0;
     ptd_camera cam;
     ptd_aabb mesh_box;
-    ptd_geom* d_geoms = nullptr; ptd_material* d_materials = nullptr; ptd_face* d_faces = nullptr;
+    ptd_geom* d_geoms = nullptr; ptd_aabb* d_geom_bounds = nullptr; ptd_material* d_materials = nullptr; ptd_face* d_faces = nullptr;
     float4* d_nodes = nullptr; float4* d_tris = nullptr;
     ptd_path_segment* d_paths[3] = {nullptr, nullptr, nullptr};
     ptd_path_segment* d_dead = nullptr;
@@ -403,6 +429,9 @@ struct ptd_pt {
     ptd_path_segment* d_trace_paths = nullptr; ptd_intersection* d_trace_isx = nullptr;
     int final_buf = 0;
     int launches = 0;
+    bool profiling = false;
+    std::vector<cudaEvent_t> events;
+    int timed_launches = 0;
     int bvh_nodes = 0, bvh_leaves = 0, bvh_max_leaf = 0, bvh_max_depth = 0;
 };
 
@@ -415,10 +444,11 @@ extern "C" int ptd_device_count(void) {
 extern "C" void ptd_pt_destroy(ptd_pt* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_geoms); cudaFree(h->d_materials); cudaFree(h->d_faces); cudaFree(h->d_nodes); cudaFree(h->d_tris);
+    cudaFree(h->d_geoms); cudaFree(h->d_geom_bounds); cudaFree(h->d_materials); cudaFree(h->d_faces); cudaFree(h->d_nodes); cudaFree(h->d_tris);
     for (int i = 0; i < 3; ++i) cudaFree(h->d_paths[i]);
     cudaFree(h->d_dead); cudaFree(h->d_image); cudaFree(h->d_gbuf_own); cudaFree(h->d_ctl); cudaFree(h->d_keys); cudaFree(h->d_hist);
     cudaFree(h->d_trace_paths); cudaFree(h->d_trace_isx);
+    for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     delete h;
 }
 
@@ -443,6 +473,12 @@ extern "C" ptd_status ptd_pt_create(const ptd_scene* sc, int device, unsigned fl
 #define UPLOAD(dst, src, bytes) do { if ((bytes) && cudaMemcpy((dst), (src), (bytes), cudaMemcpyHostToDevice) != cudaSuccess) { ptd_set_error("ptd_pt_create: upload failed: %s", cudaGetErrorString(cudaGetLastError())); ptd_pt_destroy(h); return PTD_ERR_CUDA; } } while (0)
     ALLOC(h->d_geoms, sizeof(ptd_geom) * sc->geoms.size());
     UPLOAD(h->d_geoms, sc->geoms.data(), sizeof(ptd_geom) * sc->geoms.size());
+    {
+        std::vector<ptd_aabb> gb;
+        ptd_geom_bounds(sc->geoms, gb);
+        ALLOC(h->d_geom_bounds, sizeof(ptd_aabb) * gb.size());
+        UPLOAD(h->d_geom_bounds, gb.data(), sizeof(ptd_aabb) * gb.size());
+    }
     ALLOC(h->d_materials, sizeof(ptd_material) * sc->materials.size());
     UPLOAD(h->d_materials, sc->materials.data(), sizeof(ptd_material) * sc->materials.size());
     ALLOC(h->d_faces, sizeof(ptd_face) * sc->faces.size());
@@ -452,8 +488,8 @@ extern "C" ptd_status ptd_pt_create(const ptd_scene* sc, int device, unsigned fl
         ptd_build_bvh(sc->faces, bvh);
         h->bvh_nodes = (int)bvh.nodes.size(); h->bvh_leaves = bvh.leaves; h->bvh_max_leaf = bvh.max_leaf; h->bvh_max_depth = bvh.max_depth;
         if (bvh.max_depth > PT_STACK) { ptd_set_error("ptd_pt_create: BVH depth %d exceeds traversal stack %d", bvh.max_depth, PT_STACK); ptd_pt_destroy(h); return PTD_ERR_UNSUPPORTED; }
-        ALLOC(h->d_nodes, sizeof(PtdBvhNode) * bvh.nodes.size());
-        UPLOAD(h->d_nodes, bvh.nodes.data(), sizeof(PtdBvhNode) * bvh.nodes.size());
+        ALLOC(h->d_nodes, sizeof(PtdBvhWide) * bvh.wide.size());
+        UPLOAD(h->d_nodes, bvh.wide.data(), sizeof(PtdBvhWide) * bvh.wide.size());
         ALLOC(h->d_tris, sizeof(PtdBvhTri) * bvh.tris.size());
         UPLOAD(h->d_tris, bvh.tris.data(), sizeof(PtdBvhTri) * bvh.tris.size());
     }
@@ -478,7 +514,7 @@ extern "C" ptd_status ptd_pt_create(const ptd_scene* sc, int device, unsigned fl
     }
 #undef ALLOC
 #undef UPLOAD
-    const size_t smem = PT_BLOCK * PT_WORDS * 4 + sizeof(ptd_geom) * 64;
+    const size_t smem = PT_BLOCK * PT_WORDS * 4 + (sizeof(ptd_geom) + sizeof(ptd_aabb)) * 64;
     cudaFuncSetAttribute(pt_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     cudaFuncSetAttribute(pt_bounce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     CUDA_TRY(cudaDeviceSynchronize());
@@ -497,7 +533,7 @@ extern "C" ptd_status ptd_pt_render(ptd_pt* h, const ptd_camera* cam, int iter, 
     }
     PtKernelParams p;
     memset(&p, 0, sizeof p);
-    p.geoms = h->d_geoms; p.ngeoms = h->ngeoms; p.geoms_in_smem = h->ngeoms <= 64;
+    p.geoms = h->d_geoms; p.geom_bounds = h->d_geom_bounds; p.ngeoms = h->ngeoms; p.geoms_in_smem = h->ngeoms <= 64;
     p.materials = h->d_materials; p.nmaterials = h->nmaterials;
     p.faces = h->d_faces; p.nfaces = h->nfaces;
     p.nodes = h->d_nodes; p.tris = h->d_tris; p.use_bvh = h->d_nodes != nullptr;
@@ -507,10 +543,17 @@ extern "C" ptd_status ptd_pt_render(ptd_pt* h, const ptd_camera* cam, int iter, 
     p.counts = h->d_counts; p.gbuf = gbuf; p.image = h->d_image; p.dead = h->d_dead;
     p.sort_keys = h->d_keys; p.trace_paths = h->d_trace_paths; p.trace_isx = h->d_trace_isx;
     CUDA_TRY(cudaMemsetAsync(h->d_ctl, 0, h->ctl_bytes, st));
-    const size_t smem = PT_BLOCK * PT_WORDS * 4 + (p.geoms_in_smem ? sizeof(ptd_geom) * h->ngeoms : 0);
+    const size_t smem = PT_BLOCK * PT_WORDS * 4 + (p.geoms_in_smem ? (sizeof(ptd_geom) + sizeof(ptd_aabb)) * h->ngeoms : 0);
     const bool sort = (h->flags & PTD_PT_SORT_MATERIAL) != 0;
     int cur = 0;
     h->launches = 0;
+    int nmark = 0;
+    auto mark = [&]() {
+        if (!h->profiling) return;
+        if ((int)h->events.size() <= nmark) { cudaEvent_t e; cudaEventCreate(&e); h->events.push_back(e); }
+        cudaEventRecord(h->events[nmark++], st);
+    };
+    mark();
     for (int b = 0; b < h->depth; ++b) {
         const int nxt = (cur + 1) % (sort ? 3 : 2);
         p.bounce = b;
@@ -520,6 +563,7 @@ extern "C" ptd_status ptd_pt_render(ptd_pt* h, const ptd_camera* cam, int iter, 
         if (b == 0) pt_bounce<true><<<h->ntiles, PT_BLOCK, smem, st>>>(p);
         else pt_bounce<false><<<h->ntiles, PT_BLOCK, smem, st>>>(p);
         h->launches++;
+        mark();
         cur = nxt;
         if (sort && b + 1 < h->depth) {
             const int nb = std::max(h->nmaterials, 1), srt = (cur + 1) % 3;
@@ -531,6 +575,7 @@ extern "C" ptd_status ptd_pt_render(ptd_pt* h, const ptd_camera* cam, int iter, 
         }
     }
     h->final_buf = cur;
+    if (h->profiling) h->timed_launches = nmark - 1;
     CUDA_TRY(cudaGetLastError());
     return PTD_OK;
 }
@@ -611,3 +656,19 @@ extern "C" ptd_status ptd_pt_bvh_stats(const ptd_pt* h, int* nodes, int* leaves,
     return PTD_OK;
 }
 extern "C" int ptd_pt_launches_last_render(const ptd_pt* h) { return h ? h->launches : 0; }
+extern "C" ptd_status ptd_pt_profile(ptd_pt* h, int enable) {
+    if (!h) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_profile: null handle");
+    h->profiling = enable != 0;
+    h->timed_launches = 0;
+    return PTD_OK;
+}
+extern "C" ptd_status ptd_pt_launch_times(ptd_pt* h, float* ms, int capacity, int* n) {
+    if (!h || !ms || !n) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_launch_times: null argument");
+    if (h->timed_launches <= 0) PTD_FAIL(PTD_ERR_STATE, "ptd_pt_launch_times: no profiled render has run");
+    if (capacity < h->timed_launches) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_launch_times: capacity %d < %d", capacity, h->timed_launches);
+    CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaEventSynchronize(h->events[h->timed_launches]));
+    for (int i = 0; i < h->timed_launches; ++i) CUDA_TRY(cudaEventElapsedTime(&ms[i], h->events[i], h->events[i + 1]));
+    *n = h->timed_launches;
+    return PTD_OK;
+}

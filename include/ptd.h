@@ -128,6 +128,14 @@ ptd_status ptd_dn_create_strip(const char* weights_path, int H, int W, int row0,
 ptd_status ptd_dn_padded_size(const ptd_dn*, int* Hp, int* Wp);
 /* Parity tap: copy a hidden state (level 0..5, NCHW fp32, padded size) to host. */
 ptd_status ptd_dn_dump_hidden(ptd_dn*, int level, float* host, size_t capacity_floats, int* C, int* H, int* W);
+/* Per-launch device timing (cudaEvent pairs on the caller's stream around every kernel of the NEXT forward / render).
+ * enable != 0 arms it; the *_times call synchronises and returns milliseconds per launch in launch order
+ * (denoiser: pack, 28 convs [+ pools], unpack - names via ptd_dn_launch_name; path tracer: one entry per bounce kernel). */
+ptd_status ptd_dn_profile(ptd_dn*, int enable);
+ptd_status ptd_dn_launch_times(ptd_dn*, float* ms, int capacity, int* n);
+const char* ptd_dn_launch_name(const ptd_dn*, int index);
+ptd_status ptd_pt_profile(ptd_pt*, int enable);
+ptd_status ptd_pt_launch_times(ptd_pt*, float* ms, int capacity, int* n);
 /* Number of kernels one forward launches (for bench.py's gpu_launches). */
 int ptd_dn_launches_per_forward(const ptd_dn*);
 int ptd_pt_launches_last_render(const ptd_pt*);
