@@ -3,12 +3,14 @@
 // Replaces pathtraceInit / pathtrace / pathtraceFree (Inference/src/pathtrace.cu:96-145, :422-528).
 // Where the reference runs, per bounce, memset + computeIntersections + cudaDeviceSynchronize + shadeMaterial +
 // thrust::partition (temp malloc, 3 kernels, D2H of the count) and after the loop finalGather + copy_data + a
-// 40*P-byte D2H, this file runs ONE fused kernel per bounce and nothing after the loop:
+// 40*P-byte D2H, this file runs TWO kernels per bounce and nothing after the loop:
 //
-//   pt_bounce<FIRST>:  [ray generation at bounce 0 | coalesced smem-staged load of the 44-byte PathSegment tile]
-//                      -> nearest hit over the geoms (shared-memory copy) and the mesh (BVH, tie-break exact)
+//   pt_trace<FIRST>:   [ray generation at bounce 0 | ray of PathSegment idx] -> nearest hit over the geoms (shared-memory copy)
+//                      and the mesh (BVH, tie-break exact) -> 36-byte ShadeableIntersection at slot idx (+ normal/depth planes
+//                      at bounce 0).  Persistent warps, dynamic ray fetch, no block barrier: traversal time per ray varies 10x.
+//   pt_shade<FIRST>:   coalesced smem-staged load of the PathSegment + ShadeableIntersection tile
 //                      -> shade / scatter (same RNG stream: seed = hash(iter, compacted index, remainingBounces))
-//                      -> G-buffer planes written in place (normal/depth/albedo at bounce 0, radiance at termination)
+//                      -> G-buffer planes written in place (albedo at bounce 0, radiance at termination)
 //                      -> stable stream compaction: warp-ballot ranks + block scan + decoupled look-back across tiles,
 //                         survivors staged in shared memory and stored coalesced; the live count stays on the device.
 //
@@ -38,10 +40,12 @@ struct PtKernelParams {
     const ptd_path_segment* src; ptd_path_segment* dst; ptd_path_segment* dead;
     int* counts;                    // counts[b] = live paths entering bounce b
     unsigned long long* status;     // decoupled look-back tile states of this bounce
-    int* ticket;                    // dynamic tile id of this bounce
+    int* ticket;                    // ray counter of this bounce's pt_trace (dynamic fetch)
+    int* ticket2;                   // dynamic tile id of this bounce's pt_shade
+    ptd_intersection* isx;          // ShadeableIntersection[n] exchanged between the two kernels
     float* gbuf; float* image;
     int* sort_keys;
-    ptd_path_segment* trace_paths; ptd_intersection* trace_isx;
+    ptd_path_segment* trace_paths;
 };
 
 using namespace ptm;
@@ -53,71 +57,6 @@ using namespace ptm;
 __device__ __forceinline__ void consider_face(float t, int face, float bx, float by, float& t_min, int& best_face, float& bbx, float& bby, bool& hit_face) {
     if (t > 0.0f && (t_min > t || (t_min == t && hit_face && face < best_face))) {
         t_min = t; best_face = face; bbx = bx; bby = by; hit_face = true;
-    }
-}
-
-// "while-while" traversal with a postponed leaf (Aila & Laine): all lanes of a warp walk interior nodes until every lane holds
-// a leaf, then all lanes run triangle tests, so the two divergent code paths stay converged.  One 64-byte fetch gives both
-// children's (padded) boxes.  The triangle test itself is the reference's exact expression tree; the BVH only decides WHICH
-// faces are tested, and subtrees are skipped only when their entry distance is strictly beyond the best t so far.
-#define PT_SENTINEL 0x76543210
-__device__ __forceinline__ void traverse_bvh(const float4* __restrict__ nodes, const float4* __restrict__ tris, const Ray ray,
-                                             float& t_min, int& best_face, float& bbx, float& bby, bool& hit_face) {
-    const float ooeps = 1e-30f;
-    const float idx = 1.0f / (fabsf(ray.d.x) > ooeps ? ray.d.x : copysignf(ooeps, ray.d.x));
-    const float idy = 1.0f / (fabsf(ray.d.y) > ooeps ? ray.d.y : copysignf(ooeps, ray.d.y));
-    const float idz = 1.0f / (fabsf(ray.d.z) > ooeps ? ray.d.z : copysignf(ooeps, ray.d.z));
-    const float oodx = ray.o.x * idx, oody = ray.o.y * idy, oodz = ray.o.z * idz;
-    int stack[PT_STACK];
-    stack[0] = PT_SENTINEL;
-    int sp = 0;
-    int node = 0, leaf = 0;
-    while (node != PT_SENTINEL) {
-        bool searching = true;
-        while (node >= 0 && node != PT_SENTINEL) {
-            const float4 n0 = __ldg(&nodes[4 * node]), n1 = __ldg(&nodes[4 * node + 1]), n2 = __ldg(&nodes[4 * node + 2]);
-            const float4 cn = __ldg(&nodes[4 * node + 3]);
-            // slabs; the 1e-5 relative slack keeps the (already padded) boxes conservative against the rounding of these products
-            const float c0lox = n0.x * idx - oodx, c0hix = n0.y * idx - oodx, c0loy = n0.z * idy - oody, c0hiy = n0.w * idy - oody;
-            const float c0loz = n2.x * idz - oodz, c0hiz = n2.y * idz - oodz;
-            const float c1lox = n1.x * idx - oodx, c1hix = n1.y * idx - oodx, c1loy = n1.z * idy - oody, c1hiy = n1.w * idy - oody;
-            const float c1loz = n2.z * idz - oodz, c1hiz = n2.w * idz - oodz;
-            const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
-            const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fmaxf(c0loz, c0hiz));
-            const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
-            const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fmaxf(c1loz, c1hiz));
-            const float tlim = t_min * 1.00001f;
-            const bool h0 = c0min * 0.99999f <= c0max * 1.00001f && c0min * 0.99999f <= tlim;
-            const bool h1 = c1min * 0.99999f <= c1max * 1.00001f && c1min * 0.99999f <= tlim;
-            const int child0 = __float_as_int(cn.x), child1 = __float_as_int(cn.y);
-            if (!h0 && !h1) {
-                node = stack[sp--];
-            } else {
-                node = h0 ? child0 : child1;
-                if (h0 && h1) {
-                    int other = child1;
-                    if (c1min < c0min) { other = node; node = child1; }
-                    stack[++sp] = other;
-                }
-            }
-            if (node < 0 && leaf >= 0) {            // first leaf found: postpone it and keep walking
-                searching = false;
-                leaf = node;
-                node = stack[sp--];
-            }
-            if (!__any_sync(__activemask(), searching)) break;
-        }
-        while (leaf < 0) {
-            const int code = ~leaf, first = code >> 4, count = (code & 15) + 1;
-            for (int i = 0; i < count; ++i) {
-                const float4 a = __ldg(&tris[3 * (first + i)]), b = __ldg(&tris[3 * (first + i) + 1]), c = __ldg(&tris[3 * (first + i) + 2]);
-                float bx, by;
-                const float t = triangleParam(V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), ray, bx, by);
-                consider_face(t, __float_as_int(a.w), bx, by, t_min, best_face, bbx, bby, hit_face);
-            }
-            leaf = node;
-            if (node < 0) node = stack[sp--];
-        }
     }
 }
 
@@ -135,6 +74,229 @@ __device__ __forceinline__ bool ray_may_hit_box(const Ray& ray, const ptd_aabb& 
     return !(tn * 0.9999f > tf * 1.0001f);          // NaN compares false -> "may hit"
 }
 
+// generateRayFromCamera, pathtrace.cu:155-182 (stale remainingBounces := 0 in the seed, decision D4)
+__device__ __forceinline__ Ray camera_ray(const ptd_camera& cam, int W, int iter, int idx) {
+    const int x = idx % W, y = idx / W;
+    Rng rng = make_rng(iter, idx, 0);
+    Ray ray;
+    ray.o = cam.position;
+    float jx = rng_uniform(rng, -0.5f, 0.5f);
+    float jy = rng_uniform(rng, -0.5f, 0.5f);
+    v3 a = muls(muls(cam.right, cam.pixelLength_x), fadd(ffma((float)cam.res_x, -0.5f, (float)x), jx));
+    v3 b = muls(muls(cam.up, cam.pixelLength_y), fadd(ffma((float)cam.res_y, -0.5f, (float)y), jy));
+    ray.d = normalize(sub(sub(cam.view, a), b));
+    return ray;
+}
+
+// ---- kernel 1 of a bounce: nearest intersection (computeIntersections, pathtrace.cu:200-306) -----------------------------
+// Persistent warps with dynamic ray fetch (Aila & Laine's "persistent speculative while-while"): a warp pulls rays from a
+// global counter, lanes whose ray has finished are refilled as soon as fewer than TR_REFILL lanes are still traversing, and
+// nothing in the kernel is a block barrier - BVH traversal lengths vary by 10x between neighbouring rays, so a block-wide
+// barrier (or a fixed ray-per-thread mapping) leaves most of the machine waiting for the slowest ray of each tile.
+// All loops are warp-uniform (full-mask votes decide the trip count, idle lanes are predicated off) so the warp stays
+// converged.  The result is the reference's 36-byte ShadeableIntersection record at slot `idx`, i.e. this kernel and
+// pt_shade exchange exactly the data computeIntersections and shadeMaterial exchange.
+#define TR_BLOCK 128
+#define TR_REFILL 22
+#define PT_SENTINEL 0x76543210
+
+struct TraceOut {
+    ptd_intersection* isx; float* gbuf; int P, W; bool write_gbuf;
+};
+__device__ __forceinline__ void write_hit(const TraceOut& o, int idx, float t, v3 normal, int mat, bool outside, v3 ip) {
+    ptd_intersection r;
+    r.t = t; r.surfaceNormal = normalize(normal); r.materialId = mat; r.is_inside = !outside; r.pad[0] = r.pad[1] = r.pad[2] = 0; r.intersect = ip;
+    o.isx[idx] = r;
+    if (o.write_gbuf) {                                            // :295-304, x-mirrored like copy_data; bounce 0: pixelIndex == idx
+        const int col = idx % o.W, row = idx / o.W;
+        const size_t m = (size_t)(o.W - col - 1) + (size_t)row * o.W;
+        o.gbuf[(size_t)o.P * 3 + m] = normal.x; o.gbuf[(size_t)o.P * 4 + m] = normal.y; o.gbuf[(size_t)o.P * 5 + m] = normal.z;
+        o.gbuf[(size_t)o.P * 6 + m] = t;
+    }
+}
+__device__ __forceinline__ void write_miss(const TraceOut& o, int idx) {
+    ptd_intersection r;
+    memset(&r, 0, sizeof r);                                       // the reference memsets the array every bounce (:478) ...
+    r.t = -1.0f;                                                   // ... and a miss only sets t (:283)
+    o.isx[idx] = r;
+    if (o.write_gbuf) {                                            // planes stay at the init memset's 0 (:119)
+        const int col = idx % o.W, row = idx / o.W;
+        const size_t m = (size_t)(o.W - col - 1) + (size_t)row * o.W;
+        o.gbuf[(size_t)o.P * 3 + m] = 0.f; o.gbuf[(size_t)o.P * 4 + m] = 0.f; o.gbuf[(size_t)o.P * 5 + m] = 0.f; o.gbuf[(size_t)o.P * 6 + m] = 0.f;
+    }
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(TR_BLOCK) pt_trace(const PtKernelParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ptd_geom* s_geoms = reinterpret_cast<ptd_geom*>(smem_raw);
+    const unsigned FULL = 0xffffffffu;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int n = FIRST ? p.P : p.counts[p.bounce];
+    if (p.geoms_in_smem) {
+        const uint32_t* g = reinterpret_cast<const uint32_t*>(p.geoms);
+        uint32_t* d = reinterpret_cast<uint32_t*>(s_geoms);
+        for (int i = tid; i < p.ngeoms * 62; i += TR_BLOCK) d[i] = __ldg(&g[i]);
+        const uint32_t* gb = reinterpret_cast<const uint32_t*>(p.geom_bounds);
+        uint32_t* db = reinterpret_cast<uint32_t*>(s_geoms + p.ngeoms);
+        for (int i = tid; i < p.ngeoms * 6; i += TR_BLOCK) db[i] = __ldg(&gb[i]);
+        __syncthreads();
+    }
+    const ptd_geom* geoms = p.geoms_in_smem ? s_geoms : p.geoms;
+    const ptd_aabb* gbounds = p.geoms_in_smem ? reinterpret_cast<const ptd_aabb*>(s_geoms + p.ngeoms) : p.geom_bounds;
+    TraceOut out;
+    out.isx = p.isx; out.gbuf = p.gbuf; out.P = p.P; out.W = p.W; out.write_gbuf = FIRST && p.iter == 1;
+
+    // per-lane ray state
+    int idx = 0;
+    bool have = false, exhausted = false, pool_empty = false;
+    Ray ray; ray.o = ray.d = V(0, 0, 0);
+    float idirx = 0.f, idiry = 0.f, idirz = 0.f, oodx = 0.f, oody = 0.f, oodz = 0.f;
+    float t_min = FLT_MAX, bbx = 0.f, bby = 0.f;
+    int best_face = -1;
+    bool hit_face = false, geom_hit = false, outside = true;
+    int node = PT_SENTINEL, leaf = 0, sp = 0, tri = 0, tri_end = 0;
+    int stack[PT_STACK];
+
+    for (;;) {
+        // ---- refill idle lanes from the global ray counter --------------------------------------------------------
+        const bool need = !have && !exhausted;
+        const unsigned m = __ballot_sync(FULL, need);
+        if (m) {
+            const int leader = __ffs(m) - 1;
+            int base = 0;
+            if (lane == leader) base = atomicAdd(p.ticket, __popc(m));
+            base = __shfl_sync(FULL, base, leader);
+            if (need) {
+                idx = base + __popc(m & ((1u << lane) - 1u));
+                if (idx >= n) {
+                    exhausted = true;
+                } else {
+                    have = true;
+                    if (FIRST) {
+                        ray = camera_ray(p.cam, p.W, p.iter, idx);
+                    } else {
+                        const float* w = reinterpret_cast<const float*>(p.src) + (size_t)idx * PT_WORDS;
+                        ray.o = V(w[0], w[1], w[2]); ray.d = V(w[3], w[4], w[5]);
+                    }
+                    t_min = FLT_MAX; best_face = -1; hit_face = false; outside = true; bbx = bby = 0.f;
+                    v3 ip = V(0, 0, 0), normal = V(0, 0, 0), tip = V(0, 0, 0), tn = V(0, 0, 0);
+                    int materialid = -1;
+                    for (int g = 0; g < p.ngeoms; ++g) {
+                        const ptd_geom* ge = &geoms[g];
+                        if (!ray_may_hit_box(ray, gbounds[g])) continue;              // a certain miss leaves t, outside untouched in the reference too
+                        float t = 0.f;
+                        if (ge->type == PTD_CUBE) t = boxIntersectionTest(ge, ray, tip, tn, outside);
+                        else if (ge->type == PTD_SPHERE) t = sphereIntersectionTest(ge, ray, tip, tn, outside);
+                        else continue;
+                        if (t > 0.0f && t_min > t) { t_min = t; materialid = ge->materialid; ip = tip; normal = tn; }
+                    }
+                    geom_hit = materialid != -1;
+                    if (geom_hit) write_hit(out, idx, t_min, normal, materialid, outside, ip);   // provisional: a nearer face overwrites it
+                    node = PT_SENTINEL; leaf = 0;
+                    if (p.nfaces && RayAABBintersect(ray, p.mesh_box)) {               // RAY_CULLING true, :258
+                        if (p.use_bvh) {
+                            const float ooeps = 1e-30f;
+                            idirx = 1.0f / (fabsf(ray.d.x) > ooeps ? ray.d.x : copysignf(ooeps, ray.d.x));
+                            idiry = 1.0f / (fabsf(ray.d.y) > ooeps ? ray.d.y : copysignf(ooeps, ray.d.y));
+                            idirz = 1.0f / (fabsf(ray.d.z) > ooeps ? ray.d.z : copysignf(ooeps, ray.d.z));
+                            oodx = ray.o.x * idirx; oody = ray.o.y * idiry; oodz = ray.o.z * idirz;
+                            stack[0] = PT_SENTINEL; sp = 0; node = 0;
+                        } else {                                                       // PTD_PT_NO_BVH: the reference's loop, test aid
+                            for (int f = 0; f < p.nfaces; ++f) {
+                                const ptd_face* fc = &p.faces[f];
+                                float bx, by;
+                                float t = triangleParam(fc->v[0], fc->v[1], fc->v[2], ray, bx, by);
+                                consider_face(t, f, bx, by, t_min, best_face, bbx, bby, hit_face);
+                            }
+                        }
+                    }
+                }
+            }
+            pool_empty = __any_sync(FULL, exhausted);
+        }
+        if (!__any_sync(FULL, have)) break;
+
+        // ---- traverse until too few lanes are busy ----------------------------------------------------------------
+        for (;;) {
+            // interior nodes: every lane with a node steps; the phase ends when no lane is still looking for its first leaf
+            bool searching = true;
+            for (;;) {
+                const bool can_step = node >= 0 && node != PT_SENTINEL;
+                if (!__any_sync(FULL, can_step && searching)) break;
+                if (can_step) {
+                    const float4* np = p.nodes + 4 * (size_t)node;
+                    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), cn = __ldg(np + 3);
+                    // slabs; the 1e-5 relative slack keeps the (already padded) boxes conservative against the rounding of these products
+                    const float c0lox = n0.x * idirx - oodx, c0hix = n0.y * idirx - oodx, c0loy = n0.z * idiry - oody, c0hiy = n0.w * idiry - oody;
+                    const float c0loz = n2.x * idirz - oodz, c0hiz = n2.y * idirz - oodz;
+                    const float c1lox = n1.x * idirx - oodx, c1hix = n1.y * idirx - oodx, c1loy = n1.z * idiry - oody, c1hiy = n1.w * idiry - oody;
+                    const float c1loz = n2.z * idirz - oodz, c1hiz = n2.w * idirz - oodz;
+                    const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
+                    const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fmaxf(c0loz, c0hiz));
+                    const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
+                    const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fmaxf(c1loz, c1hiz));
+                    const float tlim = t_min * 1.00001f;
+                    const bool h0 = c0min * 0.99999f <= c0max * 1.00001f && c0min * 0.99999f <= tlim;
+                    const bool h1 = c1min * 0.99999f <= c1max * 1.00001f && c1min * 0.99999f <= tlim;
+                    const int child0 = __float_as_int(cn.x), child1 = __float_as_int(cn.y);
+                    if (!h0 && !h1) {
+                        node = stack[sp--];
+                    } else {
+                        node = h0 ? child0 : child1;
+                        if (h0 && h1) {
+                            int other = child1;
+                            if (c1min < c0min) { other = node; node = child1; }
+                            stack[++sp] = other;
+                        }
+                    }
+                    if (node < 0 && leaf >= 0) {            // first leaf found: postpone it and keep walking (speculatively)
+                        searching = false;
+                        leaf = node;
+                        node = stack[sp--];
+                    }
+                }
+            }
+            // leaves: one triangle per lane per trip, so lanes with short leaves do not wait for lanes with long ones
+            if (leaf < 0) { const int code = ~leaf; tri = code >> 4; tri_end = tri + (code & 15) + 1; }
+            for (;;) {
+                const bool busy = leaf < 0;
+                if (!__any_sync(FULL, busy)) break;
+                if (busy) {
+                    const float4* tp = p.tris + 3 * (size_t)tri;
+                    const float4 a = __ldg(tp), b = __ldg(tp + 1), c = __ldg(tp + 2);
+                    float bx, by;
+                    const float t = triangleParam(V(a.x, a.y, a.z), V(b.x, b.y, b.z), V(c.x, c.y, c.z), ray, bx, by);
+                    consider_face(t, __float_as_int(a.w), bx, by, t_min, best_face, bbx, bby, hit_face);
+                    if (++tri == tri_end) {
+                        leaf = node;                        // a second leaf may be waiting in `node`
+                        if (node < 0) {
+                            node = stack[sp--];
+                            const int code = ~leaf; tri = code >> 4; tri_end = tri + (code & 15) + 1;
+                        }
+                    }
+                }
+            }
+            const unsigned act = __ballot_sync(FULL, node != PT_SENTINEL);
+            if (act == 0u) break;
+            if (!pool_empty && __popc(act) < TR_REFILL) break;
+        }
+
+        // ---- retire the rays that finished ------------------------------------------------------------------------
+        if (have && node == PT_SENTINEL) {
+            if (hit_face) {
+                const ptd_face* fc = &p.faces[best_face];
+                v3 ip, normal;
+                triangleFinish(fc, bbx, bby, ip, normal);
+                write_hit(out, idx, t_min, normal, fc->materialid, outside, ip);
+            } else if (!geom_hit) {
+                write_miss(out, idx);
+            }
+            have = false;
+        }
+    }
+}
+
 // ---- block-wide helpers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
     unsigned long long v;
@@ -145,24 +307,16 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
+// ---- kernel 2 of a bounce: shadeMaterial (:333-390) + thrust::partition (:505) + finalGather / copy_data for the paths that end here
 template <bool FIRST>
-__global__ void __launch_bounds__(PT_BLOCK) pt_bounce(const PtKernelParams p) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    uint32_t* s_words = reinterpret_cast<uint32_t*>(smem_raw);                     // PT_BLOCK * 11 words staging
-    ptd_geom* s_geoms = reinterpret_cast<ptd_geom*>(smem_raw + PT_BLOCK * PT_WORDS * 4);
+__global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
+    __shared__ __align__(16) uint32_t s_words[PT_BLOCK * PT_WORDS];                  // 5632 B staging (loads, then compacted stores)
+    __shared__ __align__(16) uint32_t s_isx[PT_BLOCK * 9];                           // 4608 B: the tile's ShadeableIntersections
     __shared__ int s_tile, s_warp_kept[PT_BLOCK / 32], s_excl;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = FIRST ? p.P : p.counts[p.bounce];
-    if (tid == 0) s_tile = atomicAdd(p.ticket, 1);
-    if (p.geoms_in_smem) {
-        const uint32_t* g = reinterpret_cast<const uint32_t*>(p.geoms);
-        uint32_t* d = reinterpret_cast<uint32_t*>(s_geoms);
-        for (int i = tid; i < p.ngeoms * 62; i += PT_BLOCK) d[i] = __ldg(&g[i]);
-        const uint32_t* gb = reinterpret_cast<const uint32_t*>(p.geom_bounds);
-        uint32_t* db = reinterpret_cast<uint32_t*>(s_geoms + p.ngeoms);
-        for (int i = tid; i < p.ngeoms * 6; i += PT_BLOCK) db[i] = __ldg(&gb[i]);
-    }
+    if (tid == 0) s_tile = atomicAdd(p.ticket2, 1);                      // dynamic tile id: look-back predecessors are always scheduled
     __syncthreads();
     const int tile = s_tile;
     const int base = tile * PT_BLOCK;
@@ -170,35 +324,36 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_bounce(const PtKernelParams p) {
     const int valid = min(PT_BLOCK, n - base);
     const int idx = base + tid;
     const bool active = tid < valid;
-    const ptd_geom* geoms = p.geoms_in_smem ? s_geoms : p.geoms;
-    const ptd_aabb* gbounds = p.geoms_in_smem ? reinterpret_cast<const ptd_aabb*>(s_geoms + p.ngeoms) : p.geom_bounds;
 
-    // ---- 1. this tile's path segments ---------------------------------------------------------------------
+    // ---- 1. this tile's path segments and intersections (coalesced, staged through shared memory) ----------------
     Ray ray; v3 color; int pixelIndex = 0, rb = 0;
     ray.o = ray.d = color = V(0, 0, 0);
+    {
+        const uint32_t* src = reinterpret_cast<const uint32_t*>(p.isx) + (size_t)base * 9;
+        if (valid == PT_BLOCK && (reinterpret_cast<uintptr_t>(src) & 15) == 0) {   // 4608 B tile
+            const uint4* s4 = reinterpret_cast<const uint4*>(src);
+            uint4* d4 = reinterpret_cast<uint4*>(s_isx);
+            for (int i = tid; i < PT_BLOCK * 9 / 4; i += PT_BLOCK) d4[i] = s4[i];
+        } else {
+            for (int i = tid; i < valid * 9; i += PT_BLOCK) s_isx[i] = src[i];
+        }
+    }
     if (FIRST) {
-        if (active) {                                                      // generateRayFromCamera, pathtrace.cu:155-182
-            const int x = idx % p.W, y = idx / p.W;
-            Rng rng = make_rng(p.iter, idx, 0);                            // stale remainingBounces := 0 (decision D4)
-            ray.o = p.cam.position;
+        if (active) {
+            ray = camera_ray(p.cam, p.W, p.iter, idx);
             color = V(1.0f, 1.0f, 1.0f);
-            float jx = rng_uniform(rng, -0.5f, 0.5f);
-            float jy = rng_uniform(rng, -0.5f, 0.5f);
-            v3 a = muls(muls(p.cam.right, p.cam.pixelLength_x), fadd(ffma((float)p.cam.res_x, -0.5f, (float)x), jx));
-            v3 b = muls(muls(p.cam.up, p.cam.pixelLength_y), fadd(ffma((float)p.cam.res_y, -0.5f, (float)y), jy));
-            ray.d = normalize(sub(sub(p.cam.view, a), b));
             pixelIndex = idx;
             rb = p.trace_depth;
         }
+        __syncthreads();
     } else {
         const uint32_t* src = reinterpret_cast<const uint32_t*>(p.src) + (size_t)base * PT_WORDS;
-        const int nwords = valid * PT_WORDS;
-        if (valid == PT_BLOCK) {                                           // 5632 B tile, 16-B aligned: 352 float4
+        if (valid == PT_BLOCK) {                                           // 5632 B tile, 16-B aligned: 352 uint4
             const uint4* s4 = reinterpret_cast<const uint4*>(src);
             uint4* d4 = reinterpret_cast<uint4*>(s_words);
             for (int i = tid; i < PT_BLOCK * PT_WORDS / 4; i += PT_BLOCK) d4[i] = s4[i];
         } else {
-            for (int i = tid; i < nwords; i += PT_BLOCK) s_words[i] = src[i];
+            for (int i = tid; i < valid * PT_WORDS; i += PT_BLOCK) s_words[i] = src[i];
         }
         __syncthreads();
         if (active) {
@@ -206,8 +361,13 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_bounce(const PtKernelParams p) {
             ray.o = V(w[0], w[1], w[2]); ray.d = V(w[3], w[4], w[5]); color = V(w[6], w[7], w[8]);
             pixelIndex = __float_as_int(w[9]); rb = __float_as_int(w[10]);
         }
-        __syncthreads();                                                   // staging buffer is reused for the stores below
     }
+    float isx_t = -1.0f; v3 isx_n = V(0, 0, 0), ip = V(0, 0, 0); int isx_mat = 0;
+    if (active) {
+        const float* w = reinterpret_cast<const float*>(s_isx) + tid * 9;                // stride 9 words: conflict free
+        isx_t = w[0]; isx_n = V(w[1], w[2], w[3]); isx_mat = __float_as_int(w[4]); ip = V(w[6], w[7], w[8]);
+    }
+    __syncthreads();                                                       // staging buffer is reused for the stores below
     if (p.trace_paths && active) {
         ptd_path_segment ps;
         ps.ray.origin = ray.o; ps.ray.direction = ray.d; ps.color = color; ps.pixelIndex = pixelIndex; ps.remainingBounces = rb;
@@ -216,63 +376,11 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_bounce(const PtKernelParams p) {
 
     bool keep = false;
     if (active) {
-        // ---- 2. nearest intersection (computeIntersections, pathtrace.cu:200-306) ---------------------------
-        float t_min = FLT_MAX;
-        v3 ip = V(0, 0, 0), normal = V(0, 0, 0), tip = V(0, 0, 0), tn = V(0, 0, 0);
-        int materialid = -1;
-        bool outside = true;
-        for (int g = 0; g < p.ngeoms; ++g) {
-            const ptd_geom* ge = &geoms[g];
-            if (!ray_may_hit_box(ray, gbounds[g])) continue;                  // a certain miss leaves t, outside untouched in the reference too
-            float t = 0.f;
-            if (ge->type == PTD_CUBE) t = boxIntersectionTest(ge, ray, tip, tn, outside);
-            else if (ge->type == PTD_SPHERE) t = sphereIntersectionTest(ge, ray, tip, tn, outside);
-            else continue;
-            if (t > 0.0f && t_min > t) { t_min = t; materialid = ge->materialid; ip = tip; normal = tn; }
-        }
-        if (p.nfaces && RayAABBintersect(ray, p.mesh_box)) {               // RAY_CULLING true, :258
-            int best_face = -1; float bbx = 0.f, bby = 0.f; bool hit_face = false;
-            if (p.use_bvh) {
-                traverse_bvh(p.nodes, p.tris, ray, t_min, best_face, bbx, bby, hit_face);
-            } else {
-                for (int f = 0; f < p.nfaces; ++f) {
-                    const ptd_face* fc = &p.faces[f];
-                    float bx, by;
-                    float t = triangleParam(fc->v[0], fc->v[1], fc->v[2], ray, bx, by);
-                    consider_face(t, f, bx, by, t_min, best_face, bbx, bby, hit_face);
-                }
-            }
-            if (hit_face) {
-                const ptd_face* fc = &p.faces[best_face];
-                materialid = fc->materialid;
-                triangleFinish(fc, bbx, bby, ip, normal);
-            }
-        }
-        float isx_t; v3 isx_n = V(0, 0, 0); int isx_mat = 0;
-        if (materialid == -1) {
-            isx_t = -1.0f;
-        } else {
-            isx_t = t_min; isx_mat = materialid; isx_n = normalize(normal);
-        }
         const bool hit = isx_t >= 0;
+        if (p.sort_keys) p.sort_keys[idx] = isx_mat;                                   // key of the UN-compacted slot (:509 quirk)
         const int col = pixelIndex % p.W, row = pixelIndex / p.W;
         const size_t mirrored = (size_t)(p.W - col - 1) + (size_t)row * p.W;          // x-mirror of copy_data / :297-299
-        if (FIRST && p.iter == 1) {                                                     // :295-304 (+ the init memset for misses)
-            p.gbuf[(size_t)p.P * 3 + mirrored] = hit ? normal.x : 0.f;
-            p.gbuf[(size_t)p.P * 4 + mirrored] = hit ? normal.y : 0.f;
-            p.gbuf[(size_t)p.P * 5 + mirrored] = hit ? normal.z : 0.f;
-            p.gbuf[(size_t)p.P * 6 + mirrored] = hit ? isx_t : 0.f;
-        }
-        if (p.trace_isx) {
-            ptd_intersection r;
-            memset(&r, 0, sizeof r);
-            r.t = isx_t;
-            if (hit) { r.surfaceNormal = isx_n; r.materialId = isx_mat; r.is_inside = !outside; r.intersect = ip; }
-            p.trace_isx[(size_t)p.bounce * p.P + idx] = r;
-        }
-        if (p.sort_keys) p.sort_keys[idx] = isx_mat;                                   // key of the UN-compacted slot (:509 quirk)
-
-        // ---- 3. shade (shadeMaterial, pathtrace.cu:333-390) -------------------------------------------------
+        // ---- 2. shade (shadeMaterial, pathtrace.cu:333-390) -------------------------------------------------
         if (isx_t > 0.0f) {
             Rng rng = make_rng(p.iter, idx, rb);
             const ptd_material m = p.materials[isx_mat];
@@ -306,7 +414,7 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_bounce(const PtKernelParams p) {
         }
     }
 
-    // ---- 4. stable stream compaction (thrust::partition, :505) -----------------------------------------------
+    // ---- 3. stable stream compaction (thrust::partition, :505) -----------------------------------------------
     const unsigned ballot = __ballot_sync(0xffffffffu, keep);
     const int lane_rank = __popc(ballot & ((1u << lane) - 1u));
     if (lane == 0) s_warp_kept[warp] = __popc(ballot);
@@ -422,6 +530,8 @@ struct ptd_pt {
     float4* d_nodes = nullptr; float4* d_tris = nullptr;
     ptd_path_segment* d_paths[3] = {nullptr, nullptr, nullptr};
     ptd_path_segment* d_dead = nullptr;
+    ptd_intersection* d_isx = nullptr;
+    int trace_blocks = 0;
     float* d_image = nullptr; float* d_gbuf_own = nullptr;
     unsigned char* d_ctl = nullptr; size_t ctl_bytes = 0;     // counts | tickets | status (memset once per frame)
     int* d_counts = nullptr; int* d_ticket = nullptr; unsigned long long* d_status = nullptr;
@@ -446,7 +556,7 @@ extern "C" void ptd_pt_destroy(ptd_pt* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_geoms); cudaFree(h->d_geom_bounds); cudaFree(h->d_materials); cudaFree(h->d_faces); cudaFree(h->d_nodes); cudaFree(h->d_tris);
     for (int i = 0; i < 3; ++i) cudaFree(h->d_paths[i]);
-    cudaFree(h->d_dead); cudaFree(h->d_image); cudaFree(h->d_gbuf_own); cudaFree(h->d_ctl); cudaFree(h->d_keys); cudaFree(h->d_hist);
+    cudaFree(h->d_dead); cudaFree(h->d_isx); cudaFree(h->d_image); cudaFree(h->d_gbuf_own); cudaFree(h->d_ctl); cudaFree(h->d_keys); cudaFree(h->d_hist);
     cudaFree(h->d_trace_paths); cudaFree(h->d_trace_isx);
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     delete h;
@@ -498,8 +608,9 @@ extern "C" ptd_status ptd_pt_create(const ptd_scene* sc, int device, unsigned fl
     if (flags & PTD_PT_KEEP_TERMINATED) { ALLOC(h->d_dead, sizeof(ptd_path_segment) * P); cudaMemset(h->d_dead, 0, sizeof(ptd_path_segment) * P); }
     ALLOC(h->d_image, sizeof(float) * 3 * P);
     cudaMemset(h->d_image, 0, sizeof(float) * 3 * P);
-    // control block: counts[depth+1] | tickets[depth] | status[depth][ntiles]
-    size_t off_counts = 0, off_ticket = ((size_t)(h->depth + 1) * 4 + 15) / 16 * 16, off_status = off_ticket + ((size_t)h->depth * 4 + 15) / 16 * 16;
+    if (!(flags & PTD_PT_TRACE)) ALLOC(h->d_isx, sizeof(ptd_intersection) * P);
+    // control block: counts[depth+1] | tickets[2*depth] | status[depth][ntiles]
+    size_t off_counts = 0, off_ticket = ((size_t)(h->depth + 1) * 4 + 15) / 16 * 16, off_status = off_ticket + ((size_t)h->depth * 8 + 15) / 16 * 16;
     h->ctl_bytes = off_status + (size_t)h->depth * h->ntiles * 8;
     ALLOC(h->d_ctl, h->ctl_bytes);
     h->d_counts = (int*)(h->d_ctl + off_counts); h->d_ticket = (int*)(h->d_ctl + off_ticket); h->d_status = (unsigned long long*)(h->d_ctl + off_status);
@@ -514,9 +625,12 @@ extern "C" ptd_status ptd_pt_create(const ptd_scene* sc, int device, unsigned fl
     }
 #undef ALLOC
 #undef UPLOAD
-    const size_t smem = PT_BLOCK * PT_WORDS * 4 + (sizeof(ptd_geom) + sizeof(ptd_aabb)) * 64;
-    cudaFuncSetAttribute(pt_bounce<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    cudaFuncSetAttribute(pt_bounce<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    {
+        int sms = 148, per_sm = 8;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pt_trace<false>, TR_BLOCK, (sizeof(ptd_geom) + sizeof(ptd_aabb)) * std::min(h->ngeoms, 64));
+        h->trace_blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (h->P + TR_BLOCK - 1) / TR_BLOCK));   // persistent: every resident warp pulls rays
+    }
     CUDA_TRY(cudaDeviceSynchronize());
     *out = h;
     return PTD_OK;
@@ -541,9 +655,9 @@ extern "C" ptd_status ptd_pt_render(ptd_pt* h, const ptd_camera* cam, int iter, 
     p.cam = cam ? *cam : h->cam;
     p.W = h->W; p.P = h->P; p.iter = iter; p.trace_depth = h->depth;
     p.counts = h->d_counts; p.gbuf = gbuf; p.image = h->d_image; p.dead = h->d_dead;
-    p.sort_keys = h->d_keys; p.trace_paths = h->d_trace_paths; p.trace_isx = h->d_trace_isx;
+    p.sort_keys = h->d_keys; p.trace_paths = h->d_trace_paths;
     CUDA_TRY(cudaMemsetAsync(h->d_ctl, 0, h->ctl_bytes, st));
-    const size_t smem = PT_BLOCK * PT_WORDS * 4 + (p.geoms_in_smem ? (sizeof(ptd_geom) + sizeof(ptd_aabb)) * h->ngeoms : 0);
+    const size_t smem = p.geoms_in_smem ? (sizeof(ptd_geom) + sizeof(ptd_aabb)) * h->ngeoms : 0;
     const bool sort = (h->flags & PTD_PT_SORT_MATERIAL) != 0;
     int cur = 0;
     h->launches = 0;
@@ -559,10 +673,14 @@ extern "C" ptd_status ptd_pt_render(ptd_pt* h, const ptd_camera* cam, int iter, 
         p.bounce = b;
         p.src = h->d_paths[cur]; p.dst = h->d_paths[nxt];
         p.status = h->d_status + (size_t)b * h->ntiles;
-        p.ticket = h->d_ticket + b;
-        if (b == 0) pt_bounce<true><<<h->ntiles, PT_BLOCK, smem, st>>>(p);
-        else pt_bounce<false><<<h->ntiles, PT_BLOCK, smem, st>>>(p);
-        h->launches++;
+        p.ticket = h->d_ticket + 2 * b; p.ticket2 = h->d_ticket + 2 * b + 1;
+        p.isx = h->d_trace_isx ? h->d_trace_isx + (size_t)b * h->P : h->d_isx;
+        if (b == 0) pt_trace<true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+        else pt_trace<false><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+        mark();
+        if (b == 0) pt_shade<true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+        else pt_shade<false><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+        h->launches += 2;
         mark();
         cur = nxt;
         if (sort && b + 1 < h->depth) {

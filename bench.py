@@ -270,14 +270,21 @@ def main():
     conv_bytes = sum(table[dn_named[i][0]][1] for i in conv_idx)
     other_dn_ms = float(sum(dn_ms)) - conv_ms
     pt_total_ms = float(sum(pt_ms))
-    pt_bytes = 44.0 * P + sum(88.0 * n for n in live[:run]) + 28.0 * P + 24.0 * P     # ray-gen + 88 B per live path per bounce + G-buffer planes
+    trace_ms, shade_ms = float(sum(pt_ms[0::2])), float(sum(pt_ms[1::2]))             # launch order: pt_trace, pt_shade per bounce
+    # algorithmic bytes (reference AoS records): intersect 44 B read + 36 B written per live path (bounce 0 generates its
+    # rays: 36 B only), shade + compaction 36 + 44 B read and 44 B written per survivor (<= per live path), G-buffer 28 P + 24 P
+    trace_bytes = 36.0 * P + sum(80.0 * n for n in live[1:run]) + 16.0 * P
+    shade_bytes = 36.0 * P + sum(80.0 * n for n in live[1:run]) + sum(44.0 * n for n in live[1:run]) + 12.0 * P + 24.0 * P
+    pt_bytes = trace_bytes + shade_bytes
     tf32_peak = peaks["bf16"] / 2.0                     # kind::tf32 issues at half the bf16 rate; no separate measured figure exists
     conv_kernel = "conv_tc_kernel" if args.mode == "tf32" else "conv3x3_fp32"
     kernels = [
         dict(kernel=conv_kernel, launches=len(conv_idx), ms=conv_ms, share=conv_ms / (pt_total_ms + float(sum(dn_ms))),
              tflops=conv_flops / (conv_ms * 1e-3) / 1e12, gbs=conv_bytes / (conv_ms * 1e-3) / 1e9),
-        dict(kernel="pt_bounce", launches=len(pt_ms), ms=pt_total_ms, share=pt_total_ms / (pt_total_ms + float(sum(dn_ms))),
-             gbs=pt_bytes / (pt_total_ms * 1e-3) / 1e9, rays=int(sum(live[:run])), mrays_per_s=sum(live[:run]) / (pt_total_ms * 1e-3) / 1e6),
+        dict(kernel="pt_trace", launches=len(pt_ms[0::2]), ms=trace_ms, share=trace_ms / (pt_total_ms + float(sum(dn_ms))),
+             gbs=trace_bytes / (trace_ms * 1e-3) / 1e9, rays=int(sum(live[:run])), mrays_per_s=sum(live[:run]) / (trace_ms * 1e-3) / 1e6),
+        dict(kernel="pt_shade", launches=len(pt_ms[1::2]), ms=shade_ms, share=shade_ms / (pt_total_ms + float(sum(dn_ms))),
+             gbs=shade_bytes / (shade_ms * 1e-3) / 1e9),
         dict(kernel="pack/pool/unpack", launches=len(dn_ms) - len(conv_idx), ms=other_dn_ms, share=other_dn_ms / (pt_total_ms + float(sum(dn_ms)))),
     ]
     if conv_ms >= pt_total_ms:
@@ -290,11 +297,12 @@ def main():
             roof = dict(bound="hbm", kernel=conv_kernel, achieved=g, peak=peaks["hbm"], unit="GB/s", frac=g / peaks["hbm"], traffic=None,
                         tensor_tflops=ach, tensor_frac_of_tf32_peak=ach / tf32_peak)
     else:
-        g = pt_bytes / (pt_total_ms * 1e-3) / 1e9
-        roof = dict(bound="hbm", kernel="pt_bounce", achieved=g, peak=peaks["hbm"], unit="GB/s", frac=g / peaks["hbm"], traffic=None)
+        g = trace_bytes / (trace_ms * 1e-3) / 1e9
+        roof = dict(bound="hbm", kernel="pt_trace", achieved=g, peak=peaks["hbm"], unit="GB/s", frac=g / peaks["hbm"], traffic=None,
+                    note="BVH traversal is latency/divergence bound, not HBM bound: see mrays_per_s in kernels[] and DESIGN.md")
     roof["peak_source"] = peaks["source"] + ("; tf32 peak = measured bf16 burst / 2" if roof["bound"] == "tensor" or "tensor_tflops" in roof else "")
     roof["per_layer_ms"] = {n: round(float(m), 4) for (n, _), m in zip(dn_named, dn_ms)}
-    roof["per_bounce_ms"] = [round(float(m), 4) for m in pt_ms]
+    roof["per_bounce_ms"] = {"pt_trace": [round(float(m), 4) for m in pt_ms[0::2]], "pt_shade": [round(float(m), 4) for m in pt_ms[1::2]]}
     roof["kernels"] = kernels
 
     # ---- end to end through the host-pointer C ABI (the calls the reference's runCuda() would make) ----

@@ -108,7 +108,8 @@ ptd_status ptd_pt_bvh_stats(const ptd_pt*, int* nodes, int* leaves, int* max_lea
 /* ---- HP-2 recurrent denoising autoencoder (replaces network_prediction_faster_version) ----------- */
 enum {
     PTD_DN_FP32 = 0u,             /* fp32 FFMA convolutions (strict-parity path)                                   */
-    PTD_DN_TF32 = 1u              /* tcgen05 kind::tf32 tensor-core convolutions, fp32 accumulate in TMEM (default of the CLI) */
+    PTD_DN_TF32 = 1u,             /* tcgen05 kind::tf32 tensor-core convolutions, fp32 accumulate in TMEM (default of the CLI) */
+    PTD_DN_3XTF32 = 2u            /* tcgen05 kind::tf32 with hi/lo operand splitting (hi*hi + hi*lo + lo*hi): fp32-class accuracy on the tensor cores */
 };
 /* weights_path: "PTDW" flat dump of the model's state_dict (ai_path_tracer_denoiser_b200/weights.py).
  * H, W: frame size (any; zero-padded bottom/right to a multiple of 32 internally, output cropped). */
