@@ -25,7 +25,7 @@ CAM_DT = np.dtype([("res", "<i4", 2), ("pos", "<f4", 3), ("lookat", "<f4", 3), (
 AABB_DT = np.dtype([("lb", "<f4", 3), ("ub", "<f4", 3)])
 
 PT_SORT_MATERIAL, PT_TRACE, PT_NO_BVH, PT_KEEP_TERMINATED = 1, 2, 4, 8
-DN_FP32, DN_TF32 = 0, 1
+DN_FP32, DN_TF32, DN_3XTF32 = 0, 1, 2
 
 EXPORTS = """ptd_last_error ptd_version ptd_sizeof ptd_device_count ptd_scene_load ptd_scene_from_arrays ptd_scene_free
 ptd_scene_counts ptd_scene_geoms ptd_scene_materials ptd_scene_faces ptd_scene_mesh_box ptd_scene_camera
@@ -34,7 +34,8 @@ ptd_pt_render ptd_pt_render_host ptd_pt_export_rgba8 ptd_pt_live_counts ptd_pt_d
 ptd_pt_dump_final_paths ptd_pt_dump_image ptd_pt_bvh_stats ptd_dn_create ptd_dn_destroy ptd_dn_forward
 ptd_dn_forward_host ptd_dn_create_strip ptd_dn_padded_size ptd_dn_dump_hidden ptd_dn_launches_per_forward
 ptd_pt_launches_last_render ptd_dn_profile ptd_dn_launch_times ptd_dn_launch_name ptd_pt_profile
-ptd_pt_launch_times""".split()
+ptd_pt_launch_times ptd_dn_strip_partition ptd_dn_strip_info_size ptd_dn_strip_export ptd_dn_strip_connect
+ptd_dn_forward_group""".split()
 
 
 class PtdError(RuntimeError):
@@ -92,6 +93,11 @@ def lib():
         L.ptd_dn_launch_name.restype = C.c_char_p
         L.ptd_pt_profile.argtypes = [C.c_void_p, C.c_int]
         L.ptd_pt_launch_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.ptd_dn_create_strip.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_void_p)]
+        L.ptd_dn_strip_partition.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.ptd_dn_strip_export.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ptd_dn_strip_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ptd_dn_forward_group.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
 
@@ -264,13 +270,34 @@ class PathTracer:
         return ms[:n.value].copy()
 
 
-class Denoiser:
-    """network_prediction_faster_version (main.cpp:101-118) / AutoEncoder.forward(x, j) behind ptd_dn_*."""
+def strip_partition(H, nstrips, index):
+    """(row0, rows) of strip `index`: the padded frame's 32-row groups split as evenly as possible."""
+    a, b = C.c_int(), C.c_int()
+    check(lib().ptd_dn_strip_partition(H, nstrips, index, C.byref(a), C.byref(b)), "ptd_dn_strip_partition")
+    return a.value, b.value
 
-    def __init__(self, weights_path, H, W, device=0, flags=DN_TF32):
+
+class Denoiser:
+    """network_prediction_faster_version (main.cpp:101-118) / AutoEncoder.forward(x, j) behind ptd_dn_*.
+    strip=(row0, rows): a row-strip handle of the multi-GPU tiling (ptd_dn_create_strip)."""
+
+    def __init__(self, weights_path, H, W, device=0, flags=DN_TF32, strip=None):
         self.h = C.c_void_p()
-        check(lib().ptd_dn_create(os.fsencode(weights_path), H, W, device, flags, C.byref(self.h)), "ptd_dn_create")
-        self.H, self.W = H, W
+        if strip is None:
+            check(lib().ptd_dn_create(os.fsencode(weights_path), H, W, device, flags, C.byref(self.h)), "ptd_dn_create")
+        else:
+            check(lib().ptd_dn_create_strip(os.fsencode(weights_path), H, W, strip[0], strip[1], device, flags, C.byref(self.h)), "ptd_dn_create_strip")
+        self.H, self.W, self.strip = H, W, strip
+
+    def export_info(self):
+        """POD blob describing this strip's arena (bytes); all-gather it and pass the neighbours' blobs to connect()."""
+        n = lib().ptd_dn_strip_info_size()
+        buf = C.create_string_buffer(n)
+        check(lib().ptd_dn_strip_export(self.h, buf, n), "ptd_dn_strip_export")
+        return buf.raw
+
+    def connect(self, up=None, down=None):
+        check(lib().ptd_dn_strip_connect(self.h, up, down), "ptd_dn_strip_connect")
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -286,6 +313,16 @@ class Denoiser:
 
     def forward(self, gbuf_dev_ptr, rgb_dev_ptr, reset, stream=None):
         check(lib().ptd_dn_forward(self.h, gbuf_dev_ptr, rgb_dev_ptr, 1 if reset else 0, stream), "ptd_dn_forward")
+
+    @staticmethod
+    def forward_group(strips, gbuf_ptrs, rgb_ptrs, reset, streams=None):
+        """Same-process strip group: one frame, issued layer by layer over the handles (ptd_dn_forward_group)."""
+        n = len(strips)
+        hs = (C.c_void_p * n)(*[s.h for s in strips])
+        g = (C.c_void_p * n)(*gbuf_ptrs)
+        r = (C.c_void_p * n)(*rgb_ptrs)
+        st = (C.c_void_p * n)(*streams) if streams else None
+        check(lib().ptd_dn_forward_group(hs, n, g, r, 1 if reset else 0, st), "ptd_dn_forward_group")
 
     def padded_size(self):
         a, b = C.c_int(), C.c_int()

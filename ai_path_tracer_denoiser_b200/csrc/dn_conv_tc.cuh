@@ -1,21 +1,28 @@
-// Tensor-core conv engine of the denoiser: shifted-tap implicit GEMM on tcgen05 (sm_100a).
+// Tensor-core conv engine of the denoiser: halo-resident implicit GEMM on tcgen05 (sm_100a).
 //
 // One conv layer = GEMM  D[pixel, cout] = sum over (tap, cin) A[pixel + tap offset, cin] * B[cout, (tap, cin)]:
-//   * M tile  = 128 output pixels = an 8 x 16 patch of the NHWC activation (pixel = TMEM lane),
+//   * M tile  = 128 output pixels = an 8-wide x 16-tall patch (pixel = TMEM lane, m = y * 8 + x),
 //   * N       = padded Cout (16 .. 112, one tcgen05.mma N),
-//   * K loop  = taps x 16-channel chunks; every (tap, chunk) is one pipeline stage:
-//                 A: one TMA box {16 ch, 16 px, 8 rows} of the source tensor shifted by the tap offset - the image border
-//                    (conv padding = 1) is TMA out-of-bounds zero fill, no halo copies, no im2col buffer;
-//                 B: one TMA box {16 k, Cout} of the pre-packed weights;
-//               both land K-major with the 64-byte swizzle, exactly the canonical UMMA layout, and feed two
-//               tcgen05.mma.cta_group::1.kind::tf32 (K = 8 each) that accumulate in TMEM (fp32).
+//   * K loop  = 16-channel chunks; per chunk ONE pipeline stage brings the patch's 10 x 18 halo tile of 4 channel quads
+//               (11.25 KB) into shared memory with one TMA box; the 9 taps of the 3x3 stencil are then 9 x 2
+//               tcgen05.mma.kind::tf32 (K = 8 each) whose A descriptors merely START at different pixels of that tile.
+//               This works because activations live in HBM as channel-quad planes [C/4][rows][W][4] ("CHW4"): the TMA box
+//               lands as [quad][row][pixel][16 B], which is exactly the canonical no-swizzle K-major UMMA layout -
+//               8 pixels x 16 B = one 128-byte core matrix, SBO = tile row pitch (160 B), LBO = quad plane pitch (2880 B) -
+//               and a no-swizzle descriptor may start at any 16-byte boundary, so a tap shift (dy, dx) is +dy*160 + dx*16 B.
+//               Each activation is therefore read from L2 1.4x (halo overlap) instead of 9x; the image border (conv
+//               padding = 1) is TMA out-of-bounds zero fill in x and a zero apron row above / below every tensor in y
+//               (the same apron rows are the halo slots of the multi-GPU row-strip mode).
+//   * B       = weights pre-packed on the host into the same core-matrix form; when a layer's whole weight set fits in
+//               shared memory next to the A stages it is loaded ONCE per CTA (cp.async.bulk) and stays resident, otherwise
+//               the chunk's 9 taps stream in with the A tile;
 //   * concat (model.py:67,136-140) = the K loop walks two tensor maps; nearest upsample x2 (model.py:40) = four 2x2-tap
 //     phase GEMMs on the half-resolution sources with the 3x3 weights pre-summed per phase (2.25x fewer MACs);
-//   * epilogue (4 warps, thread = pixel): tcgen05.ld 32x32b.x16 -> bias/BatchNorm(eval)/LeakyReLU -> NHWC float4 stores,
-//     MaxPool2d(2) fused through two warp shuffles (the 2x2 window lives in one warp), activations rounded to tf32 (RN)
-//     so the next layer's operand truncation is exact.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (one lane), 2 = TMEM allocator, 4..7 = epilogue.  Pipelines: 8 smem stages
-// (full/empty mbarriers) and 2 TMEM accumulator buffers (tmem_full/tmem_empty), persistent CTAs, one per SM.
+//   * epilogue (4 warps, thread = pixel): tcgen05.ld 32x32b.x16 -> bias/BatchNorm(eval)/LeakyReLU -> one float4 per channel
+//     quad (a warp stores 4 x 128 contiguous bytes), MaxPool2d(2) fused through two warp shuffles (the 2x2 window lives in
+//     one warp), activations rounded to tf32 (RN) so the next layer's operand truncation is exact.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (one lane), 2 = TMEM allocator, 4..7 = epilogue.  Pipelines: up to 8 smem
+// stages (full/empty mbarriers) and 2 TMEM accumulator buffers (tmem_full/tmem_empty), persistent CTAs, one per SM.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -24,33 +31,65 @@
 #include <vector>
 #include "ptd_internal.h"
 
-#define TC_STAGES 8
-#define TC_STAGE_BYTES 16384            // A 8192 + B <= 7168, 1024-aligned
-#define TC_A_BYTES 8192
-#define TC_TILE_H 8
-#define TC_TILE_W 16
+#define TC_TILE_W 8
+#define TC_TILE_H 16
+#define TC_HALO_W (TC_TILE_W + 2)
+#define TC_HALO_H (TC_TILE_H + 2)
+#define TC_ROW_PITCH (TC_HALO_W * 16)                   // 160 B: one halo row of one channel quad
+#define TC_QUAD_PITCH (TC_HALO_H * TC_ROW_PITCH)        // 2880 B: one channel quad of the halo tile
+#define TC_A_BYTES (4 * TC_QUAD_PITCH)                  // 11520 B: 16 channels
+#define TC_MAX_STAGES 8
 #define TC_THREADS 256
 #define TC_TMEM_COLS 256
 #define TC_ACC_COLS 128
+#define TC_SMEM_BUDGET (200 * 1024)
+
+// An activation tensor in HBM: [nq = cp/4][rows + 2][W][4] fp32, image row r at buffer row r + 1 (rows 0 and rows + 1 are aprons)
+struct DnTensor {
+    float* base = nullptr;
+    int cp = 0, rows = 0, W = 0;
+    __host__ __device__ size_t quad_stride() const { return (size_t)(rows + 2) * W * 4; }
+    __host__ __device__ size_t floats() const { return (size_t)(cp / 4) * quad_stride(); }
+};
 
 struct TcConvDesc {
-    const float* src0; const float* src1; int c0p, c1p; int upsample; int H, W; int coutp; float* out; bool lrelu_first;
-    const float* scale; const float* shift; const float* bias; float* pool_out;
+    DnTensor src0, src1;                 // src1.base == nullptr: single source
+    int upsample;                        // sources live at half the output resolution
+    DnTensor out, pool_out;              // pool_out.base == nullptr: no fused MaxPool
+    bool lrelu_first;
+    const float* scale; const float* shift; const float* bias;
     bool round_out = true;               // round stored activations to tf32 (all layers but the last)
+    const float* shared_wpack = nullptr; // reuse another plan's packed weights (same layer, other hidden-state parity)
+};
+
+// Row-strip (multi-GPU) coupling of one conv launch, see ptd_dn.cu "row strips".  All pointers may be null (single GPU).
+struct TcStripLink {
+    DnTensor out_up, out_down;           // the neighbour strips' copies of `out` (peer memory): our first / last row -> their apron
+    DnTensor pool_up, pool_down;
+    uint32_t* sig[4];                    // flags in the neighbours' memory: out->up, out->down, pool->up, pool->down
+    const uint32_t* wait[4];             // local flags: src0 from up, src0 from down, src1 from up, src1 from down
+    uint32_t wait_epoch[4];
+    uint32_t* done;                      // local CTA-completion counter of this layer (monotonic)
+    uint32_t epoch;                      // frame sequence number written to the flags
 };
 
 struct __align__(64) TcParams {
-    CUtensorMap mapA0, mapA1, mapB;
+    CUtensorMap mapA0, mapA1;
+    const float* wpack;                  // packed weights, stage-major
     int n0, n1;                          // 16-channel chunks of source 0 / source 1
     int ntaps, nphases;
     int dy[4][9], dx[4][9];
     int tiles_x, tiles_y, total_items;
     int Hs, Ws;                          // tile domain (= source resolution)
-    int out_stride, Wout;
+    int out_mul;                         // 1, or 2 for the upsampling layers
     int coutp;
+    int stages, resident;                // smem pipeline depth; weights resident in smem (1) or streamed per stage (0)
+    uint32_t b_stage_bytes;              // ntaps * coutp * 64
+    uint32_t w_total_bytes;
     const float* scale; const float* shift; const float* bias;
     int lrelu_first, round_out;
-    float* out; float* pool_out;
+    DnTensor out, pool_out;
+    TcStripLink link;
 };
 
 struct TcConvPlan {
@@ -88,23 +127,23 @@ __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, u
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
                  ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-                 ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+__device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-// K-major operand tile with 64-byte swizzle: rows 64 B apart, 8-row groups 512 B apart (SBO), descriptor version 1 (sm_100)
-__device__ __forceinline__ uint64_t make_desc_sw64(uint32_t saddr) {
+// K-major operand without swizzle: core matrix = 8 rows x 16 B (128 contiguous bytes); LBO = byte distance between the core
+// matrices adjacent in K, SBO = between the 8-row groups adjacent in M / N; descriptor version 1 (sm_100), layout type 0
+__device__ __forceinline__ uint64_t make_desc_nosw(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
     uint64_t d = 0;
     d |= (uint64_t)((saddr & 0x3FFFF) >> 4);            // start address, bits [0,14)
-    d |= (uint64_t)1 << 16;                              // leading byte offset (unused for swizzled K-major), bits [16,30)
-    d |= (uint64_t)(512 >> 4) << 32;                     // stride byte offset, bits [32,46)
+    d |= (uint64_t)((lbo >> 4) & 0x3FFF) << 16;         // leading byte offset, bits [16,30)
+    d |= (uint64_t)((sbo >> 4) & 0x3FFF) << 32;         // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                              // descriptor version
-    d |= (uint64_t)4 << 61;                              // layout type SWIZZLE_64B
     return d;
 }
 __device__ __forceinline__ void mma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
@@ -125,6 +164,14 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t* r) {
                  : "r"(taddr));
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ float round_tf32(float x) {
     uint32_t r;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -132,28 +179,31 @@ __device__ __forceinline__ float round_tf32(float x) {
 }
 }  // namespace tc
 
+// shared memory carve-up (offsets from the 1024-aligned base): [A stage 0..S) | B (resident: whole layer; streamed: S stages) | barriers
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
-    uint64_t* full = (uint64_t*)(smem + TC_STAGES * TC_STAGE_BYTES);
-    uint64_t* empty = full + TC_STAGES;
-    uint64_t* tmem_full = empty + TC_STAGES;
+    uint8_t* smem_a = smem;
+    uint8_t* smem_b = smem + (size_t)p.stages * TC_A_BYTES;
+    const size_t b_bytes = p.resident ? (size_t)p.w_total_bytes : (size_t)p.stages * p.b_stage_bytes;
+    uint64_t* full = (uint64_t*)(smem_b + ((b_bytes + 15) & ~(size_t)15));
+    uint64_t* empty = full + TC_MAX_STAGES;
+    uint64_t* tmem_full = empty + TC_MAX_STAGES;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_base_slot = (uint32_t*)(tmem_empty + 2);
+    uint64_t* wfull = tmem_empty + 2;
+    uint32_t* tmem_base_slot = (uint32_t*)(wfull + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = p.n0 + p.n1;
-    const int nstages_item = p.ntaps * nchunks;
-    const uint32_t stage_tx = TC_A_BYTES + (uint32_t)p.coutp * 64u;
 
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&p.mapA0);
         if (p.n1) tc::prefetch_tmap(&p.mapA1);
-        tc::prefetch_tmap(&p.mapB);
     }
     if (warp == 1 && lane == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
+        for (int s = 0; s < TC_MAX_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
         for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 128); }
+        tc::mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -168,21 +218,33 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (warp == 0) {
         // ===== TMA producer ==================================================================================
         if (lane == 0) {
+            // row-strip mode: the apron rows of the sources are written by the neighbour GPUs; wait for this frame's flags
+            bool waited = false;
+            for (int i = 0; i < 4; ++i)
+                if (p.link.wait[i]) { while ((int)(tc::ld_acquire_sys(p.link.wait[i]) - p.link.wait_epoch[i]) < 0) { } waited = true; }
+            if (waited) asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (TMA) reads
+            if (p.resident) {                                        // the layer's whole weight set, once per CTA
+                tc::mbar_expect_tx(wfull, p.w_total_bytes);
+                for (uint32_t off = 0; off < p.w_total_bytes; off += 32768u) {
+                    const uint32_t n = p.w_total_bytes - off < 32768u ? p.w_total_bytes - off : 32768u;
+                    tc::bulk_load(smem_b + off, (const uint8_t*)p.wpack + off, n, wfull);
+                }
+            }
             int stage = 0; uint32_t phase = 0;
+            const uint32_t stage_tx = TC_A_BYTES + (p.resident ? 0u : p.b_stage_bytes);
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
                 const int ph = item % p.nphases, tile = item / p.nphases;
                 const int x0 = (tile % p.tiles_x) * TC_TILE_W, y0 = (tile / p.tiles_x) * TC_TILE_H;
-                for (int t = 0; t < p.ntaps; ++t) {
-                    const int yy = y0 + p.dy[ph][t], xx = x0 + p.dx[ph][t];
-                    for (int c = 0; c < nchunks; ++c) {
-                        tc::mbar_wait(&empty[stage], phase ^ 1);
-                        uint8_t* sa = smem + stage * TC_STAGE_BYTES;
-                        tc::mbar_expect_tx(&full[stage], stage_tx);
-                        if (c < p.n0) tc::tma_load_3d(sa, &p.mapA0, &full[stage], c * 16, xx, yy);
-                        else tc::tma_load_3d(sa, &p.mapA1, &full[stage], (c - p.n0) * 16, xx, yy);
-                        tc::tma_load_2d(sa + TC_A_BYTES, &p.mapB, &full[stage], 0, ((ph * p.ntaps + t) * nchunks + c) * p.coutp);
-                        if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
-                    }
+                for (int c = 0; c < nchunks; ++c) {
+                    tc::mbar_wait(&empty[stage], phase ^ 1);
+                    tc::mbar_expect_tx(&full[stage], stage_tx);
+                    // halo tile origin: pixel (x0 - 1, y0 - 1) = buffer row y0 (apron offset +1); x < 0 / x >= W are zero filled
+                    if (c < p.n0) tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, &p.mapA0, &full[stage], (x0 - 1) * 4, y0, c * 4);
+                    else tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, &p.mapA1, &full[stage], (x0 - 1) * 4, y0, (c - p.n0) * 4);
+                    if (!p.resident)
+                        tc::bulk_load(smem_b + (size_t)stage * p.b_stage_bytes, (const uint8_t*)p.wpack + (size_t)(ph * nchunks + c) * p.b_stage_bytes,
+                                      p.b_stage_bytes, &full[stage]);
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -191,39 +253,52 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (lane == 0) {
             // instruction descriptor: D = f32, A = B = tf32, both K-major, N = coutp, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.coutp >> 3) << 17) | ((128u >> 4) << 24);
+            const uint32_t b_lbo = (uint32_t)p.coutp * 16u;                 // K-adjacent core matrices of B: one quad block of N rows
+            const uint32_t b_kstep = (uint32_t)p.coutp * 32u;               // one K = 8 step of one tap
+            if (p.resident) { tc::mbar_wait(wfull, 0); tc::fence_after_sync(); }
             int stage = 0; uint32_t phase = 0;
             int acc = 0; uint32_t acc_phase = 0;
             for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+                const int ph = item % p.nphases;
                 tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
                 tc::fence_after_sync();
                 const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_COLS;
-                for (int s = 0; s < nstages_item; ++s) {
+                for (int c = 0; c < nchunks; ++c) {
                     tc::mbar_wait(&full[stage], phase);
                     tc::fence_after_sync();
-                    const uint32_t sa = tc::smem_u32(smem + stage * TC_STAGE_BYTES);
-                    const uint64_t adesc = tc::make_desc_sw64(sa), bdesc = tc::make_desc_sw64(sa + TC_A_BYTES);
-                    tc::mma_tf32(d_tmem, adesc, bdesc, idesc, s > 0 ? 1u : 0u);
-                    tc::mma_tf32(d_tmem, adesc + 2, bdesc + 2, idesc, 1u);            // +32 B along K inside the swizzle row
+                    const uint32_t sa = tc::smem_u32(smem_a + (size_t)stage * TC_A_BYTES);
+                    const uint32_t sb = tc::smem_u32(smem_b) + (p.resident ? (uint32_t)(ph * nchunks + c) : (uint32_t)stage) * p.b_stage_bytes;
+                    for (int t = 0; t < p.ntaps; ++t) {
+                        const uint32_t a_tap = sa + (uint32_t)((1 + p.dy[ph][t]) * TC_ROW_PITCH + (1 + p.dx[ph][t]) * 16);
+                        const uint32_t b_tap = sb + (uint32_t)t * 2u * b_kstep;
+#pragma unroll
+                        for (int j = 0; j < 2; ++j) {
+                            const uint64_t adesc = tc::make_desc_nosw(a_tap + (uint32_t)j * 2u * TC_QUAD_PITCH, TC_QUAD_PITCH, TC_ROW_PITCH);
+                            const uint64_t bdesc = tc::make_desc_nosw(b_tap + (uint32_t)j * b_kstep, b_lbo, 128u);
+                            tc::mma_tf32(d_tmem, adesc, bdesc, idesc, (c | t | j) ? 1u : 0u);
+                        }
+                    }
                     tc::mma_commit(&empty[stage]);                                    // frees the smem stage when the MMAs retire
-                    if (s == nstages_item - 1) tc::mma_commit(&tmem_full[acc]);       // accumulator complete -> epilogue
-                    if (++stage == TC_STAGES) { stage = 0; phase ^= 1; }
+                    if (c == nchunks - 1) tc::mma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
     } else if (warp >= 4) {
-        // ===== epilogue: TMEM -> registers -> bias/BN/LeakyReLU -> NHWC ============================================
+        // ===== epilogue: TMEM -> registers -> bias/BN/LeakyReLU -> CHW4 ============================================
         const int q = warp & 3;                                    // TMEM lane quarter this warp may read
         const int m = q * 32 + lane;                               // pixel of the tile == TMEM lane
-        const int ty = m >> 4, tx = m & 15;
+        const int ty = m >> 3, tx = m & 7;
+        const size_t oqs = p.out.quad_stride(), pqs = p.pool_out.quad_stride();
         int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const int ph = item % p.nphases, tile = item / p.nphases;
             const int x = (tile % p.tiles_x) * TC_TILE_W + tx, y = (tile / p.tiles_x) * TC_TILE_H + ty;
             const bool valid = x < p.Ws && y < p.Hs;
-            const int oy = p.out_stride * y + (p.nphases > 1 ? (ph >> 1) : 0), ox = p.out_stride * x + (p.nphases > 1 ? (ph & 1) : 0);
-            float* orow = p.out + ((size_t)oy * p.Wout + ox) * p.coutp;
-            float* prow = p.pool_out ? p.pool_out + ((size_t)(y >> 1) * (p.Wout >> 1) + (x >> 1)) * p.coutp : nullptr;
+            const int oy = p.out_mul * y + (p.nphases > 1 ? (ph >> 1) : 0), ox = p.out_mul * x + (p.nphases > 1 ? (ph & 1) : 0);
+            float* orow = p.out.base + ((size_t)(oy + 1) * p.out.W + ox) * 4;
+            float* prow = p.pool_out.base ? p.pool_out.base + ((size_t)((y >> 1) + 1) * p.pool_out.W + (x >> 1)) * 4 : nullptr;
             tc::mbar_wait(&tmem_full[acc], acc_phase);
             tc::fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_ACC_COLS;
@@ -242,20 +317,45 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     o[j] = p.round_out ? tc::round_tf32(v) : v;
                 }
                 if (valid) {
-                    float4* d = reinterpret_cast<float4*>(orow + c0);
-                    d[0] = make_float4(o[0], o[1], o[2], o[3]); d[1] = make_float4(o[4], o[5], o[6], o[7]);
-                    d[2] = make_float4(o[8], o[9], o[10], o[11]); d[3] = make_float4(o[12], o[13], o[14], o[15]);
+#pragma unroll
+                    for (int qd = 0; qd < 4; ++qd)
+                        *reinterpret_cast<float4*>(orow + (size_t)(c0 / 4 + qd) * oqs) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
+                    // row-strip mode: our first / last row is the neighbour's bottom / top apron row - stored straight over NVLink
+                    if (oy == 0 && p.link.out_up.base) {
+                        float* d = p.link.out_up.base + ((size_t)(p.link.out_up.rows + 1) * p.out.W + ox) * 4;
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd)
+                            *reinterpret_cast<float4*>(d + (size_t)(c0 / 4 + qd) * p.link.out_up.quad_stride()) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
+                    }
+                    if (oy == p.out.rows - 1 && p.link.out_down.base) {
+                        float* d = p.link.out_down.base + (size_t)ox * 4;
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd)
+                            *reinterpret_cast<float4*>(d + (size_t)(c0 / 4 + qd) * p.link.out_down.quad_stride()) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
+                    }
                 }
-                if (p.pool_out) {                                  // MaxPool2d(2): partners are lanes ^1 (x) and ^16 (y)
+                if (prow) {                                        // MaxPool2d(2): partners are lanes ^1 (x) and ^8 (y)
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         float v = fmaxf(o[j], __shfl_xor_sync(0xffffffffu, o[j], 1));
-                        o[j] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 16));
+                        o[j] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
                     }
                     if (valid && !(tx & 1) && !(ty & 1)) {
-                        float4* d = reinterpret_cast<float4*>(prow + c0);
-                        d[0] = make_float4(o[0], o[1], o[2], o[3]); d[1] = make_float4(o[4], o[5], o[6], o[7]);
-                        d[2] = make_float4(o[8], o[9], o[10], o[11]); d[3] = make_float4(o[12], o[13], o[14], o[15]);
+#pragma unroll
+                        for (int qd = 0; qd < 4; ++qd)
+                            *reinterpret_cast<float4*>(prow + (size_t)(c0 / 4 + qd) * pqs) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
+                        if ((y >> 1) == 0 && p.link.pool_up.base) {
+                            float* d = p.link.pool_up.base + ((size_t)(p.link.pool_up.rows + 1) * p.pool_out.W + (x >> 1)) * 4;
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd)
+                                *reinterpret_cast<float4*>(d + (size_t)(c0 / 4 + qd) * p.link.pool_up.quad_stride()) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
+                        }
+                        if ((y >> 1) == p.pool_out.rows - 1 && p.link.pool_down.base) {
+                            float* d = p.link.pool_down.base + (size_t)(x >> 1) * 4;
+#pragma unroll
+                            for (int qd = 0; qd < 4; ++qd)
+                                *reinterpret_cast<float4*>(d + (size_t)(c0 / 4 + qd) * p.link.pool_down.quad_stride()) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
+                        }
                     }
                 }
             }
@@ -264,8 +364,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
+    if (p.link.done && warp >= 4) __threadfence_system();          // our apron stores into the neighbours' memory, before the flag
     tc::fence_before_sync();
     __syncthreads();
+    if (p.link.done && threadIdx.x == 0) {
+        // last CTA of the launch: every CTA's stores are ordered before its counter increment, so the flags can be raised
+        __threadfence();
+        const uint32_t old = atomicAdd(p.link.done, 1u);
+        if ((old + 1u) % gridDim.x == 0u) {
+            __threadfence_system();
+            for (int i = 0; i < 4; ++i)
+                if (p.link.sig[i]) tc::st_release_sys(p.link.sig[i], p.link.epoch);
+        }
+    }
     if (warp == 2) {
         tc::fence_after_sync();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
@@ -298,16 +409,17 @@ static float host_round_tf32(float x) {            // round-to-nearest (ties awa
     return r;
 }
 
-static ptd_status tc_make_map_act(CUtensorMap* map, const float* base, int cp, int W, int H) {
+// tensor map over a CHW4 activation: dims (W * 4 floats, rows + 2, quads); box = the 10 x 18 halo tile of 4 quads
+static ptd_status tc_make_map_act(CUtensorMap* map, const DnTensor& t) {
     PFN_encodeTiled enc = tc_get_encode();
     if (!enc) PTD_FAIL(PTD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[3] = {(cuuint64_t)cp, (cuuint64_t)W, (cuuint64_t)H};
-    cuuint64_t strides[2] = {(cuuint64_t)cp * 4, (cuuint64_t)W * cp * 4};
-    cuuint32_t box[3] = {16, TC_TILE_W, TC_TILE_H};
+    cuuint64_t dims[3] = {(cuuint64_t)t.W * 4, (cuuint64_t)t.rows + 2, (cuuint64_t)t.cp / 4};
+    cuuint64_t strides[2] = {(cuuint64_t)t.W * 16, (cuuint64_t)(t.rows + 2) * t.W * 16};
+    cuuint32_t box[3] = {TC_HALO_W * 4, TC_HALO_H, 4};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) PTD_FAIL(PTD_ERR_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", H, W, cp, (int)r);
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)t.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) PTD_FAIL(PTD_ERR_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", t.rows, t.W, t.cp, (int)r);
     return PTD_OK;
 }
 
@@ -315,21 +427,28 @@ inline void tc_plan_destroy(TcConvPlan& plan) { plan.valid = 0; }
 
 // w9: [9][cinp][coutp] fp32 (padded, zero-filled); builds the packed tf32 weights, the tensor maps and the launch shape.
 inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& w9, int cinp, TcConvPlan& plan, std::vector<void*>& allocs) {
-    if (d.coutp % 16 || d.coutp < 16 || d.coutp > TC_ACC_COLS || d.c0p % 16 || d.c1p % 16)
-        PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: channel padding %d/%d -> %d unsupported", d.c0p, d.c1p, d.coutp);
+    const int coutp = d.out.cp;
+    const int c0p = d.src0.cp, c1p = d.src1.base ? d.src1.cp : 0;
+    if (coutp % 16 || coutp < 16 || coutp > TC_ACC_COLS || c0p % 16 || c1p % 16 || c0p + c1p != cinp)
+        PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: channel padding %d/%d -> %d unsupported", c0p, c1p, coutp);
     TcParams& p = plan.p;
     memset(&p, 0, sizeof p);
-    p.n0 = d.c0p / 16; p.n1 = d.c1p / 16;
+    p.n0 = c0p / 16; p.n1 = c1p / 16;
     const int nch = p.n0 + p.n1;
-    const int Hs = d.upsample ? d.H / 2 : d.H, Ws = d.upsample ? d.W / 2 : d.W;
-    p.Hs = Hs; p.Ws = Ws; p.Wout = d.W; p.out_stride = d.upsample ? 2 : 1;
+    const int Hs = d.src0.rows, Ws = d.src0.W;
+    if (d.upsample ? (d.out.rows != 2 * Hs || d.out.W != 2 * Ws) : (d.out.rows != Hs || d.out.W != Ws))
+        PTD_FAIL(PTD_ERR_ARG, "tc conv: source %dx%d does not match output %dx%d", Hs, Ws, d.out.rows, d.out.W);
+    if (d.src1.base && (d.src1.rows != Hs || d.src1.W != Ws)) PTD_FAIL(PTD_ERR_ARG, "tc conv: concat sources differ in size");
+    p.Hs = Hs; p.Ws = Ws; p.out_mul = d.upsample ? 2 : 1;
     p.nphases = d.upsample ? 4 : 1; p.ntaps = d.upsample ? 4 : 9;
-    p.coutp = d.coutp; p.scale = d.scale; p.shift = d.shift; p.bias = d.bias; p.lrelu_first = d.lrelu_first; p.round_out = d.round_out;
+    p.coutp = coutp; p.scale = d.scale; p.shift = d.shift; p.bias = d.bias; p.lrelu_first = d.lrelu_first; p.round_out = d.round_out;
     p.out = d.out; p.pool_out = d.pool_out;
     p.tiles_x = (Ws + TC_TILE_W - 1) / TC_TILE_W; p.tiles_y = (Hs + TC_TILE_H - 1) / TC_TILE_H;
     p.total_items = p.tiles_x * p.tiles_y * p.nphases;
-    // taps and packed weights  B[((phase * ntaps + tap) * nch + chunk) * coutp + n][16]
-    std::vector<float> pack((size_t)p.nphases * p.ntaps * nch * d.coutp * 16, 0.f);
+    p.b_stage_bytes = (uint32_t)(p.ntaps * coutp * 64);
+    p.w_total_bytes = (uint32_t)(p.nphases * nch) * p.b_stage_bytes;
+    // packed weights: [phase][chunk][tap][kstep j][k quad][n / 8][n % 8][4 floats]  (see make_desc_nosw)
+    std::vector<float> pack((size_t)p.w_total_bytes / 4, 0.f);
     for (int ph = 0; ph < p.nphases; ++ph) {
         for (int t = 0; t < p.ntaps; ++t) {
             int kys[3], kxs[3], nky = 0, nkx = 0;
@@ -346,40 +465,46 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
                 else { if (tj == 0) { kxs[nkx++] = 0; kxs[nkx++] = 1; } else kxs[nkx++] = 2; }
             }
             for (int c = 0; c < cinp; ++c)
-                for (int n = 0; n < d.coutp; ++n) {
+                for (int n = 0; n < coutp; ++n) {
                     float s = 0.f;
                     for (int i = 0; i < nky; ++i)
-                        for (int j = 0; j < nkx; ++j) s += w9[((size_t)(kys[i] * 3 + kxs[j]) * cinp + c) * d.coutp + n];
-                    pack[((((size_t)ph * p.ntaps + t) * nch + c / 16) * d.coutp + n) * 16 + c % 16] = host_round_tf32(s);
+                        for (int j = 0; j < nkx; ++j) s += w9[((size_t)(kys[i] * 3 + kxs[j]) * cinp + c) * coutp + n];
+                    const int chunk = c / 16, kstep = (c % 16) / 8, kq = (c % 8) / 4, ke = c % 4;
+                    const size_t off = ((((size_t)(ph * nch + chunk) * p.ntaps + t) * 2 + kstep) * 2 + kq) * (size_t)coutp * 4 + (size_t)n * 4 + ke;
+                    pack[off] = host_round_tf32(s);
                 }
         }
     }
-    void* dw = nullptr;
-    if (cudaMalloc(&dw, pack.size() * 4) != cudaSuccess) PTD_FAIL(PTD_ERR_CUDA, "tc conv: cudaMalloc(weights) failed");
-    allocs.push_back(dw);
-    cudaMemcpy(dw, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice);
-    plan.d_wpack = (float*)dw;
-    ptd_status rc = tc_make_map_act(&p.mapA0, d.src0, d.c0p, Ws, Hs);
-    if (rc != PTD_OK) return rc;
-    if (p.n1) { rc = tc_make_map_act(&p.mapA1, d.src1, d.c1p, Ws, Hs); if (rc != PTD_OK) return rc; }
-    else p.mapA1 = p.mapA0;
-    {
-        PFN_encodeTiled enc = tc_get_encode();
-        cuuint64_t dims[2] = {16, (cuuint64_t)p.nphases * p.ntaps * nch * d.coutp};
-        cuuint64_t strides[1] = {64};
-        cuuint32_t box[2] = {16, (cuuint32_t)d.coutp};
-        cuuint32_t estr[2] = {1, 1};
-        CUresult r = enc(&p.mapB, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, dw, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                         CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        if (r != CUDA_SUCCESS) PTD_FAIL(PTD_ERR_CUDA, "cuTensorMapEncodeTiled(weights) failed: %d", (int)r);
+    void* dw = (void*)d.shared_wpack;
+    if (!dw) {
+        if (cudaMalloc(&dw, pack.size() * 4) != cudaSuccess) PTD_FAIL(PTD_ERR_CUDA, "tc conv: cudaMalloc(weights) failed");
+        allocs.push_back(dw);
+        cudaMemcpy(dw, pack.data(), pack.size() * 4, cudaMemcpyHostToDevice);
     }
+    plan.d_wpack = (float*)dw;
+    p.wpack = plan.d_wpack;
+    ptd_status rc = tc_make_map_act(&p.mapA0, d.src0);
+    if (rc != PTD_OK) return rc;
+    if (p.n1) { rc = tc_make_map_act(&p.mapA1, d.src1); if (rc != PTD_OK) return rc; }
+    else p.mapA1 = p.mapA0;
+    // shared memory plan: resident weights when they leave room for >= 4 A stages
+    const size_t budget = TC_SMEM_BUDGET;
+    if ((size_t)p.w_total_bytes + 4 * TC_A_BYTES <= budget) {
+        p.resident = 1;
+        p.stages = (int)std::min<size_t>(TC_MAX_STAGES, (budget - p.w_total_bytes) / TC_A_BYTES);
+    } else {
+        p.resident = 0;
+        p.stages = (int)std::min<size_t>(TC_MAX_STAGES, budget / (TC_A_BYTES + p.b_stage_bytes));
+        if (p.stages < 2) PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: a stage of %u B does not fit twice in shared memory", TC_A_BYTES + p.b_stage_bytes);
+    }
+    const size_t b_bytes = p.resident ? (size_t)p.w_total_bytes : (size_t)p.stages * p.b_stage_bytes;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     plan.grid = p.total_items < sms ? p.total_items : sms;
-    plan.smem = (size_t)TC_STAGES * TC_STAGE_BYTES + 1024 + 256;
-    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan.smem) != cudaSuccess)
-        PTD_FAIL(PTD_ERR_CUDA, "tc conv: cannot reserve %zu B of shared memory: %s", plan.smem, cudaGetErrorString(cudaGetLastError()));
+    plan.smem = (size_t)p.stages * TC_A_BYTES + ((b_bytes + 15) & ~(size_t)15) + 1024 + 512;
+    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess)
+        PTD_FAIL(PTD_ERR_CUDA, "tc conv: cannot reserve shared memory: %s", cudaGetErrorString(cudaGetLastError()));
     plan.valid = 1;
     return PTD_OK;
 }
@@ -388,6 +513,6 @@ inline ptd_status tc_conv_launch(TcConvPlan& plan, cudaStream_t st, int* launche
     if (!plan.valid) PTD_FAIL(PTD_ERR_STATE, "tc conv: plan not built");
     conv_tc_kernel<<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.p);
     if (launches) ++*launches;
-    if (pooled) *pooled = plan.p.pool_out != nullptr;
+    if (pooled) *pooled = plan.p.pool_out.base != nullptr;
     return PTD_OK;
 }

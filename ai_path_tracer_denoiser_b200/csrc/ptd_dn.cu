@@ -5,14 +5,19 @@
 // 5 x MaxPool2, 5 x nearest Upsample x2, 11 x channel concat, 6 recurrent hidden states - with eval-mode BN and carried
 // hidden state (SURVEY.md decisions D1, D3).
 //
-// Data layout in HBM: every activation is NHWC fp32 with the channel count padded to a multiple of 16 (10->16, 32, 43->48,
-// 57->64, 76->80, 101->112, 3->16; pad channels are kept at exactly 0), so one pixel's channels are one contiguous,
-// 64-byte-aligned run: coalesced for the CUDA-core path and a legal TMA box for the tensor-core path.  Concats and the
-// decoder's upsample are never materialised (the convs read two sources / index at half resolution); conv bias, BN and
-// LeakyReLU are folded into the conv epilogue.  Two conv engines share the buffers and the layer graph:
+// Data layout in HBM ("CHW4"): every activation is fp32 channel-quad planes [C/4][rows + 2][W][4] with the channel count padded
+// to a multiple of 16 (10->16, 32, 43->48, 57->64, 76->80, 101->112, 3->16; pad channels are kept at exactly 0) and one zero
+// apron row above and below the image (conv padding in y; the halo slots of the multi-GPU row-strip mode).  A pixel's four
+// channels of a quad are one 16-byte vector and a row of a quad is contiguous, so (a) CUDA-core loads / stores are float4 and
+// coalesced along x and (b) a TMA box of a halo tile lands in shared memory directly in the canonical no-swizzle K-major UMMA
+// layout (dn_conv_tc.cuh).  Concats and the decoder's upsample are never materialised (the convs read two sources / index at
+// half resolution); conv bias, BN and LeakyReLU are folded into the conv epilogue.  Two conv engines share the buffers and
+// the layer graph:
 //   PTD_DN_FP32  conv3x3_fp32   - implicit-GEMM on CUDA cores (FFMA), strict-parity path;
 //   PTD_DN_TF32  dn_conv_tc.cuh - TMA-staged tiles + tcgen05.mma kind::tf32 with TMEM accumulators.
 #include <cuda_runtime.h>
+#include <unistd.h>
+#include <algorithm>
 #include <cstdint>
 #include <cstring>
 #include <cmath>
@@ -37,14 +42,13 @@
 #define FC_PS (10 * FC_RS)
 
 struct FpConvArgs {
-    const float* src0; const float* src1;   // NHWC, padded channel counts c0p / c1p (src1 may be null)
-    int c0p, c1p;
+    DnTensor src0, src1;                    // CHW4 (src1.base may be null)
     int upsample;                           // sources live at (H/2, W/2): nearest x2 (model.py:40)
     int H, W;                               // output (= conv input) resolution
     const float* w;                         // [9][c0p + c1p][coutp]
     const float* scale; const float* shift; const float* bias;   // [coutp]
-    int coutp; int order;                   // 0: lrelu(scale*acc + shift)   1: scale*lrelu(acc + bias) + shift
-    float* out;                             // NHWC [H][W][coutp]
+    int order;                              // 0: lrelu(scale*acc + shift)   1: scale*lrelu(acc + bias) + shift
+    DnTensor out;
 };
 
 __global__ void __launch_bounds__(128) conv3x3_fp32(const FpConvArgs a) {
@@ -54,8 +58,8 @@ __global__ void __launch_bounds__(128) conv3x3_fp32(const FpConvArgs a) {
     const int x0 = blockIdx.x * FC_TW, y0 = blockIdx.y * FC_TH, co0 = blockIdx.z * FC_BN;
     const int col = lane & 15, rbase = (lane >> 4) * 4;     // thread's pixels: rows rbase..rbase+3 of the tile, column col
     const int cg = warp * 8;                                  // thread's 8 output channels inside the 32-wide tile
-    const int cin = a.c0p + a.c1p;
-    const int sH = a.upsample ? a.H >> 1 : a.H, sW = a.upsample ? a.W >> 1 : a.W;
+    const int c0p = a.src0.cp, c1p = a.src1.base ? a.src1.cp : 0, coutp = a.out.cp;
+    const int cin = c0p + c1p;
     float acc[4][8];
 #pragma unroll
     for (int i = 0; i < 4; ++i)
@@ -63,17 +67,17 @@ __global__ void __launch_bounds__(128) conv3x3_fp32(const FpConvArgs a) {
         for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
 
     for (int c0 = 0; c0 < cin; c0 += FC_CK) {
-        const float* src = c0 < a.c0p ? a.src0 : a.src1;
-        const int cs = c0 < a.c0p ? c0 : c0 - a.c0p, cp = c0 < a.c0p ? a.c0p : a.c1p;
+        const DnTensor& src = c0 < c0p ? a.src0 : a.src1;
+        const int cs = c0 < c0p ? c0 : c0 - c0p;
         __syncthreads();
-        // halo tile: 10 x 18 pixels x 8 channels (two float4 per pixel), zero outside the image (padding = 1)
+        // halo tile: 10 x 18 pixels x 8 channels (two quads per pixel), zero outside the image (padding = 1)
         for (int i = tid; i < 10 * 18 * 2; i += 128) {
-            const int half = i & 1, pix = i >> 1, r = pix / 18, c = pix % 18;
+            const int half = i / (10 * 18), pix = i % (10 * 18), r = pix / 18, c = pix % 18;
             const int gy = y0 + r - 1, gx = x0 + c - 1;
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W) {
                 const int sy = a.upsample ? gy >> 1 : gy, sx = a.upsample ? gx >> 1 : gx;
-                v = __ldg(reinterpret_cast<const float4*>(src + ((size_t)sy * sW + sx) * cp + cs + half * 4));
+                v = __ldg(reinterpret_cast<const float4*>(src.base + (size_t)(cs / 4 + half) * src.quad_stride() + ((size_t)(sy + 1) * src.W + sx) * 4));
             }
             float* d = s_in + (half * 4) * FC_PS + r * FC_RS + c;
             d[0] = v.x; d[FC_PS] = v.y; d[2 * FC_PS] = v.z; d[3 * FC_PS] = v.w;
@@ -82,7 +86,7 @@ __global__ void __launch_bounds__(128) conv3x3_fp32(const FpConvArgs a) {
         for (int i = tid; i < 9 * FC_CK * FC_BN / 4; i += 128) {
             const int j4 = i % (FC_BN / 4), c = (i / (FC_BN / 4)) % FC_CK, tap = i / (FC_BN / 4 * FC_CK);
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (co0 + j4 * 4 < a.coutp) v = __ldg(reinterpret_cast<const float4*>(a.w + ((size_t)tap * cin + c0 + c) * a.coutp + co0 + j4 * 4));
+            if (co0 + j4 * 4 < coutp) v = __ldg(reinterpret_cast<const float4*>(a.w + ((size_t)tap * cin + c0 + c) * coutp + co0 + j4 * 4));
             reinterpret_cast<float4*>(s_w)[i] = v;
         }
         __syncthreads();
@@ -110,7 +114,7 @@ __global__ void __launch_bounds__(128) conv3x3_fp32(const FpConvArgs a) {
         }
     }
     const int co = co0 + cg;
-    if (co >= a.coutp) return;
+    if (co >= coutp) return;
     float sc[8], sh[8], bi[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { sc[j] = a.scale[co + j]; sh[j] = a.shift[co + j]; bi[j] = a.bias[co + j]; }
@@ -125,32 +129,35 @@ __global__ void __launch_bounds__(128) conv3x3_fp32(const FpConvArgs a) {
             if (a.order == 0) { float v = fmaf(acc[i][j], sc[j], sh[j]); o[j] = v > 0.f ? v : 0.1f * v; }
             else { float v = acc[i][j] + bi[j]; v = v > 0.f ? v : 0.1f * v; o[j] = fmaf(v, sc[j], sh[j]); }
         }
-        float4* dst = reinterpret_cast<float4*>(a.out + ((size_t)gy * a.W + gx) * a.coutp + co);
-        dst[0] = make_float4(o[0], o[1], o[2], o[3]);
-        dst[1] = make_float4(o[4], o[5], o[6], o[7]);
+        float* dst = a.out.base + (size_t)(co / 4) * a.out.quad_stride() + ((size_t)(gy + 1) * a.out.W + gx) * 4;
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+        *reinterpret_cast<float4*>(dst + a.out.quad_stride()) = make_float4(o[4], o[5], o[6], o[7]);
     }
 }
 
-// MaxPool2d(2) on NHWC (model.py:19): one thread = one output pixel x 4 channels
-__global__ void maxpool2_nhwc(const float* __restrict__ in, float* __restrict__ out, int Ho, int Wo, int cp) {
+// MaxPool2d(2) on CHW4 (model.py:19): one thread = one output pixel of one channel quad
+__global__ void maxpool2_chw4(const DnTensor in, const DnTensor out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    const int c4 = cp / 4;
-    if (i >= (size_t)Ho * Wo * c4) return;
-    const int c = (int)(i % c4), x = (int)((i / c4) % Wo), y = (int)(i / ((size_t)c4 * Wo));
-    const float4* p = reinterpret_cast<const float4*>(in) + ((size_t)(2 * y) * (2 * Wo) + 2 * x) * c4 + c;
-    const float4 a = p[0], b = p[c4], d = p[(size_t)2 * Wo * c4], e = p[(size_t)2 * Wo * c4 + c4];
-    reinterpret_cast<float4*>(out)[i] = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
-                                                    fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
+    const int nq = out.cp / 4, Ho = out.rows, Wo = out.W;
+    if (i >= (size_t)nq * Ho * Wo) return;
+    const int x = (int)(i % Wo), y = (int)((i / Wo) % Ho), q = (int)(i / ((size_t)Wo * Ho));
+    const float4* p = reinterpret_cast<const float4*>(in.base + (size_t)q * in.quad_stride()) + (size_t)(2 * y + 1) * in.W + 2 * x;
+    const float4 a = p[0], b = p[1], d = p[in.W], e = p[in.W + 1];
+    float4* o = reinterpret_cast<float4*>(out.base + (size_t)q * out.quad_stride()) + (size_t)(y + 1) * Wo + x;
+    *o = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
+                     fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
 }
-// planar G-buffer [10][H][W] rows [row0, row0+rows) -> NHWC16 [rows_p][Wp][16], zero padded (decision D3)
-__global__ void pack_gbuffer(const float* __restrict__ g, int H, int W, int Hp, int Wp, float* __restrict__ out, int round_tf32) {
+// planar G-buffer [10][H][W] -> CHW4 with 16 channels (4 quads): the strip's rows plus its two apron rows (frame rows row0 - 1 ..
+// row0 + rows), zero outside the frame and in the bottom / right padding (decision D3); thread = pixel
+__global__ void pack_gbuffer(const float* __restrict__ g, int H, int W, int row0, const DnTensor out, int round_tf32) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)Hp * Wp) return;
-    const int x = (int)(i % Wp), y = (int)(i / Wp);
+    const int Wp = out.W;
+    if (i >= (size_t)(out.rows + 2) * Wp) return;
+    const int x = (int)(i % Wp), br = (int)(i / Wp), y = row0 + br - 1;
     float v[16];
 #pragma unroll
     for (int c = 0; c < 16; ++c) v[c] = 0.f;
-    if (x < W && y < H) {
+    if (x < W && y >= 0 && y < H) {
 #pragma unroll
         for (int c = 0; c < 10; ++c) v[c] = g[(size_t)c * H * W + (size_t)y * W + x];
         if (round_tf32) {
@@ -158,24 +165,26 @@ __global__ void pack_gbuffer(const float* __restrict__ g, int H, int W, int Hp, 
             for (int c = 0; c < 10; ++c) v[c] = tc::round_tf32(v[c]);
         }
     }
-    float4* d = reinterpret_cast<float4*>(out + i * 16);
-    d[0] = make_float4(v[0], v[1], v[2], v[3]); d[1] = make_float4(v[4], v[5], v[6], v[7]);
-    d[2] = make_float4(v[8], v[9], v[10], v[11]); d[3] = make_float4(v[12], v[13], v[14], v[15]);
+    float* d = out.base + ((size_t)br * Wp + x) * 4;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(d + (size_t)q * out.quad_stride()) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
 }
-// NHWC16 -> planar [3][H][W], cropped
-__global__ void unpack_rgb(const float* __restrict__ in, int H, int W, int Wp, float* __restrict__ rgb) {
+// CHW4 quad 0 -> planar [3][H][W]: frame rows [r0, r0 + nrows) of this strip (tensor row 1 == frame row r0), cropped to W
+__global__ void unpack_rgb(const DnTensor in, int H, int W, int r0, int nrows, float* __restrict__ rgb) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= (size_t)H * W) return;
-    const int x = (int)(i % W), y = (int)(i / W);
-    const float4 v = *reinterpret_cast<const float4*>(in + ((size_t)y * Wp + x) * 16);
-    rgb[i] = v.x; rgb[(size_t)H * W + i] = v.y; rgb[(size_t)2 * H * W + i] = v.z;
+    if (i >= (size_t)nrows * W) return;
+    const int x = (int)(i % W), ry = (int)(i / W);
+    const float4 v = *reinterpret_cast<const float4*>(in.base + ((size_t)(ry + 1) * in.W + x) * 4);
+    const size_t o = (size_t)(r0 + ry) * W + x;
+    rgb[o] = v.x; rgb[(size_t)H * W + o] = v.y; rgb[(size_t)2 * H * W + o] = v.z;
 }
-// NHWC padded -> NCHW (hidden-state parity tap)
-__global__ void nhwc_to_nchw(const float* __restrict__ in, int C, int cp, int H, int W, float* __restrict__ out) {
+// CHW4 -> NCHW (hidden-state parity tap)
+__global__ void chw4_to_nchw(const DnTensor in, int C, float* __restrict__ out) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int H = in.rows, W = in.W;
     if (i >= (size_t)C * H * W) return;
     const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)(i / ((size_t)W * H));
-    out[i] = in[((size_t)y * W + x) * cp + c];
+    out[i] = in.base[(size_t)(c >> 2) * in.quad_stride() + ((size_t)(y + 1) * W + x) * 4 + (c & 3)];
 }
 
 // ---- weights ---------------------------------------------------------------------------------------------------------
@@ -203,57 +212,94 @@ static ptd_status read_ptdw(const char* path, std::map<std::string, std::vector<
 }
 
 // ---- handle ----------------------------------------------------------------------------------------------------------
+// Row strips (multi-GPU): a handle owns padded rows [row0, row0 + rows) of the frame, rows % 32 == 0, i.e.
+// rows >> l rows of every level-l tensor.  Every 3x3 conv needs one row of its inputs from the strip above and below; those
+// rows are the apron rows of the CHW4 tensors.  The producing conv's epilogue stores its first / last output row straight
+// into the neighbour GPU's apron (peer pointers from cudaIpcOpenMemHandle, NVLink) and the launch's last CTA raises a
+// per-tensor flag there (st.release.sys); the consuming conv's TMA producer spins on its local flags (ld.acquire.sys) before
+// the first load.  Flags carry the frame sequence number, so nothing is ever reset.  The six hidden states are double
+// buffered (frame k reads parity k & 1, writes the other): a neighbour that runs ahead can then never overwrite an apron
+// row that is still being read.  One strip covering the whole frame is the single-GPU case: aprons stay zero.
+#define DN_MAX_TENSORS 48
+struct ptd_strip_info {                      // POD, exchanged between the ranks as bytes (ptd_dn_strip_export / _connect)
+    unsigned char ipc[64];                   // cudaIpcMemHandle_t of the activation arena
+    unsigned long long arena;                // the arena's address in the owner's process (same-process connections)
+    int pid_tag, device, row0, rows, Hp, Wp, ntensors, reserved;
+    unsigned long long tensor_off[DN_MAX_TENSORS];   // byte offset of tensor i in the arena
+    int tensor_rows[DN_MAX_TENSORS];
+    unsigned long long flags_off;            // uint32 flags[ntensors][2] (from up, from down), 32-byte stride
+};
+
 struct DnLayer {
     DnLayerSpec spec;
-    int H, W;                       // output resolution
-    const float* src0; const float* src1; int c0p, c1p;
-    float* out; int coutp;
+    int H, W;                       // output resolution (this strip)
+    int src0, src1, out, pool;      // tensor ids (-1 = none); hidden-state ids are resolved per parity
     float* d_w9 = nullptr;          // [9][cin_p][coutp]  (CUDA-core engine)
     float* d_scale = nullptr; float* d_shift = nullptr; float* d_bias = nullptr;
-    TcConvPlan tc;                  // tensor-core engine plan (tensor maps, packed weights)
+    TcConvPlan tc[2];               // tensor-core engine plans, one per hidden-state parity
+    uint32_t* d_done = nullptr;
 };
 
 struct ptd_dn {
     int device = 0; unsigned flags = 0;
-    int H = 0, W = 0, Hp = 0, Wp = 0;
+    int H = 0, W = 0, Hp = 0, Wp = 0;           // frame, padded frame
+    int row0 = 0, rows = 0;                     // this strip (padded rows)
+    bool strip = false;
     std::vector<DnLayer> layers;
     std::vector<void*> allocs;
-    float* d_in16 = nullptr;        // packed input
+    unsigned char* arena = nullptr; size_t arena_bytes = 0;
+    std::vector<DnTensor> tensors;              // id -> tensor (base inside the arena)
+    std::vector<size_t> tensor_off;
+    size_t flags_off = 0;
+    int t_in16 = -1, t_hidden[6][2], t_final = -1;
+    int hidden_c[6] = {0};
     float* d_gbuf = nullptr; float* d_rgb = nullptr;   // staging for the host-pointer entry point
-    float* hidden[6] = {nullptr}; int hidden_c[6] = {0}; size_t hidden_bytes[6] = {0};
-    struct Pool { const float* in; float* out; int Ho, Wo, cp; };
-    std::vector<Pool> pools;        // pools[k] follows layer 3k+2
-    float* d_final = nullptr;
+    struct Pool { int in[2], out; };
+    std::vector<Pool> pools;        // pools[k] follows layer 3k+2 (CUDA-core engine only; the TC engine pools in its epilogue)
+    // neighbours
+    unsigned char* peer_arena[2] = {nullptr, nullptr};     // up, down
+    bool peer_ipc[2] = {false, false};
+    ptd_strip_info peer_info[2];
+    bool has_peer[2] = {false, false};
+    uint32_t epoch = 0;
+    int parity = 0;
     int launches = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> events;          // events[i], events[i+1] bracket launch i
     std::vector<std::string> launch_names;
     int timed_launches = 0;
+    uint32_t* flag(int tensor, int dir) const { return (uint32_t*)(arena + flags_off + ((size_t)tensor * 2 + dir) * 32); }
 };
 
 extern "C" void ptd_dn_destroy(ptd_dn* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (auto& L : h->layers) tc_plan_destroy(L.tc);
+    for (int d = 0; d < 2; ++d) if (h->peer_arena[d] && h->peer_ipc[d]) cudaIpcCloseMemHandle(h->peer_arena[d]);
+    for (auto& L : h->layers) { tc_plan_destroy(L.tc[0]); tc_plan_destroy(L.tc[1]); }
     for (void* p : h->allocs) cudaFree(p);
+    cudaFree(h->arena);
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     delete h;
 }
 
 static inline int cpad(int c) { return (c + 15) & ~15; }
 
-extern "C" ptd_status ptd_dn_create(const char* weights_path, int H, int W, int device, unsigned flags, ptd_dn** out) {
+static ptd_status dn_create(const char* weights_path, int H, int W, int row0, int rows, bool strip, int device, unsigned flags, ptd_dn** out) {
     if (!weights_path || !out || H <= 0 || W <= 0) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: bad argument");
     *out = nullptr;
     if (ptd_device_count() <= device || device < 0) PTD_FAIL(PTD_ERR_CUDA, "ptd_dn_create: CUDA device %d not available (no CPU fallback exists)", device);
+    if (flags == PTD_DN_3XTF32) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_dn_create: PTD_DN_3XTF32 is not built yet");
     if (flags != PTD_DN_FP32 && flags != PTD_DN_TF32) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: unknown flags %u", flags);
+    const int Hp = (H + 31) / 32 * 32, Wp = (W + 31) / 32 * 32;
+    if (!strip) { row0 = 0; rows = Hp; }
+    if (row0 < 0 || rows <= 0 || row0 % 32 || rows % 32 || row0 + rows > Hp) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create_strip: rows [%d, %d) must be multiples of 32 inside the padded frame of %d rows", row0, row0 + rows, Hp);
+    if (strip && flags != PTD_DN_TF32) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_dn_create_strip: row strips need the tensor-core engine (PTD_DN_TF32)");
     std::map<std::string, std::vector<float>> sd;
     ptd_status rc = read_ptdw(weights_path, sd);
     if (rc != PTD_OK) return rc;
     CUDA_TRY(cudaSetDevice(device));
     ptd_dn* h = new ptd_dn();
-    h->device = device; h->flags = flags; h->H = H; h->W = W;
-    h->Hp = (H + 31) / 32 * 32; h->Wp = (W + 31) / 32 * 32;
+    h->device = device; h->flags = flags; h->H = H; h->W = W; h->Hp = Hp; h->Wp = Wp; h->row0 = row0; h->rows = rows; h->strip = strip;
     auto fail = [&](ptd_status code) { ptd_dn_destroy(h); return code; };
     auto dalloc = [&](size_t floats) -> float* {
         void* p = nullptr;
@@ -263,66 +309,70 @@ extern "C" ptd_status ptd_dn_create(const char* weights_path, int H, int W, int 
         return (float*)p;
     };
 #define DALLOC(var, floats) do { (var) = dalloc(floats); if (!(var)) return fail(PTD_ERR_CUDA); } while (0)
-    const size_t px0 = (size_t)h->Hp * h->Wp;
-    DALLOC(h->d_in16, px0 * 16);
     DALLOC(h->d_gbuf, (size_t)10 * H * W);
     DALLOC(h->d_rgb, (size_t)3 * H * W);
 
-    std::vector<DnLayerSpec> specs = dn_layer_specs();
-    // activation buffers
+    // ---- activation arena: every tensor the convs read or write, one allocation (one IPC handle per strip) ----
+    size_t arena_bytes = 0;
+    auto tnew = [&](int c, int lvl) -> int {
+        DnTensor t;
+        t.cp = cpad(c); t.rows = rows >> lvl; t.W = Wp >> lvl;
+        h->tensors.push_back(t);
+        h->tensor_off.push_back(arena_bytes);
+        arena_bytes += (t.floats() * 4 + 1023) & ~(size_t)1023;
+        return (int)h->tensors.size() - 1;
+    };
+    h->t_in16 = tnew(10, 0);
     const int encC[6] = {32, 43, 57, 76, 101, 101};
-    float* out1[6]; float* mid[6]; float* pooled[5];
+    int out1[6], mid[6], pooled[5];
     for (int l = 0; l < 6; ++l) {
-        const size_t px = px0 >> (2 * l);
-        const int cp = cpad(encC[l]);
-        DALLOC(out1[l], px * cp); DALLOC(mid[l], px * cp); DALLOC(h->hidden[l], px * cp);
-        h->hidden_c[l] = encC[l]; h->hidden_bytes[l] = px * cp * 4;
-        if (l < 5) DALLOC(pooled[l], (px >> 2) * cp);
+        out1[l] = tnew(encC[l], l); mid[l] = tnew(encC[l], l);
+        h->t_hidden[l][0] = tnew(encC[l], l); h->t_hidden[l][1] = tnew(encC[l], l);
+        h->hidden_c[l] = encC[l];
+        if (l < 5) pooled[l] = tnew(encC[l], l + 1);
     }
     const int decC[5] = {76, 57, 43, 32, 3};          // dec5 .. dec1 outputs, at levels 4 .. 0
-    float* dc1[5]; float* dc2[5];
-    for (int i = 0; i < 5; ++i) {
-        const int lvl = 4 - i;
-        const size_t px = px0 >> (2 * lvl);
-        DALLOC(dc1[i], px * cpad(decC[i])); DALLOC(dc2[i], px * cpad(decC[i]));
-    }
-    h->d_final = dc2[4];
+    int dc1[5], dc2[5];
+    for (int i = 0; i < 5; ++i) { dc1[i] = tnew(decC[i], 4 - i); dc2[i] = tnew(decC[i], 4 - i); }
+    h->t_final = dc2[4];
+    if ((int)h->tensors.size() > DN_MAX_TENSORS) { ptd_set_error("ptd_dn_create: tensor table overflow"); return fail(PTD_ERR_STATE); }
+    h->flags_off = arena_bytes;
+    arena_bytes += h->tensors.size() * 2 * 32 + 1024;
+    if (cudaMalloc((void**)&h->arena, arena_bytes) != cudaSuccess) { ptd_set_error("ptd_dn_create: cudaMalloc(%zu B activation arena) failed: %s", arena_bytes, cudaGetErrorString(cudaGetLastError())); return fail(PTD_ERR_CUDA); }
+    h->arena_bytes = arena_bytes;
+    cudaMemset(h->arena, 0, arena_bytes);
+    for (size_t i = 0; i < h->tensors.size(); ++i) h->tensors[i].base = (float*)(h->arena + h->tensor_off[i]);
 
-    // wire the 28 convs (execution order of recurrent_autoencoder_model.py:129-140)
+    // ---- wire the 28 convs (execution order of recurrent_autoencoder_model.py:129-140) ----
+    // ids < 0 encode hidden states: -(10 + level) = "read parity", -(20 + level) = "write parity"
+    auto HR = [](int l) { return -(10 + l); };
+    auto HW = [](int l) { return -(20 + l); };
+    auto resolve = [&](int id, int parity) -> int {
+        if (id <= -20) return h->t_hidden[-id - 20][parity ^ 1];
+        if (id <= -10) return h->t_hidden[-id - 10][parity];
+        return id;
+    };
+    std::vector<DnLayerSpec> specs = dn_layer_specs();
     for (size_t li = 0; li < specs.size(); ++li) {
         DnLayer L;
         L.spec = specs[li];
         const DnLayerSpec& s = specs[li];
         const int lvl = s.level;
-        L.H = h->Hp >> lvl; L.W = h->Wp >> lvl;
-        L.src1 = nullptr; L.c1p = 0;
-        if (s.kind == DN_L1) {
-            L.src0 = lvl == 0 ? h->d_in16 : pooled[lvl - 1]; L.c0p = cpad(s.cin0);
-            L.out = out1[lvl];
-        } else if (s.kind == DN_L2A) {
-            L.src0 = out1[lvl]; L.c0p = cpad(s.cin0); L.src1 = h->hidden[lvl]; L.c1p = cpad(s.cin1);
-            L.out = mid[lvl];
-        } else if (s.kind == DN_L2B) {
-            L.src0 = mid[lvl]; L.c0p = cpad(s.cin0);
-            L.out = h->hidden[lvl];
-        } else if (s.kind == DN_DEC1) {
-            const int i = 4 - lvl;                     // dec index: level 4 -> dec5 (i = 0)
-            L.src0 = i == 0 ? h->hidden[5] : dc2[i - 1]; L.c0p = cpad(s.cin0);
-            L.src1 = pooled[lvl]; L.c1p = cpad(s.cin1);
-            L.out = dc1[i];
-        } else {
-            const int i = 4 - lvl;
-            L.src0 = dc1[i]; L.c0p = cpad(s.cin0);
-            L.out = dc2[i];
-        }
-        L.coutp = cpad(s.cout);
+        L.H = rows >> lvl; L.W = Wp >> lvl;
+        L.src1 = -1; L.pool = -1;
+        if (s.kind == DN_L1) { L.src0 = lvl == 0 ? h->t_in16 : pooled[lvl - 1]; L.out = out1[lvl]; }
+        else if (s.kind == DN_L2A) { L.src0 = out1[lvl]; L.src1 = HR(lvl); L.out = mid[lvl]; }
+        else if (s.kind == DN_L2B) { L.src0 = mid[lvl]; L.out = HW(lvl); if (lvl < 5) L.pool = pooled[lvl]; }
+        else if (s.kind == DN_DEC1) { const int i = 4 - lvl; L.src0 = i == 0 ? HW(5) : dc2[i - 1]; L.src1 = pooled[lvl]; L.out = dc1[i]; }   // dec5 reads the bottleneck output of THIS frame
+        else { const int i = 4 - lvl; L.src0 = dc1[i]; L.out = dc2[i]; }
+        const int c0p = cpad(s.cin0), c1p = s.cin1 ? cpad(s.cin1) : 0, coutp = cpad(s.cout);
         // ---- parameters: conv weight/bias + BN folded to scale/shift ----
         auto get = [&](const std::string& k, size_t want) -> const std::vector<float>* {
             auto it = sd.find(k);
             if (it == sd.end() || it->second.size() != want) { ptd_set_error("weight file: tensor '%s' missing or wrong size (want %zu)", k.c_str(), want); return nullptr; }
             return &it->second;
         };
-        const int cin = s.cin0 + s.cin1, cinp = L.c0p + L.c1p;
+        const int cin = s.cin0 + s.cin1, cinp = c0p + c1p;
         const std::vector<float>* w = get(s.conv_key + ".weight", (size_t)s.cout * cin * 9);
         const std::vector<float>* b = get(s.conv_key + ".bias", s.cout);
         const std::vector<float>* g = get(s.bn_key + ".weight", s.cout);
@@ -330,35 +380,44 @@ extern "C" ptd_status ptd_dn_create(const char* weights_path, int H, int W, int 
         const std::vector<float>* mu = get(s.bn_key + ".running_mean", s.cout);
         const std::vector<float>* var = get(s.bn_key + ".running_var", s.cout);
         if (!w || !b || !g || !be || !mu || !var) return fail(PTD_ERR_PARSE);
-        std::vector<float> w9((size_t)9 * cinp * L.coutp, 0.f), scale(L.coutp, 0.f), shift(L.coutp, 0.f), bias(L.coutp, 0.f);
-        auto cmap = [&](int c) { return c < s.cin0 ? c : L.c0p + (c - s.cin0); };      // position of real channel c in the padded concat
+        std::vector<float> w9((size_t)9 * cinp * coutp, 0.f), scale(coutp, 0.f), shift(coutp, 0.f), bias(coutp, 0.f);
+        auto cmap = [&](int c) { return c < s.cin0 ? c : c0p + (c - s.cin0); };      // position of real channel c in the padded concat
         for (int co = 0; co < s.cout; ++co)
             for (int c = 0; c < cin; ++c)
                 for (int t = 0; t < 9; ++t)
-                    w9[((size_t)t * cinp + cmap(c)) * L.coutp + co] = (*w)[((size_t)co * cin + c) * 9 + t];
+                    w9[((size_t)t * cinp + cmap(c)) * coutp + co] = (*w)[((size_t)co * cin + c) * 9 + t];
         for (int co = 0; co < s.cout; ++co) {
             const float sc = (*g)[co] / sqrtf((*var)[co] + 1e-5f);                      // BatchNorm2d eval, eps 1e-5
             const float sh = (*be)[co] - (*mu)[co] * sc;
             scale[co] = sc; bias[co] = (*b)[co];
             shift[co] = s.lrelu_first ? sh : sh + sc * (*b)[co];
         }
-        DALLOC(L.d_w9, w9.size()); DALLOC(L.d_scale, L.coutp); DALLOC(L.d_shift, L.coutp); DALLOC(L.d_bias, L.coutp);
+        DALLOC(L.d_w9, w9.size()); DALLOC(L.d_scale, coutp); DALLOC(L.d_shift, coutp); DALLOC(L.d_bias, coutp);
         cudaMemcpy(L.d_w9, w9.data(), w9.size() * 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(L.d_scale, scale.data(), L.coutp * 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(L.d_shift, shift.data(), L.coutp * 4, cudaMemcpyHostToDevice);
-        cudaMemcpy(L.d_bias, bias.data(), L.coutp * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(L.d_scale, scale.data(), coutp * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(L.d_shift, shift.data(), coutp * 4, cudaMemcpyHostToDevice);
+        cudaMemcpy(L.d_bias, bias.data(), coutp * 4, cudaMemcpyHostToDevice);
         if (flags == PTD_DN_TF32) {
-            TcConvDesc d;
-            d.src0 = L.src0; d.src1 = L.src1; d.c0p = L.c0p; d.c1p = L.c1p; d.upsample = s.kind == DN_DEC1;
-            d.H = L.H; d.W = L.W; d.coutp = L.coutp; d.out = L.out; d.lrelu_first = s.lrelu_first;
-            d.scale = L.d_scale; d.shift = L.d_shift; d.bias = L.d_bias;
-            d.pool_out = (s.kind == DN_L2B && lvl < 5) ? pooled[lvl] : nullptr;
-            d.round_out = li + 1 < specs.size();
-            rc = tc_plan_create(d, w9, cinp, L.tc, h->allocs);
-            if (rc != PTD_OK) return fail(rc);
+            float* dd = nullptr;
+            DALLOC(dd, 64);
+            L.d_done = (uint32_t*)dd;
+            for (int parity = 0; parity < 2; ++parity) {
+                TcConvDesc d;
+                d.src0 = h->tensors[resolve(L.src0, parity)];
+                if (L.src1 != -1) d.src1 = h->tensors[resolve(L.src1, parity)];
+                d.upsample = s.kind == DN_DEC1;
+                d.out = h->tensors[resolve(L.out, parity)];
+                if (L.pool != -1) d.pool_out = h->tensors[L.pool];
+                d.lrelu_first = s.lrelu_first;
+                d.scale = L.d_scale; d.shift = L.d_shift; d.bias = L.d_bias;
+                d.round_out = li + 1 < specs.size();
+                d.shared_wpack = parity ? L.tc[0].d_wpack : nullptr;
+                rc = tc_plan_create(d, w9, cinp, L.tc[parity], h->allocs);
+                if (rc != PTD_OK) return fail(rc);
+            }
         }
         h->layers.push_back(L);
-        if (s.kind == DN_L2B && lvl < 5) h->pools.push_back({h->hidden[lvl], pooled[lvl], L.H / 2, L.W / 2, L.coutp});
+        if (s.kind == DN_L2B && lvl < 5) h->pools.push_back({{h->t_hidden[lvl][0], h->t_hidden[lvl][1]}, pooled[lvl]});
     }
 #undef DALLOC
     CUDA_TRY(cudaDeviceSynchronize());
@@ -366,74 +425,202 @@ extern "C" ptd_status ptd_dn_create(const char* weights_path, int H, int W, int 
     return PTD_OK;
 }
 
-extern "C" ptd_status ptd_dn_create_strip(const char*, int, int, int, int, int, unsigned, ptd_halo_fn, void*, ptd_dn** out) {
-    if (out) *out = nullptr;
-    PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_dn_create_strip: row-strip tiling is not built yet (DESIGN.md, multi-GPU)");
+extern "C" ptd_status ptd_dn_create(const char* weights_path, int H, int W, int device, unsigned flags, ptd_dn** out) {
+    return dn_create(weights_path, H, W, 0, 0, false, device, flags, out);
+}
+extern "C" ptd_status ptd_dn_create_strip(const char* weights_path, int H, int W, int row0, int rows, int device, unsigned flags, ptd_dn** out) {
+    return dn_create(weights_path, H, W, row0, rows, true, device, flags, out);
+}
+// Rows of strip `index` of `nstrips`: the padded frame's 32-row groups split as evenly as possible (earlier strips get the extras).
+extern "C" ptd_status ptd_dn_strip_partition(int H, int nstrips, int index, int* row0, int* rows) {
+    const int groups = (H + 31) / 32;
+    if (H <= 0 || nstrips < 1 || index < 0 || index >= nstrips || !row0 || !rows) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_partition: bad argument");
+    if (nstrips > groups) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_partition: %d strips but the padded frame has only %d groups of 32 rows", nstrips, groups);
+    const int base = groups / nstrips, extra = groups % nstrips;
+    const int g0 = index * base + (index < extra ? index : extra), gn = base + (index < extra ? 1 : 0);
+    *row0 = g0 * 32; *rows = gn * 32;
+    return PTD_OK;
+}
+extern "C" int ptd_dn_strip_info_size(void) { return (int)sizeof(ptd_strip_info); }
+extern "C" ptd_status ptd_dn_strip_export(ptd_dn* h, void* info_out, int capacity) {
+    if (!h || !info_out || capacity < (int)sizeof(ptd_strip_info)) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_export: need a buffer of %zu bytes", sizeof(ptd_strip_info));
+    CUDA_TRY(cudaSetDevice(h->device));
+    ptd_strip_info info;
+    memset(&info, 0, sizeof info);
+    cudaIpcMemHandle_t ipc;
+    if (cudaIpcGetMemHandle(&ipc, h->arena) == cudaSuccess) memcpy(info.ipc, &ipc, sizeof ipc);
+    else cudaGetLastError();                                  // same-process connections do not need it
+    info.arena = (unsigned long long)(uintptr_t)h->arena;
+    info.pid_tag = (int)getpid(); info.device = h->device; info.row0 = h->row0; info.rows = h->rows; info.Hp = h->Hp; info.Wp = h->Wp;
+    info.ntensors = (int)h->tensors.size();
+    for (size_t i = 0; i < h->tensors.size(); ++i) { info.tensor_off[i] = h->tensor_off[i]; info.tensor_rows[i] = h->tensors[i].rows; }
+    info.flags_off = h->flags_off;
+    memcpy(info_out, &info, sizeof info);
+    return PTD_OK;
+}
+// up / down: ptd_strip_info of the strips above / below (null = frame border).  Same process: the pointer is used directly
+// (peer access is enabled when the devices differ); other process: the arena is opened through CUDA IPC.
+extern "C" ptd_status ptd_dn_strip_connect(ptd_dn* h, const void* up, const void* down) {
+    if (!h) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: null handle");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const void* src[2] = {up, down};
+    for (int d = 0; d < 2; ++d) {
+        if (h->peer_arena[d] && h->peer_ipc[d]) cudaIpcCloseMemHandle(h->peer_arena[d]);
+        h->peer_arena[d] = nullptr; h->has_peer[d] = false; h->peer_ipc[d] = false;
+        if (!src[d]) continue;
+        ptd_strip_info info;
+        memcpy(&info, src[d], sizeof info);
+        if (info.ntensors != (int)h->tensors.size() || info.Hp != h->Hp || info.Wp != h->Wp) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: neighbour was built for another frame size");
+        if ((d == 0 && info.row0 + info.rows != h->row0) || (d == 1 && h->row0 + h->rows != info.row0)) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: neighbour rows [%d, %d) are not adjacent to [%d, %d)", info.row0, info.row0 + info.rows, h->row0, h->row0 + h->rows);
+        if (info.pid_tag == (int)getpid()) {
+            if (info.device != h->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(info.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ptd_set_error("ptd_dn_strip_connect: no peer access %d -> %d: %s", h->device, info.device, cudaGetErrorString(e)); return PTD_ERR_CUDA; }
+                cudaGetLastError();
+            }
+            h->peer_arena[d] = (unsigned char*)(uintptr_t)info.arena;
+        } else {
+            cudaIpcMemHandle_t ipc;
+            memcpy(&ipc, info.ipc, sizeof ipc);
+            void* p = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_arena[d] = (unsigned char*)p; h->peer_ipc[d] = true;
+        }
+        h->peer_info[d] = info; h->has_peer[d] = true;
+    }
+    return PTD_OK;
 }
 
-extern "C" ptd_status ptd_dn_forward(ptd_dn* h, const float* gbuf, float* rgb, int reset_hidden, void* stream_) {
-    if (!h || !gbuf || !rgb) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_forward: null argument");
-    cudaStream_t st = (cudaStream_t)stream_;
+static DnTensor peer_tensor(const ptd_dn* h, int dir, int id) {
+    DnTensor t = h->tensors[id];
+    t.base = (float*)(h->peer_arena[dir] + h->peer_info[dir].tensor_off[id]);
+    t.rows = h->peer_info[dir].tensor_rows[id];
+    return t;
+}
+static uint32_t* peer_flag(const ptd_dn* h, int dir, int id, int from) {
+    return (uint32_t*)(h->peer_arena[dir] + h->peer_info[dir].flags_off + ((size_t)id * 2 + from) * 32);
+}
+
+// Launches layers [first, last) of forward(x, j) on `st`.  ptd_dn_forward runs them all; a same-GPU strip group (tests) interleaves.
+static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hidden, cudaStream_t st, int first, int last) {
     CUDA_TRY(cudaSetDevice(h->device));
-    int launches = 0;
-    int nmark = 0;
-    if (h->profiling) h->launch_names.clear();
+    const int nl = (int)h->layers.size();
     auto mark = [&](const char* name) {                                 // event after the launch just issued (and one before the first)
         if (!h->profiling) return;
+        const int nmark = (int)h->launch_names.size() + (name ? 1 : 0);
         if ((int)h->events.size() <= nmark) { cudaEvent_t e; cudaEventCreate(&e); h->events.push_back(e); }
-        cudaEventRecord(h->events[nmark++], st);
+        cudaEventRecord(h->events[name ? nmark : 0], st);
         if (name) h->launch_names.push_back(name);
     };
-    if (reset_hidden)                                                   // forward(x, j == 0): model.py:121-128
-        for (int l = 0; l < 6; ++l) CUDA_TRY(cudaMemsetAsync(h->hidden[l], 0, h->hidden_bytes[l], st));
-    {
-        const size_t n = (size_t)h->Hp * h->Wp;
+    const bool tf32 = h->flags == PTD_DN_TF32;
+    if (first <= -1) {                                                  // stage -1: start of the frame
+        h->epoch += 1;
+        h->launches = 0;
+        if (h->profiling) h->launch_names.clear();
+        if (reset_hidden)                                               // forward(x, j == 0): model.py:121-128
+            for (int l = 0; l < 6; ++l) {
+                const DnTensor& t = h->tensors[h->t_hidden[l][h->parity]];
+                CUDA_TRY(cudaMemsetAsync(t.base, 0, t.floats() * 4, st));
+            }
+        const DnTensor& in = h->tensors[h->t_in16];
+        const size_t n = (size_t)(in.rows + 2) * in.W;
         mark(nullptr);
-        pack_gbuffer<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gbuf, h->H, h->W, h->Hp, h->Wp, h->d_in16, h->flags == PTD_DN_TF32);
-        ++launches;
+        // rows row0 - 1 .. row0 + rows of the frame: the strip plus its two apron rows, straight from the G-buffer
+        pack_gbuffer<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gbuf, h->H, h->W, h->row0, in, tf32);
+        ++h->launches;
         mark("pack_gbuffer");
     }
-    size_t pool_i = 0;
-    for (size_t li = 0; li < h->layers.size(); ++li) {
+    for (int li = first < 0 ? 0 : first; li < last && li < nl; ++li) {
         DnLayer& L = h->layers[li];
-        bool pooled_in_epilogue = false;
-        if (h->flags == PTD_DN_TF32) {
-            ptd_status rc = tc_conv_launch(L.tc, st, &launches, &pooled_in_epilogue);
+        auto res = [&](int id) -> int {
+            if (id <= -20) return h->t_hidden[-id - 20][h->parity ^ 1];
+            if (id <= -10) return h->t_hidden[-id - 10][h->parity];
+            return id;
+        };
+        const int s0 = res(L.src0), s1 = L.src1 == -1 ? -1 : res(L.src1), o = res(L.out);
+        if (tf32) {
+            TcConvPlan& plan = L.tc[h->parity];
+            TcStripLink& k = plan.p.link;
+            memset(&k, 0, sizeof k);
+            if (h->has_peer[0] || h->has_peer[1]) {
+                k.done = L.d_done; k.epoch = h->epoch;
+                const int srcs[2] = {s0, s1};
+                for (int i = 0; i < 2; ++i) {
+                    if (srcs[i] < 0 || srcs[i] == h->t_in16) continue;                     // the packed input brings its own apron rows
+                    // a hidden state read by layer2's first conv was produced by the PREVIOUS frame (or just zeroed)
+                    const bool prev = L.spec.kind == DN_L2A && i == 1;
+                    if (prev && reset_hidden) continue;
+                    for (int d = 0; d < 2; ++d)
+                        if (h->has_peer[d]) { k.wait[2 * i + d] = h->flag(srcs[i], d); k.wait_epoch[2 * i + d] = prev ? h->epoch - 1 : h->epoch; }
+                }
+                for (int d = 0; d < 2; ++d) {
+                    if (!h->has_peer[d]) continue;
+                    // our first row -> the UP neighbour's bottom apron, flagged there as "from down" (1); last row -> DOWN neighbour, "from up" (0)
+                    (d == 0 ? k.out_up : k.out_down) = peer_tensor(h, d, o);
+                    k.sig[d] = peer_flag(h, d, o, d == 0 ? 1 : 0);
+                    if (L.pool != -1) {
+                        (d == 0 ? k.pool_up : k.pool_down) = peer_tensor(h, d, L.pool);
+                        k.sig[2 + d] = peer_flag(h, d, L.pool, d == 0 ? 1 : 0);
+                    }
+                }
+            }
+            ptd_status rc = tc_conv_launch(plan, st, &h->launches, nullptr);
             if (rc != PTD_OK) return rc;
+            mark(L.spec.name.c_str());
         } else {
             FpConvArgs a;
-            a.src0 = L.src0; a.src1 = L.src1; a.c0p = L.c0p; a.c1p = L.c1p; a.upsample = L.spec.kind == DN_DEC1;
+            a.src0 = h->tensors[s0]; a.src1 = s1 >= 0 ? h->tensors[s1] : DnTensor(); a.upsample = L.spec.kind == DN_DEC1;
             a.H = L.H; a.W = L.W; a.w = L.d_w9; a.scale = L.d_scale; a.shift = L.d_shift; a.bias = L.d_bias;
-            a.coutp = L.coutp; a.order = L.spec.lrelu_first ? 1 : 0; a.out = L.out;
-            dim3 grid((L.W + FC_TW - 1) / FC_TW, (L.H + FC_TH - 1) / FC_TH, (L.coutp + FC_BN - 1) / FC_BN);
+            a.order = L.spec.lrelu_first ? 1 : 0; a.out = h->tensors[o];
+            dim3 grid((L.W + FC_TW - 1) / FC_TW, (L.H + FC_TH - 1) / FC_TH, (a.out.cp + FC_BN - 1) / FC_BN);
             conv3x3_fp32<<<grid, 128, 0, st>>>(a);
-            ++launches;
-        }
-        mark(L.spec.name.c_str());
-        if (L.spec.kind == DN_L2B && L.spec.level < 5) {
-            const ptd_dn::Pool& p = h->pools[pool_i++];
-            if (!pooled_in_epilogue) {
-                const size_t n = (size_t)p.Ho * p.Wo * (p.cp / 4);
-                maxpool2_nhwc<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p.in, p.out, p.Ho, p.Wo, p.cp);
-                ++launches;
+            ++h->launches;
+            mark(L.spec.name.c_str());
+            if (L.pool != -1) {
+                const DnTensor& po = h->tensors[L.pool];
+                const size_t n = (size_t)(po.cp / 4) * po.rows * po.W;
+                maxpool2_chw4<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->tensors[o], po);
+                ++h->launches;
                 mark("maxpool2");
             }
         }
     }
-    {
-        const size_t n = (size_t)h->H * h->W;
-        unpack_rgb<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->d_final, h->H, h->W, h->Wp, rgb);
-        ++launches;
-        mark("unpack_rgb");
+    if (last > nl) {                                                    // stage nl: end of the frame
+        const int r0 = h->row0, r1 = std::min(h->row0 + h->rows, h->H);
+        if (r1 > r0) {
+            const size_t n = (size_t)(r1 - r0) * h->W;
+            unpack_rgb<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(h->tensors[h->t_final], h->H, h->W, r0, r1 - r0, rgb);
+            ++h->launches;
+            mark("unpack_rgb");
+        }
+        h->parity ^= 1;
+        if (h->profiling) h->timed_launches = (int)h->launch_names.size();
     }
-    h->launches = launches;
-    if (h->profiling) h->timed_launches = nmark - 1;
     CUDA_TRY(cudaGetLastError());
+    return PTD_OK;
+}
+
+extern "C" ptd_status ptd_dn_forward(ptd_dn* h, const float* gbuf, float* rgb, int reset_hidden, void* stream_) {
+    if (!h || !gbuf || !rgb) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_forward: null argument");
+    return dn_run(h, gbuf, rgb, reset_hidden, (cudaStream_t)stream_, -1, (int)h->layers.size() + 1);
+}
+
+// Same-process strip group (one or several devices): the layers of all strips are issued layer by layer, so that on a
+// single GPU - where the strips' kernels cannot run concurrently - every flag a kernel waits for has already been raised.
+extern "C" ptd_status ptd_dn_forward_group(ptd_dn** hs, int n, const float* const* gbufs, float* const* rgbs, int reset_hidden, void* const* streams) {
+    if (!hs || n < 1 || !gbufs || !rgbs) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_forward_group: bad argument");
+    const int nl = (int)hs[0]->layers.size();
+    for (int stage = -1; stage <= nl; ++stage)
+        for (int i = 0; i < n; ++i) {
+            ptd_status rc = dn_run(hs[i], gbufs[i], rgbs[i], reset_hidden, streams ? (cudaStream_t)streams[i] : nullptr, stage, stage == -1 ? 0 : stage + 1);
+            if (rc != PTD_OK) return rc;
+        }
     return PTD_OK;
 }
 
 extern "C" ptd_status ptd_dn_forward_host(ptd_dn* h, const float* gbuf_host, float* rgb_host, int reset_hidden) {
     if (!h || !gbuf_host || !rgb_host) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_forward_host: null argument");
+    if (h->strip) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_dn_forward_host: a row-strip handle takes device pointers (ptd_dn_forward)");
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t P = (size_t)h->H * h->W;
     CUDA_TRY(cudaMemcpy(h->d_gbuf, gbuf_host, P * 40, cudaMemcpyHostToDevice));          // main.cpp:104-105
@@ -453,12 +640,13 @@ extern "C" ptd_status ptd_dn_padded_size(const ptd_dn* h, int* Hp, int* Wp) {
 extern "C" ptd_status ptd_dn_dump_hidden(ptd_dn* h, int level, float* host, size_t cap, int* C, int* H, int* W) {
     if (!h || !host || level < 0 || level > 5) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_dump_hidden: bad argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    const int c = h->hidden_c[level], hh = h->Hp >> level, ww = h->Wp >> level;
+    const DnTensor& t = h->tensors[h->t_hidden[level][h->parity]];       // the state the NEXT forward will read
+    const int c = h->hidden_c[level], hh = t.rows, ww = t.W;
     const size_t n = (size_t)c * hh * ww;
     if (cap < n) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_dump_hidden: capacity %zu < %zu", cap, n);
     float* tmp = nullptr;
     CUDA_TRY(cudaMalloc((void**)&tmp, n * 4));
-    nhwc_to_nchw<<<(unsigned)((n + 255) / 256), 256>>>(h->hidden[level], c, cpad(c), hh, ww, tmp);
+    chw4_to_nchw<<<(unsigned)((n + 255) / 256), 256>>>(t, c, tmp);
     cudaError_t e = cudaMemcpy(host, tmp, n * 4, cudaMemcpyDeviceToHost);
     cudaFree(tmp);
     CUDA_TRY(e);

@@ -120,12 +120,22 @@ void ptd_dn_destroy(ptd_dn*);
 ptd_status ptd_dn_forward(ptd_dn*, const float* gbuffer_dev, float* rgb_dev, int reset_hidden, void* stream);
 /* Host-pointer form == the reference call site (main.cpp:101-118: H2D of 40*P bytes, forward, D2H of 12*P). Blocking. */
 ptd_status ptd_dn_forward_host(ptd_dn*, const float* gbuffer_host, float* rgb_host, int reset_hidden);
-/* Row-strip mode for multi-GPU tiling: this handle owns padded rows [row0, row0+rows) of a
- * Hp-row frame; rows multiple of 32.  Halo rows are exchanged by the caller-provided callback once per conv. */
-typedef void (*ptd_halo_fn)(void* user, int layer, float* send_up_dev, float* send_down_dev,
-                            float* recv_up_dev, float* recv_down_dev, size_t bytes, void* stream);
-ptd_status ptd_dn_create_strip(const char* weights_path, int H, int W, int row0, int rows, int device, unsigned flags,
-                               ptd_halo_fn halo, void* user, ptd_dn** out);
+/* ---- row-strip mode: the denoiser of ONE frame tiled over several GPUs ----------------------------
+ * A strip handle owns padded rows [row0, row0 + rows) (multiples of 32) of the frame.  Its convs store their first / last
+ * output row directly into the neighbour strips' halo rows over NVLink (peer pointers) and raise a flag there; the
+ * neighbours' next conv waits for the flag on the device.  No host round trip, no NCCL call on the data path.
+ * Setup (once): every rank creates its strip, exports a ptd_dn_strip_info_size()-byte POD blob, the ranks exchange the blobs
+ * (torch.distributed all_gather on the host side) and connect to the strips above / below.  Needs PTD_DN_TF32.
+ * Per frame every rank calls ptd_dn_forward with the FULL-frame G-buffer [10][H][W] on its own device; it writes rows
+ * [row0, min(row0 + rows, H)) of the full-frame rgb [3][H][W].  All ranks must pass the same reset_hidden. */
+ptd_status ptd_dn_strip_partition(int H, int nstrips, int index, int* row0, int* rows);   /* even split of the 32-row groups */
+ptd_status ptd_dn_create_strip(const char* weights_path, int H, int W, int row0, int rows, int device, unsigned flags, ptd_dn** out);
+int ptd_dn_strip_info_size(void);
+ptd_status ptd_dn_strip_export(ptd_dn*, void* info_out, int capacity);
+ptd_status ptd_dn_strip_connect(ptd_dn*, const void* info_up, const void* info_down);     /* NULL = frame border */
+/* Strips living in ONE process (tests; single-process multi-GPU): issues the frame layer by layer across the handles. */
+ptd_status ptd_dn_forward_group(ptd_dn** strips, int n, const float* const* gbuffers_dev, float* const* rgbs_dev, int reset_hidden,
+                                void* const* streams);
 ptd_status ptd_dn_padded_size(const ptd_dn*, int* Hp, int* Wp);
 /* Parity tap: copy a hidden state (level 0..5, NCHW fp32, padded size) to host. */
 ptd_status ptd_dn_dump_hidden(ptd_dn*, int level, float* host, size_t capacity_floats, int* C, int* H, int* W);

@@ -101,3 +101,31 @@ def test_full_size_720p_properties(mode, wfile):
     ys = dn.forward_host(xs, reset=True)
     a, b = ys[:, 300:420, 32 + 300:32 + 900], y1[:, 300:420, 300:900]
     assert np.abs(a - b).max() <= 2 * TOL[mode][0]
+
+
+@pytest.mark.parametrize("nstrips", [2, 3])
+def test_row_strips_equal_the_full_frame(nstrips, wfile):
+    """Multi-GPU tiling on ONE device: the frame cut into row strips (32-row aligned, uneven), each strip a handle with its
+    own arena, halo rows stored into the neighbour's apron by the conv epilogues + device-side flags.  Result must be
+    bit-identical to the single-handle forward over 4 frames (recurrent state carried, then reset)."""
+    capi = _capi()
+    import torch
+    from oracle.dn_oracle import synthetic_gbuffer
+    H, W = 150, 100                                   # padded 160 x 128: 5 groups of 32 rows
+    full = capi.Denoiser(wfile, H, W, flags=capi.DN_TF32)
+    parts = [capi.strip_partition(H, nstrips, i) for i in range(nstrips)]
+    strips = [capi.Denoiser(wfile, H, W, flags=capi.DN_TF32, strip=p) for p in parts]
+    infos = [s.export_info() for s in strips]
+    for i, s in enumerate(strips):
+        s.connect(infos[i - 1] if i > 0 else None, infos[i + 1] if i + 1 < nstrips else None)
+    g = torch.empty(10 * H * W, dtype=torch.float32, device="cuda")
+    out = torch.zeros(3 * H * W, dtype=torch.float32, device="cuda")
+    for j, reset in enumerate([True, False, False, True, False]):
+        x = synthetic_gbuffer(H, W, seed=5, frame=j)
+        ref = full.forward_host(x, reset=reset)
+        g.copy_(torch.from_numpy(x).reshape(-1))
+        out.zero_()
+        capi.Denoiser.forward_group(strips, [g.data_ptr()] * nstrips, [out.data_ptr()] * nstrips, reset)
+        torch.cuda.synchronize()
+        y = out.cpu().numpy().reshape(3, H, W)
+        assert y.tobytes() == ref.tobytes(), (j, float(np.abs(y - ref).max()))

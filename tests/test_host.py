@@ -88,3 +88,38 @@ def test_no_cpu_fallback_without_a_device(tmp_path):
     w = weights.save_weights(weights.synthetic_state_dict(1234), str(tmp_path / "w.ptdw"))
     with pytest.raises(capi.PtdError, match="no CPU fallback"):
         capi.Denoiser(w, 64, 64)
+
+
+def test_strip_partition_covers_the_padded_frame():
+    """Row strips of the multi-GPU denoiser: contiguous, multiples of 32, cover the padded frame, sizes differ by <= 32."""
+    from ai_path_tracer_denoiser_b200 import capi
+    for H in (720, 1080, 1440, 64, 400):
+        Hp = (H + 31) // 32 * 32
+        for n in (1, 2, 4, 8):
+            if n > Hp // 32:
+                with pytest.raises(capi.PtdError):
+                    capi.strip_partition(H, n, 0)
+                continue
+            parts = [capi.strip_partition(H, n, i) for i in range(n)]
+            assert parts[0][0] == 0 and parts[-1][0] + parts[-1][1] == Hp
+            for (a0, an), (b0, bn) in zip(parts, parts[1:]):
+                assert a0 + an == b0
+            assert all(r % 32 == 0 and r > 0 for _, r in parts)
+            assert max(r for _, r in parts) - min(r for _, r in parts) <= 32
+    with pytest.raises(capi.PtdError):
+        capi.strip_partition(720, 0, 0)
+
+
+def test_compute_entry_points_fail_loudly_without_a_device(tmp_path):
+    """No CPU fallback: on a box without a GPU every compute constructor must raise, not silently compute on the host."""
+    from ai_path_tracer_denoiser_b200 import capi, weights
+    if capi.device_count() > 0:
+        pytest.skip("a CUDA device is present")
+    sc = capi.Scene(path=os.path.join(SCENES, "cornell_64x48.txt"))
+    with pytest.raises(capi.PtdError, match="no CPU fallback"):
+        capi.PathTracer(sc)
+    w = weights.save_weights(weights.synthetic_state_dict(1234), str(tmp_path / "w.ptdw"))
+    with pytest.raises(capi.PtdError, match="no CPU fallback"):
+        capi.Denoiser(w, 48, 64)
+    with pytest.raises(capi.PtdError, match="no CPU fallback"):
+        capi.Denoiser(w, 64, 64, strip=(0, 32))
