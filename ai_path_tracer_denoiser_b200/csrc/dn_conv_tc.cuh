@@ -21,8 +21,9 @@
 //   * epilogue (4 warps, thread = pixel): tcgen05.ld 32x32b.x16 -> bias/BatchNorm(eval)/LeakyReLU -> one float4 per channel
 //     quad (a warp stores 4 x 128 contiguous bytes), MaxPool2d(2) fused through two warp shuffles (the 2x2 window lives in
 //     one warp), activations rounded to tf32 (RN) so the next layer's operand truncation is exact.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (one lane), 2 = TMEM allocator, 4..7 = epilogue.  Pipelines: up to 8 smem
-// stages (full/empty mbarriers) and 2 TMEM accumulator buffers (tmem_full/tmem_empty), persistent CTAs, one per SM.
+// Warp roles: 0 = TMA producer, 1 = MMA issuer (one lane), 2 = TMEM allocator, 4..11 = epilogue (two warps per TMEM lane
+// quarter, alternating 16-column chunks, so every SM sub-partition has two epilogue warps to hide latency).  Pipelines: up
+// to 8 smem stages (full/empty mbarriers) and 2 TMEM accumulator buffers (tmem_full/tmem_empty), persistent CTAs, one per SM.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
@@ -39,7 +40,7 @@
 #define TC_QUAD_PITCH (TC_HALO_H * TC_ROW_PITCH)        // 2880 B: one channel quad of the halo tile
 #define TC_A_BYTES (4 * TC_QUAD_PITCH)                  // 11520 B: 16 channels
 #define TC_MAX_STAGES 8
-#define TC_THREADS 256
+#define TC_THREADS 384                                  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
 #define TC_TMEM_COLS 256
 #define TC_ACC_COLS 128
 #define TC_SMEM_BUDGET (200 * 1024)
@@ -177,6 +178,79 @@ __device__ __forceinline__ float round_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+__device__ __forceinline__ bool elect_one() {            // one lane of the (converged) warp, known to the compiler as such
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}" : "=r"(pred));
+    return pred != 0;
+}
+__device__ __forceinline__ void mma_tf32_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        ".reg .b64 da, db;\n\t"
+        "mov.b64 da, {%1, %2};\n\t"
+        "mov.b64 db, {%3, %4};\n\t"
+        "setp.ne.b32 p, %6, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+}
+}  // namespace tc
+
+namespace tc {
+}  // namespace tc
+
+namespace tc {
+// K-major no-swizzle descriptors, split into 32-bit words: lo = start >> 4 | (LBO >> 4) << 16, hi = SBO >> 4 | version 1 << 14
+template <int NTAPS>
+__device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full, uint64_t* empty,
+                                         uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int lane) {
+    // instruction descriptor: D = f32, A = B = tf32, both K-major, N = coutp, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.coutp >> 3) << 17) | ((128u >> 4) << 24);
+    const uint32_t a_hi = (uint32_t)(TC_ROW_PITCH >> 4) | (1u << 14);          // SBO = halo row pitch
+    const uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);                  // SBO = next 8 output channels
+    const uint32_t a_lbo = (uint32_t)(TC_QUAD_PITCH >> 4) << 16;              // LBO = next channel quad
+    const uint32_t b_lbo = (uint32_t)p.coutp << 16;                           // (coutp * 16 B) >> 4: next k quad of the same tap
+    const uint32_t b_kstep = (uint32_t)p.coutp * 2u;                          // (coutp * 32 B) >> 4: one K = 8 step
+    const int nchunks = p.n0 + p.n1;
+    const uint32_t sa0 = smem_u32(smem_a) >> 4, sb0 = smem_u32(smem_b) >> 4;
+    const uint32_t b_stage16 = p.b_stage_bytes >> 4;
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+        const int ph = item % p.nphases;
+        uint32_t aoff[NTAPS];
+#pragma unroll
+        for (int t = 0; t < NTAPS; ++t) aoff[t] = (uint32_t)(((1 + p.dy[ph][t]) * TC_ROW_PITCH + (1 + p.dx[ph][t]) * 16) >> 4);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        fence_after_sync();
+        const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)acc * TC_ACC_COLS;   // provably warp-uniform
+        for (int c = 0; c < nchunks; ++c) {
+            mbar_wait(&full[stage], phase);
+            fence_after_sync();
+            const uint32_t a_base = (sa0 + (uint32_t)stage * (TC_A_BYTES >> 4)) | a_lbo;
+            const uint32_t b_base = (sb0 + (p.resident ? (uint32_t)(ph * nchunks + c) : (uint32_t)stage) * b_stage16) | b_lbo;
+            if (elect_one()) {
+#pragma unroll
+                for (int t = 0; t < NTAPS; ++t) {
+#pragma unroll
+                    for (int j = 0; j < 2; ++j)
+                        mma_tf32_w(d_tmem, a_base + aoff[t] + (uint32_t)j * (2u * TC_QUAD_PITCH >> 4), a_hi,
+                                   b_base + (uint32_t)(t * 2 + j) * b_kstep, b_hi, idesc, (t | j) ? 1u : (c ? 1u : 0u));
+                }
+                mma_commit(&empty[stage]);                                    // frees the smem stage when the MMAs retire
+                if (c == nchunks - 1) mma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+            }
+            __syncwarp();
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+}
 }  // namespace tc
 
 // shared memory carve-up (offsets from the 1024-aligned base): [A stage 0..S) | B (resident: whole layer; streamed: S stages) | barriers
@@ -192,6 +266,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint64_t* tmem_empty = tmem_full + 2;
     uint64_t* wfull = tmem_empty + 2;
     uint32_t* tmem_base_slot = (uint32_t*)(wfull + 1);
+    float4* s_par = (float4*)(((uintptr_t)(tmem_base_slot + 1) + 15) & ~(uintptr_t)15);                  // per output channel: (s1, b1, s2, b2), out = lrelu(acc*s1 + b1)*s2 + b2
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = p.n0 + p.n1;
@@ -202,7 +277,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 128); }
+        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 8); }
         tc::mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -210,33 +285,42 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_base_slot)), "n"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
+    if (warp >= 4) {
+        // conv bias + BatchNorm(eval) + LeakyReLU as one branch-free form: BN->LReLU layers use (scale, shift', 1, 0),
+        // the LReLU->BN layer (encoder layer2's first conv, model.py:30-32) uses (1, bias, scale, shift)
+        for (int c = threadIdx.x - 128; c < p.coutp; c += TC_THREADS - 128) {
+            const float sc = __ldg(&p.scale[c]), sh = __ldg(&p.shift[c]), bi = __ldg(&p.bias[c]);
+            s_par[c] = p.lrelu_first ? make_float4(1.0f, bi, sc, sh) : make_float4(sc, sh, 1.0f, 0.0f);
+        }
+    }
     tc::fence_before_sync();
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_base_slot;
 
     if (warp == 0) {
-        // ===== TMA producer ==================================================================================
-        if (lane == 0) {
-            // row-strip mode: the apron rows of the sources are written by the neighbour GPUs; wait for this frame's flags
-            bool waited = false;
-            for (int i = 0; i < 4; ++i)
-                if (p.link.wait[i]) { while ((int)(tc::ld_acquire_sys(p.link.wait[i]) - p.link.wait_epoch[i]) < 0) { } waited = true; }
-            if (waited) asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (TMA) reads
-            if (p.resident) {                                        // the layer's whole weight set, once per CTA
-                tc::mbar_expect_tx(wfull, p.w_total_bytes);
-                for (uint32_t off = 0; off < p.w_total_bytes; off += 32768u) {
-                    const uint32_t n = p.w_total_bytes - off < 32768u ? p.w_total_bytes - off : 32768u;
-                    tc::bulk_load(smem_b + off, (const uint8_t*)p.wpack + off, n, wfull);
-                }
+        // ===== TMA producer: warp-uniform loop, one elected lane issues (same reason as the MMA role below) ==========
+        // row-strip mode: the apron rows of the sources are written by the neighbour GPUs; wait for this frame's flags
+        bool waited = false;
+        for (int i = 0; i < 4; ++i)
+            if (p.link.wait[i]) { while ((int)(tc::ld_acquire_sys(p.link.wait[i]) - p.link.wait_epoch[i]) < 0) { } waited = true; }
+        if (waited) asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (TMA) reads
+        if (p.resident && tc::elect_one()) {                         // the layer's whole weight set, once per CTA
+            tc::mbar_expect_tx(wfull, p.w_total_bytes);
+            for (uint32_t off = 0; off < p.w_total_bytes; off += 32768u) {
+                const uint32_t n = p.w_total_bytes - off < 32768u ? p.w_total_bytes - off : 32768u;
+                tc::bulk_load(smem_b + off, (const uint8_t*)p.wpack + off, n, wfull);
             }
-            int stage = 0; uint32_t phase = 0;
-            const uint32_t stage_tx = TC_A_BYTES + (p.resident ? 0u : p.b_stage_bytes);
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const int ph = item % p.nphases, tile = item / p.nphases;
-                const int x0 = (tile % p.tiles_x) * TC_TILE_W, y0 = (tile / p.tiles_x) * TC_TILE_H;
-                for (int c = 0; c < nchunks; ++c) {
-                    tc::mbar_wait(&empty[stage], phase ^ 1);
+        }
+        __syncwarp();
+        int stage = 0; uint32_t phase = 0;
+        const uint32_t stage_tx = TC_A_BYTES + (p.resident ? 0u : p.b_stage_bytes);
+        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
+            const int ph = item % p.nphases, tile = item / p.nphases;
+            const int x0 = (tile % p.tiles_x) * TC_TILE_W, y0 = (tile / p.tiles_x) * TC_TILE_H;
+            for (int c = 0; c < nchunks; ++c) {
+                tc::mbar_wait(&empty[stage], phase ^ 1);
+                if (tc::elect_one()) {
                     tc::mbar_expect_tx(&full[stage], stage_tx);
                     // halo tile origin: pixel (x0 - 1, y0 - 1) = buffer row y0 (apron offset +1); x < 0 / x >= W are zero filled
                     if (c < p.n0) tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, &p.mapA0, &full[stage], (x0 - 1) * 4, y0, c * 4);
@@ -244,50 +328,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     if (!p.resident)
                         tc::bulk_load(smem_b + (size_t)stage * p.b_stage_bytes, (const uint8_t*)p.wpack + (size_t)(ph * nchunks + c) * p.b_stage_bytes,
                                       p.b_stage_bytes, &full[stage]);
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
+                __syncwarp();
+                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
     } else if (warp == 1) {
-        // ===== MMA issuer (single lane) =========================================================================
-        if (lane == 0) {
-            // instruction descriptor: D = f32, A = B = tf32, both K-major, N = coutp, M = 128
-            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.coutp >> 3) << 17) | ((128u >> 4) << 24);
-            const uint32_t b_lbo = (uint32_t)p.coutp * 16u;                 // K-adjacent core matrices of B: one quad block of N rows
-            const uint32_t b_kstep = (uint32_t)p.coutp * 32u;               // one K = 8 step of one tap
-            if (p.resident) { tc::mbar_wait(wfull, 0); tc::fence_after_sync(); }
-            int stage = 0; uint32_t phase = 0;
-            int acc = 0; uint32_t acc_phase = 0;
-            for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-                const int ph = item % p.nphases;
-                tc::mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-                tc::fence_after_sync();
-                const uint32_t d_tmem = tmem_base + (uint32_t)acc * TC_ACC_COLS;
-                for (int c = 0; c < nchunks; ++c) {
-                    tc::mbar_wait(&full[stage], phase);
-                    tc::fence_after_sync();
-                    const uint32_t sa = tc::smem_u32(smem_a + (size_t)stage * TC_A_BYTES);
-                    const uint32_t sb = tc::smem_u32(smem_b) + (p.resident ? (uint32_t)(ph * nchunks + c) : (uint32_t)stage) * p.b_stage_bytes;
-                    for (int t = 0; t < p.ntaps; ++t) {
-                        const uint32_t a_tap = sa + (uint32_t)((1 + p.dy[ph][t]) * TC_ROW_PITCH + (1 + p.dx[ph][t]) * 16);
-                        const uint32_t b_tap = sb + (uint32_t)t * 2u * b_kstep;
-#pragma unroll
-                        for (int j = 0; j < 2; ++j) {
-                            const uint64_t adesc = tc::make_desc_nosw(a_tap + (uint32_t)j * 2u * TC_QUAD_PITCH, TC_QUAD_PITCH, TC_ROW_PITCH);
-                            const uint64_t bdesc = tc::make_desc_nosw(b_tap + (uint32_t)j * b_kstep, b_lbo, 128u);
-                            tc::mma_tf32(d_tmem, adesc, bdesc, idesc, (c | t | j) ? 1u : 0u);
-                        }
-                    }
-                    tc::mma_commit(&empty[stage]);                                    // frees the smem stage when the MMAs retire
-                    if (c == nchunks - 1) tc::mma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
-                }
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-            }
-        }
+        // ===== MMA issuer: the whole warp runs the (warp-uniform) loop so that descriptors live in uniform registers;
+        //       one elected lane issues.  One tcgen05.mma costs a handful of uniform-datapath adds here - issued from divergent
+        //       code the same loop cost ~135 cycles per MMA (R2UR + ELECT sequences) and was the kernel's bottleneck.
+        if (p.resident) { tc::mbar_wait(wfull, 0); tc::fence_after_sync(); }
+        if (p.ntaps == 9) tc::mma_role<9>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, lane);
+        else tc::mma_role<4>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, lane);
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> bias/BN/LeakyReLU -> CHW4 ============================================
         const int q = warp & 3;                                    // TMEM lane quarter this warp may read
+        const int half = (warp - 4) >> 2;                          // which of the alternating 16-column chunks this warp takes
         const int m = q * 32 + lane;                               // pixel of the tile == TMEM lane
         const int ty = m >> 3, tx = m & 7;
         const size_t oqs = p.out.quad_stride(), pqs = p.pool_out.quad_stride();
@@ -302,18 +358,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             tc::mbar_wait(&tmem_full[acc], acc_phase);
             tc::fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_ACC_COLS;
-            for (int c0 = 0; c0 < p.coutp; c0 += 16) {
+            for (int c0 = half * 16; c0 < p.coutp; c0 += 32) {
                 uint32_t r[16];
                 tc::tmem_ld16(taddr + c0, r);
                 tc::tmem_ld_wait();
                 float o[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
-                    const float a = __uint_as_float(r[j]);
-                    const float sc = __ldg(&p.scale[c0 + j]), sh = __ldg(&p.shift[c0 + j]);
-                    float v;
-                    if (p.lrelu_first) { v = a + __ldg(&p.bias[c0 + j]); v = v > 0.f ? v : 0.1f * v; v = fmaf(v, sc, sh); }
-                    else { v = fmaf(a, sc, sh); v = v > 0.f ? v : 0.1f * v; }
+                    const float4 k = s_par[c0 + j];                // broadcast LDS.128
+                    float v = fmaf(__uint_as_float(r[j]), k.x, k.y);
+                    v = fmaxf(v, 0.1f * v);                        // LeakyReLU(0.1)
+                    v = fmaf(v, k.z, k.w);
                     o[j] = p.round_out ? tc::round_tf32(v) : v;
                 }
                 if (valid) {
@@ -360,7 +415,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 }
             }
             tc::fence_before_sync();
-            tc::mbar_arrive(&tmem_empty[acc]);
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
@@ -502,7 +558,7 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     plan.grid = p.total_items < sms ? p.total_items : sms;
-    plan.smem = (size_t)p.stages * TC_A_BYTES + ((b_bytes + 15) & ~(size_t)15) + 1024 + 512;
+    plan.smem = (size_t)p.stages * TC_A_BYTES + ((b_bytes + 15) & ~(size_t)15) + 1024 + 256 + TC_ACC_COLS * 16;
     if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess)
         PTD_FAIL(PTD_ERR_CUDA, "tc conv: cannot reserve shared memory: %s", cudaGetErrorString(cudaGetLastError()));
     plan.valid = 1;
