@@ -35,7 +35,8 @@ ptd_pt_dump_final_paths ptd_pt_dump_image ptd_pt_bvh_stats ptd_dn_create ptd_dn_
 ptd_dn_forward_host ptd_dn_create_strip ptd_dn_padded_size ptd_dn_dump_hidden ptd_dn_launches_per_forward
 ptd_pt_launches_last_render ptd_dn_profile ptd_dn_launch_times ptd_dn_launch_name ptd_pt_profile
 ptd_pt_launch_times ptd_dn_strip_partition ptd_dn_strip_info_size ptd_dn_strip_export ptd_dn_strip_connect
-ptd_dn_forward_group""".split()
+ptd_dn_forward_group ptd_pt_create_strip ptd_pt_strip_info_size ptd_pt_strip_export ptd_pt_strip_connect
+ptd_pt_render_group""".split()
 
 
 class PtdError(RuntimeError):
@@ -93,6 +94,10 @@ def lib():
         L.ptd_dn_launch_name.restype = C.c_char_p
         L.ptd_pt_profile.argtypes = [C.c_void_p, C.c_int]
         L.ptd_pt_launch_times.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
+        L.ptd_pt_create_strip.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+        L.ptd_pt_strip_export.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.ptd_pt_strip_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
+        L.ptd_pt_render_group.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_dn_create_strip.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_void_p)]
         L.ptd_dn_strip_partition.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ptd_dn_strip_export.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
@@ -193,14 +198,43 @@ def frame_camera(cam, frame=0, dphi=0.002):
 class PathTracer:
     """pathtraceInit / pathtrace / pathtraceFree (pathtrace.h:6-8) behind ptd_pt_*."""
 
-    def __init__(self, scene, device=0, flags=0):
+    def __init__(self, scene, device=0, flags=0, strip=None):
+        """strip=(row0, rows): trace only those image rows (ptd_pt_create_strip, multi-GPU tiling)."""
         self.scene = scene
         self.h = C.c_void_p()
-        check(lib().ptd_pt_create(scene.h, device, flags, C.byref(self.h)), "ptd_pt_create")
         cam = scene.camera[0]
         self.W, self.H = int(cam["res"][0]), int(cam["res"][1])
-        self.P = self.W * self.H
+        if strip is None:
+            check(lib().ptd_pt_create(scene.h, device, flags, C.byref(self.h)), "ptd_pt_create")
+            self.P = self.W * self.H
+        else:
+            check(lib().ptd_pt_create_strip(scene.h, device, flags, strip[0], strip[1], C.byref(self.h)), "ptd_pt_create_strip")
+            self.P = self.W * strip[1]
+        self.strip = strip
         self.depth = scene.counts()[3]
+
+    def export_info(self):
+        n = lib().ptd_pt_strip_info_size()
+        buf = C.create_string_buffer(n)
+        check(lib().ptd_pt_strip_export(self.h, buf, n), "ptd_pt_strip_export")
+        return buf.raw
+
+    def connect(self, infos, my_rank):
+        """infos: the exported blobs of ALL strips in strip order (top first)."""
+        check(lib().ptd_pt_strip_connect(self.h, b"".join(infos), len(infos), my_rank), "ptd_pt_strip_connect")
+
+    @staticmethod
+    def render_group(strips, gbuf_ptrs, cam=None, iter=1, streams=None):
+        """Same-process strip group: one iteration, issued bounce by bounce over the handles (ptd_pt_render_group)."""
+        n = len(strips)
+        hs = (C.c_void_p * n)(*[s.h for s in strips])
+        g = (C.c_void_p * n)(*gbuf_ptrs)
+        st = (C.c_void_p * n)(*streams) if streams else None
+        camp = None
+        if cam is not None:
+            cam = np.ascontiguousarray(cam, CAM_DT).reshape(1)
+            camp = cam.ctypes.data
+        check(lib().ptd_pt_render_group(hs, n, camp, iter, g, st), "ptd_pt_render_group")
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -209,7 +243,7 @@ class PathTracer:
 
     def render_host(self, cam=None, iter=1):
         """== pathtrace(pbo, 0, iter) + the D2H of host_tensor (pathtrace.cu:525). Returns float32 [10,H,W]."""
-        out = np.empty((10, self.H, self.W), np.float32)
+        out = np.zeros((10, self.H, self.W), np.float32)
         camp = None
         if cam is not None:
             cam = np.ascontiguousarray(cam, CAM_DT).reshape(1)

@@ -147,27 +147,56 @@ __global__ void maxpool2_chw4(const DnTensor in, const DnTensor out) {
     *o = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
                      fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
 }
-// planar G-buffer [10][H][W] -> CHW4 with 16 channels (4 quads): the strip's rows plus its two apron rows (frame rows row0 - 1 ..
-// row0 + rows), zero outside the frame and in the bottom / right padding (decision D3); thread = pixel
-__global__ void pack_gbuffer(const float* __restrict__ g, int H, int W, int row0, const DnTensor out, int round_tf32) {
+// planar G-buffer [10][H][W] -> CHW4 with 16 channels (4 quads): the strip's rows (frame rows row0 .. row0 + rows - 1), zero in the
+// bottom / right padding (decision D3); thread = pixel.  Apron rows: zero at the frame border; where a neighbour strip exists
+// it pushes its boundary row into OUR apron (and we push ours into its), then the last block raises the neighbours' flags -
+// the same protocol as the conv epilogues (dn_conv_tc.cuh), so only the strip's own G-buffer rows need to be valid here.
+struct PackLink { DnTensor up, down; uint32_t* sig_up; uint32_t* sig_down; uint32_t* done; uint32_t epoch; };
+__global__ void pack_gbuffer(const float* __restrict__ g, int H, int W, int row0, const DnTensor out, int round_tf32, const PackLink link) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const int Wp = out.W;
-    if (i >= (size_t)(out.rows + 2) * Wp) return;
-    const int x = (int)(i % Wp), br = (int)(i / Wp), y = row0 + br - 1;
-    float v[16];
+    if (i < (size_t)(out.rows + 2) * Wp) {
+        const int x = (int)(i % Wp), br = (int)(i / Wp), y = row0 + br - 1;
+        const bool apron = br == 0 || br == out.rows + 1;
+        if (!(apron && ((br == 0 && link.up.base) || (br != 0 && link.down.base)))) {   // a neighbour owns that apron row
+            float v[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) v[c] = 0.f;
-    if (x < W && y >= 0 && y < H) {
+            for (int c = 0; c < 16; ++c) v[c] = 0.f;
+            if (!apron && x < W && y >= 0 && y < H) {
 #pragma unroll
-        for (int c = 0; c < 10; ++c) v[c] = g[(size_t)c * H * W + (size_t)y * W + x];
-        if (round_tf32) {
+                for (int c = 0; c < 10; ++c) v[c] = g[(size_t)c * H * W + (size_t)y * W + x];
+                if (round_tf32) {
 #pragma unroll
-            for (int c = 0; c < 10; ++c) v[c] = tc::round_tf32(v[c]);
+                    for (int c = 0; c < 10; ++c) v[c] = tc::round_tf32(v[c]);
+                }
+            }
+            float* d = out.base + ((size_t)br * Wp + x) * 4;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(d + (size_t)q * out.quad_stride()) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            if (br == 1 && link.up.base) {
+                float* pd = link.up.base + ((size_t)(link.up.rows + 1) * Wp + x) * 4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(pd + (size_t)q * link.up.quad_stride()) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
+            if (br == out.rows && link.down.base) {
+                float* pd = link.down.base + (size_t)x * 4;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(pd + (size_t)q * link.down.quad_stride()) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+            }
         }
     }
-    float* d = out.base + ((size_t)br * Wp + x) * 4;
-#pragma unroll
-    for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(d + (size_t)q * out.quad_stride()) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+    if (link.done) {
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const uint32_t old = atomicAdd(link.done, 1u);
+            if ((old + 1u) % gridDim.x == 0u) {
+                __threadfence_system();
+                if (link.sig_up) tc::st_release_sys(link.sig_up, link.epoch);
+                if (link.sig_down) tc::st_release_sys(link.sig_down, link.epoch);
+            }
+        }
+    }
 }
 // CHW4 quad 0 -> planar [3][H][W]: frame rows [r0, r0 + nrows) of this strip (tensor row 1 == frame row r0), cropped to W
 __global__ void unpack_rgb(const DnTensor in, int H, int W, int r0, int nrows, float* __restrict__ rgb) {
@@ -262,6 +291,7 @@ struct ptd_dn {
     ptd_strip_info peer_info[2];
     bool has_peer[2] = {false, false};
     uint32_t epoch = 0;
+    uint32_t* d_pack_done = nullptr;
     int parity = 0;
     int launches = 0;
     bool profiling = false;
@@ -311,6 +341,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
 #define DALLOC(var, floats) do { (var) = dalloc(floats); if (!(var)) return fail(PTD_ERR_CUDA); } while (0)
     DALLOC(h->d_gbuf, (size_t)10 * H * W);
     DALLOC(h->d_rgb, (size_t)3 * H * W);
+    { float* dd = nullptr; DALLOC(dd, 64); h->d_pack_done = (uint32_t*)dd; }
 
     // ---- activation arena: every tensor the convs read or write, one allocation (one IPC handle per strip) ----
     size_t arena_bytes = 0;
@@ -525,8 +556,14 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
         const DnTensor& in = h->tensors[h->t_in16];
         const size_t n = (size_t)(in.rows + 2) * in.W;
         mark(nullptr);
-        // rows row0 - 1 .. row0 + rows of the frame: the strip plus its two apron rows, straight from the G-buffer
-        pack_gbuffer<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gbuf, h->H, h->W, h->row0, in, tf32);
+        PackLink link;
+        memset(&link, 0, sizeof link);
+        if (h->has_peer[0] || h->has_peer[1]) {
+            link.done = h->d_pack_done; link.epoch = h->epoch;
+            if (h->has_peer[0]) { link.up = peer_tensor(h, 0, h->t_in16); link.sig_up = peer_flag(h, 0, h->t_in16, 1); }
+            if (h->has_peer[1]) { link.down = peer_tensor(h, 1, h->t_in16); link.sig_down = peer_flag(h, 1, h->t_in16, 0); }
+        }
+        pack_gbuffer<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gbuf, h->H, h->W, h->row0, in, tf32, link);
         ++h->launches;
         mark("pack_gbuffer");
     }
@@ -546,7 +583,7 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
                 k.done = L.d_done; k.epoch = h->epoch;
                 const int srcs[2] = {s0, s1};
                 for (int i = 0; i < 2; ++i) {
-                    if (srcs[i] < 0 || srcs[i] == h->t_in16) continue;                     // the packed input brings its own apron rows
+                    if (srcs[i] < 0) continue;
                     // a hidden state read by layer2's first conv was produced by the PREVIOUS frame (or just zeroed)
                     const bool prev = L.spec.kind == DN_L2A && i == 1;
                     if (prev && reset_hidden) continue;

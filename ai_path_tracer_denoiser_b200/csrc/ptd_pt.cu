@@ -18,6 +18,8 @@
 // algorithmic bytes are the survey's 44 B read + 44 B written per live path per bounce); coalescing comes from the
 // shared-memory staging, not from a layout change.  No host synchronisation happens inside a frame.
 #include <cuda_runtime.h>
+#include <unistd.h>
+#include <algorithm>
 #include <cstring>
 #include <vector>
 #include "ptd_internal.h"
@@ -26,6 +28,7 @@
 #define PT_BLOCK 128
 #define PT_WORDS 11                 // sizeof(PathSegment) / 4
 #define PT_STACK 64
+#define PT_MAX_RANKS 8
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ptd_set_error("%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return PTD_ERR_CUDA; } } while (0)
 
@@ -36,7 +39,12 @@ struct PtKernelParams {
     const float4* nodes; const float4* tris; int use_bvh;
     ptd_aabb mesh_box;
     ptd_camera cam;
-    int W, P, iter, bounce, trace_depth;
+    int W, P, iter, bounce, trace_depth;   // P = pixels of THIS handle (the whole frame, or its row strip)
+    int Pfull, pix0;                       // pixels of the whole frame (G-buffer plane stride); global index of this handle's first pixel
+    int rank, nranks;                      // row-strip mode: position among the strips of the frame (0, 1 when not tiled)
+    const unsigned long long* mail;        // [trace_depth + 1][PT_MAX_RANKS]: (epoch << 32 | live count) written by the strips above us
+    unsigned long long* peer_mail[PT_MAX_RANKS];   // the other strips' mailboxes (peer memory), null for ranks <= ours
+    unsigned epoch;
     const ptd_path_segment* src; ptd_path_segment* dst; ptd_path_segment* dead;
     int* counts;                    // counts[b] = live paths entering bounce b
     unsigned long long* status;     // decoupled look-back tile states of this bounce
@@ -101,14 +109,14 @@ __device__ __forceinline__ Ray camera_ray(const ptd_camera& cam, int W, int iter
 #define PT_SENTINEL 0x76543210
 
 struct TraceOut {
-    ptd_intersection* isx; float* gbuf; int P, W; bool write_gbuf;
+    ptd_intersection* isx; float* gbuf; int P, W, pix0; bool write_gbuf;   // P: pixels of the whole frame
 };
 __device__ __forceinline__ void write_hit(const TraceOut& o, int idx, float t, v3 normal, int mat, bool outside, v3 ip) {
     ptd_intersection r;
     r.t = t; r.surfaceNormal = normalize(normal); r.materialId = mat; r.is_inside = !outside; r.pad[0] = r.pad[1] = r.pad[2] = 0; r.intersect = ip;
     o.isx[idx] = r;
-    if (o.write_gbuf) {                                            // :295-304, x-mirrored like copy_data; bounce 0: pixelIndex == idx
-        const int col = idx % o.W, row = idx / o.W;
+    if (o.write_gbuf) {                                            // :295-304, x-mirrored like copy_data; bounce 0: pixelIndex == pix0 + idx
+        const int col = (o.pix0 + idx) % o.W, row = (o.pix0 + idx) / o.W;
         const size_t m = (size_t)(o.W - col - 1) + (size_t)row * o.W;
         o.gbuf[(size_t)o.P * 3 + m] = normal.x; o.gbuf[(size_t)o.P * 4 + m] = normal.y; o.gbuf[(size_t)o.P * 5 + m] = normal.z;
         o.gbuf[(size_t)o.P * 6 + m] = t;
@@ -120,7 +128,7 @@ __device__ __forceinline__ void write_miss(const TraceOut& o, int idx) {
     r.t = -1.0f;                                                   // ... and a miss only sets t (:283)
     o.isx[idx] = r;
     if (o.write_gbuf) {                                            // planes stay at the init memset's 0 (:119)
-        const int col = idx % o.W, row = idx / o.W;
+        const int col = (o.pix0 + idx) % o.W, row = (o.pix0 + idx) / o.W;
         const size_t m = (size_t)(o.W - col - 1) + (size_t)row * o.W;
         o.gbuf[(size_t)o.P * 3 + m] = 0.f; o.gbuf[(size_t)o.P * 4 + m] = 0.f; o.gbuf[(size_t)o.P * 5 + m] = 0.f; o.gbuf[(size_t)o.P * 6 + m] = 0.f;
     }
@@ -145,7 +153,7 @@ __global__ void __launch_bounds__(TR_BLOCK) pt_trace(const PtKernelParams p) {
     const ptd_geom* geoms = p.geoms_in_smem ? s_geoms : p.geoms;
     const ptd_aabb* gbounds = p.geoms_in_smem ? reinterpret_cast<const ptd_aabb*>(s_geoms + p.ngeoms) : p.geom_bounds;
     TraceOut out;
-    out.isx = p.isx; out.gbuf = p.gbuf; out.P = p.P; out.W = p.W; out.write_gbuf = FIRST && p.iter == 1;
+    out.isx = p.isx; out.gbuf = p.gbuf; out.P = p.Pfull; out.W = p.W; out.pix0 = p.pix0; out.write_gbuf = FIRST && p.iter == 1;
 
     // per-lane ray state
     int idx = 0;
@@ -174,7 +182,7 @@ __global__ void __launch_bounds__(TR_BLOCK) pt_trace(const PtKernelParams p) {
                 } else {
                     have = true;
                     if (FIRST) {
-                        ray = camera_ray(p.cam, p.W, p.iter, idx);
+                        ray = camera_ray(p.cam, p.W, p.iter, p.pix0 + idx);
                     } else {
                         const float* w = reinterpret_cast<const float*>(p.src) + (size_t)idx * PT_WORDS;
                         ray.o = V(w[0], w[1], w[2]); ray.d = V(w[3], w[4], w[5]);
@@ -313,7 +321,7 @@ template <bool FIRST>
 __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
     __shared__ __align__(16) uint32_t s_words[PT_BLOCK * PT_WORDS];                  // 5632 B staging (loads, then compacted stores)
     __shared__ __align__(16) uint32_t s_isx[PT_BLOCK * 9];                           // 4608 B: the tile's ShadeableIntersections
-    __shared__ int s_tile, s_warp_kept[PT_BLOCK / 32], s_excl;
+    __shared__ int s_tile, s_warp_kept[PT_BLOCK / 32], s_excl, s_goff;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int n = FIRST ? p.P : p.counts[p.bounce];
@@ -321,7 +329,27 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
     __syncthreads();
     const int tile = s_tile;
     const int base = tile * PT_BLOCK;
-    if (base >= n) return;
+    if (base >= n) {
+        if (n == 0 && tile == 0 && tid == 0) {                            // nothing alive here: still tell the strips below
+            const unsigned long long m = (unsigned long long)p.epoch << 32;
+            for (int r = p.rank + 1; r < p.nranks; ++r)
+                if (p.peer_mail[r]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_mail[r] + (size_t)(p.bounce + 1) * PT_MAX_RANKS + p.rank), "l"(m) : "memory");
+        }
+        return;
+    }
+    if (tid == 0) {
+        // Row-strip mode: the reference seeds its RNG with the index in the frame-wide compacted array (pathtrace.cu:351).  Strips
+        // are contiguous pixel ranges and compaction is stable, so that index is (live paths of the strips above) + local index;
+        // the strips above published their live counts of this bounce into our mailbox (peer stores) when they compacted.
+        int goff = FIRST ? p.pix0 : 0;
+        if (!FIRST)
+            for (int r = 0; r < p.rank; ++r) {
+                unsigned long long m;
+                do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(m) : "l"(p.mail + (size_t)p.bounce * PT_MAX_RANKS + r) : "memory"); } while ((unsigned)(m >> 32) != p.epoch);
+                goff += (int)(unsigned)m;
+            }
+        s_goff = goff;                                                    // read after the next __syncthreads
+    }
     const int valid = min(PT_BLOCK, n - base);
     const int idx = base + tid;
     const bool active = tid < valid;
@@ -341,9 +369,9 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
     }
     if (FIRST) {
         if (active) {
-            ray = camera_ray(p.cam, p.W, p.iter, idx);
+            ray = camera_ray(p.cam, p.W, p.iter, p.pix0 + idx);
             color = V(1.0f, 1.0f, 1.0f);
-            pixelIndex = idx;
+            pixelIndex = p.pix0 + idx;
             rb = p.trace_depth;
         }
         __syncthreads();
@@ -383,7 +411,7 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
         const size_t mirrored = (size_t)(p.W - col - 1) + (size_t)row * p.W;          // x-mirror of copy_data / :297-299
         // ---- 2. shade (shadeMaterial, pathtrace.cu:333-390) -------------------------------------------------
         if (isx_t > 0.0f) {
-            Rng rng = make_rng(p.iter, idx, rb);
+            Rng rng = make_rng(p.iter, s_goff + idx, rb);                           // frame-wide compacted index
             const ptd_material m = p.materials[isx_mat];
             if (m.emittance > 0.0f) {
                 rb = 0;
@@ -397,21 +425,21 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
             rb = 0;
         }
         if (FIRST && p.iter == 1) {                                                     // :379-387
-            p.gbuf[(size_t)p.P * 7 + mirrored] = hit ? color.x : 0.f;
-            p.gbuf[(size_t)p.P * 8 + mirrored] = hit ? color.y : 0.f;
-            p.gbuf[(size_t)p.P * 9 + mirrored] = hit ? color.z : 0.f;
+            p.gbuf[(size_t)p.Pfull * 7 + mirrored] = hit ? color.x : 0.f;
+            p.gbuf[(size_t)p.Pfull * 8 + mirrored] = hit ? color.y : 0.f;
+            p.gbuf[(size_t)p.Pfull * 9 + mirrored] = hit ? color.z : 0.f;
         }
         keep = rb > 0;
         if (!keep) {
             // finalGather (:393-402) + copy_data (:81-94): every segment terminates exactly once per iteration, so its
             // throughput is accumulated and the radiance planes are emitted here instead of in two extra passes over P.
-            float* img = p.image + (size_t)pixelIndex * 3;
+            float* img = p.image + (size_t)(pixelIndex - p.pix0) * 3;
             v3 acc = add(p.iter != 1 ? V(img[0], img[1], img[2]) : V(0.f, 0.f, 0.f), color);
             img[0] = acc.x; img[1] = acc.y; img[2] = acc.z;
             const float fi = (float)p.iter;
             p.gbuf[mirrored] = __fdiv_rn(acc.x, fi);
-            p.gbuf[(size_t)p.P + mirrored] = __fdiv_rn(acc.y, fi);
-            p.gbuf[(size_t)p.P * 2 + mirrored] = __fdiv_rn(acc.z, fi);
+            p.gbuf[(size_t)p.Pfull + mirrored] = __fdiv_rn(acc.y, fi);
+            p.gbuf[(size_t)p.Pfull * 2 + mirrored] = __fdiv_rn(acc.z, fi);
         }
     }
 
@@ -442,7 +470,12 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
             st_status(&p.status[tile], (2ull << 32) | (unsigned)(excl + block_kept));
         }
         s_excl = excl;
-        if (base + PT_BLOCK >= n) p.counts[p.bounce + 1] = excl + block_kept;            // last tile publishes the live count
+        if (base + PT_BLOCK >= n) {                                                       // last tile publishes the live count
+            p.counts[p.bounce + 1] = excl + block_kept;
+            const unsigned long long m = ((unsigned long long)p.epoch << 32) | (unsigned)(excl + block_kept);
+            for (int r = p.rank + 1; r < p.nranks; ++r)                                    // ... and mails it to the strips below (NVLink peer stores)
+                if (p.peer_mail[r]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_mail[r] + (size_t)(p.bounce + 1) * PT_MAX_RANKS + p.rank), "l"(m) : "memory");
+        }
     }
     const int local_rank = warp_off + lane_rank;
     if (keep) {
@@ -510,7 +543,7 @@ __global__ void sort_scatter(const int* __restrict__ keys, const int* __restrict
 }
 
 __global__ void export_rgba8(const float* __restrict__ image, int W, int H, int iter, uchar4* __restrict__ pbo) {   // sendImageToPBO :59-79
-    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y * blockDim.y + threadIdx.y;   // H: rows of this handle
     if (x >= W || y >= H) return;
     const int index = x + y * W;
     const float* pix = image + (size_t)index * 3;
@@ -524,7 +557,11 @@ __global__ void export_rgba8(const float* __restrict__ image, int W, int H, int 
 struct ptd_pt {
     int device = 0;
     unsigned flags = 0;
-    int W = 0, H = 0, P = 0, depth = 0, ngeoms = 0, nmaterials = 0, nfaces = 0, ntiles = 0;
+    int W = 0, H = 0, P = 0, depth = 0, ngeoms = 0, nmaterials = 0, nfaces = 0, ntiles = 0;   // P: pixels of this handle (frame or strip)
+    int Pfull = 0, row0 = 0, rows = 0;                        // whole-frame pixels; this handle's image rows [row0, row0 + rows)
+    int rank = 0, nranks = 1; unsigned epoch = 0;
+    unsigned long long* d_mail = nullptr;                     // [depth + 1][PT_MAX_RANKS], written by the strips above (peer stores)
+    unsigned long long* peer_mail[PT_MAX_RANKS] = {nullptr}; bool peer_ipc[PT_MAX_RANKS] = {false};
     ptd_camera cam;
     ptd_aabb mesh_box;
     ptd_geom* d_geoms = nullptr; ptd_aabb* d_geom_bounds = nullptr; ptd_material* d_materials = nullptr; ptd_face* d_faces = nullptr;
@@ -538,7 +575,7 @@ struct ptd_pt {
     int* d_counts = nullptr; int* d_ticket = nullptr; unsigned long long* d_status = nullptr;
     int* d_keys = nullptr; int* d_hist = nullptr; int sort_blocks = 0;
     ptd_path_segment* d_trace_paths = nullptr; ptd_intersection* d_trace_isx = nullptr;
-    int final_buf = 0;
+    int final_buf = 0, cur = 0, nmark = 0;
     int launches = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> events;
@@ -558,13 +595,27 @@ extern "C" void ptd_pt_destroy(ptd_pt* h) {
     cudaFree(h->d_geoms); cudaFree(h->d_geom_bounds); cudaFree(h->d_materials); cudaFree(h->d_faces); cudaFree(h->d_nodes); cudaFree(h->d_tris);
     for (int i = 0; i < 3; ++i) cudaFree(h->d_paths[i]);
     cudaFree(h->d_dead); cudaFree(h->d_isx); cudaFree(h->d_image); cudaFree(h->d_gbuf_own); cudaFree(h->d_ctl); cudaFree(h->d_keys); cudaFree(h->d_hist);
-    cudaFree(h->d_trace_paths); cudaFree(h->d_trace_isx);
+    cudaFree(h->d_trace_paths); cudaFree(h->d_trace_isx); cudaFree(h->d_mail);
+    for (int r = 0; r < PT_MAX_RANKS; ++r) if (h->peer_mail[r] && h->peer_ipc[r]) cudaIpcCloseMemHandle(h->peer_mail[r]);
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     delete h;
 }
 
+static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int row0, int rows, ptd_pt** out);
 extern "C" ptd_status ptd_pt_create(const ptd_scene* sc, int device, unsigned flags, ptd_pt** out) {
     if (!sc || !out) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_create: null argument");
+    return pt_create(sc, device, flags, 0, sc->camera.res_y, out);
+}
+// Row-strip mode: this handle traces image rows [row0, row0 + rows) of the frame.  Pixels are independent; the
+// only coupling is the frame-wide compacted index in the RNG seed, restored on the device from the live counts the strips
+// mail each other (pt_shade).  Material sort permutes paths across the whole frame and is not available in strip mode.
+extern "C" ptd_status ptd_pt_create_strip(const ptd_scene* sc, int device, unsigned flags, int row0, int rows, ptd_pt** out) {
+    if (!sc || !out) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_create_strip: null argument");
+    if (row0 < 0 || rows < 1 || row0 + rows > sc->camera.res_y) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_create_strip: rows [%d, %d) outside the %d-row frame", row0, row0 + rows, sc->camera.res_y);
+    if (flags & PTD_PT_SORT_MATERIAL) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_pt_create_strip: material sort is frame-wide and not available in row-strip mode");
+    return pt_create(sc, device, flags, row0, rows, out);
+}
+static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int row0, int rows, ptd_pt** out) {
     *out = nullptr;
     if (ptd_device_count() <= device || device < 0) PTD_FAIL(PTD_ERR_CUDA, "ptd_pt_create: CUDA device %d not available (no CPU fallback exists)", device);
     if (sc->trace_depth < 1 || sc->trace_depth > 1023) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_create: trace depth %d out of range", sc->trace_depth);
@@ -576,7 +627,8 @@ extern "C" ptd_status ptd_pt_create(const ptd_scene* sc, int device, unsigned fl
     ptd_pt* h = new ptd_pt();
     h->device = device; h->flags = flags;
     h->cam = sc->camera; h->mesh_box = sc->mesh_box;
-    h->W = sc->camera.res_x; h->H = sc->camera.res_y; h->P = h->W * h->H; h->depth = sc->trace_depth;
+    h->W = sc->camera.res_x; h->H = sc->camera.res_y; h->Pfull = h->W * h->H; h->depth = sc->trace_depth;
+    h->row0 = row0; h->rows = rows; h->P = h->W * rows;
     h->ngeoms = (int)sc->geoms.size(); h->nmaterials = (int)sc->materials.size(); h->nfaces = (int)sc->faces.size();
     h->ntiles = (h->P + PT_BLOCK - 1) / PT_BLOCK;
     const size_t P = (size_t)h->P;
@@ -614,6 +666,8 @@ extern "C" ptd_status ptd_pt_create(const ptd_scene* sc, int device, unsigned fl
     size_t off_counts = 0, off_ticket = ((size_t)(h->depth + 1) * 4 + 15) / 16 * 16, off_status = off_ticket + ((size_t)h->depth * 8 + 15) / 16 * 16;
     h->ctl_bytes = off_status + (size_t)h->depth * h->ntiles * 8;
     ALLOC(h->d_ctl, h->ctl_bytes);
+    ALLOC(h->d_mail, sizeof(unsigned long long) * (size_t)(h->depth + 1) * PT_MAX_RANKS);
+    cudaMemset(h->d_mail, 0, sizeof(unsigned long long) * (size_t)(h->depth + 1) * PT_MAX_RANKS);
     h->d_counts = (int*)(h->d_ctl + off_counts); h->d_ticket = (int*)(h->d_ctl + off_ticket); h->d_status = (unsigned long long*)(h->d_ctl + off_status);
     if (sort) {
         h->sort_blocks = (h->P + SORT_TILE - 1) / SORT_TILE;
@@ -637,13 +691,13 @@ extern "C" ptd_status ptd_pt_create(const ptd_scene* sc, int device, unsigned fl
     return PTD_OK;
 }
 
-extern "C" ptd_status ptd_pt_render(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf, void* stream_) {
-    if (!h || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_render: bad argument");
-    cudaStream_t st = (cudaStream_t)stream_;
+// Bounces [first, last) of one iteration; first == 0 also starts the frame.  ptd_pt_render runs them all; a same-process strip
+// group issues them bounce by bounce over the strips (ptd_pt_render_group).
+static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf, cudaStream_t st, int first, int last) {
     CUDA_TRY(cudaSetDevice(h->device));
     if (cam && (cam->res_x != h->W || cam->res_y != h->H)) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_render: camera resolution %dx%d differs from the handle's %dx%d", cam->res_x, cam->res_y, h->W, h->H);
     if (!gbuf) {
-        if (!h->d_gbuf_own) { CUDA_TRY(cudaMalloc((void**)&h->d_gbuf_own, sizeof(float) * 10 * (size_t)h->P)); CUDA_TRY(cudaMemset(h->d_gbuf_own, 0, sizeof(float) * 10 * (size_t)h->P)); }
+        if (!h->d_gbuf_own) { CUDA_TRY(cudaMalloc((void**)&h->d_gbuf_own, sizeof(float) * 10 * (size_t)h->Pfull)); CUDA_TRY(cudaMemset(h->d_gbuf_own, 0, sizeof(float) * 10 * (size_t)h->Pfull)); }
         gbuf = h->d_gbuf_own;
     }
     PtKernelParams p;
@@ -655,22 +709,26 @@ extern "C" ptd_status ptd_pt_render(ptd_pt* h, const ptd_camera* cam, int iter, 
     p.mesh_box = h->mesh_box;
     p.cam = cam ? *cam : h->cam;
     p.W = h->W; p.P = h->P; p.iter = iter; p.trace_depth = h->depth;
+    p.Pfull = h->Pfull; p.pix0 = h->row0 * h->W; p.rank = h->rank; p.nranks = h->nranks; p.mail = h->d_mail;
+    for (int r = 0; r < PT_MAX_RANKS; ++r) p.peer_mail[r] = h->peer_mail[r];
     p.counts = h->d_counts; p.gbuf = gbuf; p.image = h->d_image; p.dead = h->d_dead;
     p.sort_keys = h->d_keys; p.trace_paths = h->d_trace_paths;
-    CUDA_TRY(cudaMemsetAsync(h->d_ctl, 0, h->ctl_bytes, st));
     const size_t smem = p.geoms_in_smem ? (sizeof(ptd_geom) + sizeof(ptd_aabb)) * h->ngeoms : 0;
     const bool sort = (h->flags & PTD_PT_SORT_MATERIAL) != 0;
-    int cur = 0;
-    h->launches = 0;
-    int nmark = 0;
     auto mark = [&]() {
         if (!h->profiling) return;
-        if ((int)h->events.size() <= nmark) { cudaEvent_t e; cudaEventCreate(&e); h->events.push_back(e); }
-        cudaEventRecord(h->events[nmark++], st);
+        if ((int)h->events.size() <= h->nmark) { cudaEvent_t e; cudaEventCreate(&e); h->events.push_back(e); }
+        cudaEventRecord(h->events[h->nmark++], st);
     };
-    mark();
-    for (int b = 0; b < h->depth; ++b) {
-        const int nxt = (cur + 1) % (sort ? 3 : 2);
+    if (first == 0) {
+        h->epoch += 1;
+        CUDA_TRY(cudaMemsetAsync(h->d_ctl, 0, h->ctl_bytes, st));
+        h->cur = 0; h->launches = 0; h->nmark = 0;
+        mark();
+    }
+    p.epoch = h->epoch;
+    for (int b = first; b < last && b < h->depth; ++b) {
+        const int cur = h->cur, nxt = (cur + 1) % (sort ? 3 : 2);
         p.bounce = b;
         p.src = h->d_paths[cur]; p.dst = h->d_paths[nxt];
         p.status = h->d_status + (size_t)b * h->ntiles;
@@ -683,19 +741,93 @@ extern "C" ptd_status ptd_pt_render(ptd_pt* h, const ptd_camera* cam, int iter, 
         else pt_shade<false><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
         h->launches += 2;
         mark();
-        cur = nxt;
+        h->cur = nxt;
         if (sort && b + 1 < h->depth) {
-            const int nb = std::max(h->nmaterials, 1), srt = (cur + 1) % 3;
+            const int nb = std::max(h->nmaterials, 1), srt = (h->cur + 1) % 3;
             sort_hist<<<h->sort_blocks, SORT_TILE, nb * sizeof(int), st>>>(h->d_keys, h->d_counts + b + 1, nb, h->sort_blocks, h->d_hist);
             sort_scan<<<1, 1024, 0, st>>>(h->d_hist, nb * h->sort_blocks);
-            sort_scatter<<<h->sort_blocks, SORT_TILE, 0, st>>>(h->d_keys, h->d_counts + b + 1, nb, h->sort_blocks, h->d_hist, h->d_paths[cur], h->d_paths[srt]);
+            sort_scatter<<<h->sort_blocks, SORT_TILE, 0, st>>>(h->d_keys, h->d_counts + b + 1, nb, h->sort_blocks, h->d_hist, h->d_paths[h->cur], h->d_paths[srt]);
             h->launches += 3;
-            cur = srt;
+            h->cur = srt;
         }
     }
-    h->final_buf = cur;
-    if (h->profiling) h->timed_launches = nmark - 1;
+    if (last >= h->depth) {
+        h->final_buf = h->cur;
+        if (h->profiling) h->timed_launches = h->nmark - 1;
+    }
     CUDA_TRY(cudaGetLastError());
+    return PTD_OK;
+}
+
+extern "C" ptd_status ptd_pt_render(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf, void* stream_) {
+    if (!h || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_render: bad argument");
+    return pt_run(h, cam, iter, gbuf, (cudaStream_t)stream_, 0, h->depth);
+}
+
+// Same-process strip group (tests; single-process multi-GPU): bounce by bounce over the strips in rank order, so that on one
+// GPU - where the strips' kernels run one after the other - every live count a kernel waits for has already been mailed.
+extern "C" ptd_status ptd_pt_render_group(ptd_pt** hs, int n, const ptd_camera* cam, int iter, float* const* gbufs, void* const* streams) {
+    if (!hs || n < 1 || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_render_group: bad argument");
+    for (int b = 0; b < hs[0]->depth; ++b)
+        for (int i = 0; i < n; ++i) {
+            ptd_status rc = pt_run(hs[i], cam, iter, gbufs ? gbufs[i] : nullptr, streams ? (cudaStream_t)streams[i] : nullptr, b, b + 1);
+            if (rc != PTD_OK) return rc;
+        }
+    return PTD_OK;
+}
+
+struct ptd_pt_strip_info { unsigned char ipc[64]; unsigned long long mail; int pid_tag, device, row0, rows, W, H, depth, reserved; };
+extern "C" int ptd_pt_strip_info_size(void) { return (int)sizeof(ptd_pt_strip_info); }
+extern "C" ptd_status ptd_pt_strip_export(ptd_pt* h, void* info_out, int capacity) {
+    if (!h || !info_out || capacity < (int)sizeof(ptd_pt_strip_info)) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_strip_export: need a buffer of %zu bytes", sizeof(ptd_pt_strip_info));
+    CUDA_TRY(cudaSetDevice(h->device));
+    ptd_pt_strip_info info;
+    memset(&info, 0, sizeof info);
+    cudaIpcMemHandle_t ipc;
+    if (cudaIpcGetMemHandle(&ipc, h->d_mail) == cudaSuccess) memcpy(info.ipc, &ipc, sizeof ipc);
+    else cudaGetLastError();
+    info.mail = (unsigned long long)(uintptr_t)h->d_mail;
+    info.pid_tag = (int)getpid(); info.device = h->device; info.row0 = h->row0; info.rows = h->rows; info.W = h->W; info.H = h->H; info.depth = h->depth;
+    memcpy(info_out, &info, sizeof info);
+    return PTD_OK;
+}
+// infos: the nranks exported blobs in strip order (top strip first), back to back; my_rank: this handle's position.
+extern "C" ptd_status ptd_pt_strip_connect(ptd_pt* h, const void* infos, int nranks, int my_rank) {
+    if (!h || !infos || nranks < 1 || nranks > PT_MAX_RANKS || my_rank < 0 || my_rank >= nranks) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_strip_connect: bad argument (at most %d strips)", PT_MAX_RANKS);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const ptd_pt_strip_info* in = (const ptd_pt_strip_info*)infos;
+    int row = 0;
+    for (int r = 0; r < nranks; ++r) {
+        ptd_pt_strip_info info;
+        memcpy(&info, &in[r], sizeof info);
+        if (info.W != h->W || info.H != h->H || info.depth != h->depth || info.row0 != row) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_strip_connect: strip %d does not continue the frame at row %d", r, row);
+        row += info.rows;
+        if (r == my_rank && (info.row0 != h->row0 || info.rows != h->rows)) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_strip_connect: blob %d is not this handle's", r);
+    }
+    if (row != h->H) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_strip_connect: the strips cover %d of %d rows", row, h->H);
+    for (int r = 0; r < PT_MAX_RANKS; ++r) {
+        if (h->peer_mail[r] && h->peer_ipc[r]) cudaIpcCloseMemHandle(h->peer_mail[r]);
+        h->peer_mail[r] = nullptr; h->peer_ipc[r] = false;
+    }
+    for (int r = my_rank + 1; r < nranks; ++r) {                      // we only ever write to the strips below us
+        ptd_pt_strip_info info;
+        memcpy(&info, &in[r], sizeof info);
+        if (info.pid_tag == (int)getpid()) {
+            if (info.device != h->device) {
+                cudaError_t e = cudaDeviceEnablePeerAccess(info.device, 0);
+                if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ptd_set_error("ptd_pt_strip_connect: no peer access %d -> %d: %s", h->device, info.device, cudaGetErrorString(e)); return PTD_ERR_CUDA; }
+                cudaGetLastError();
+            }
+            h->peer_mail[r] = (unsigned long long*)(uintptr_t)info.mail;
+        } else {
+            cudaIpcMemHandle_t ipc;
+            memcpy(&ipc, info.ipc, sizeof ipc);
+            void* q = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&q, ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_mail[r] = (unsigned long long*)q; h->peer_ipc[r] = true;
+        }
+    }
+    h->rank = my_rank; h->nranks = nranks;
     return PTD_OK;
 }
 
@@ -703,15 +835,15 @@ extern "C" ptd_status ptd_pt_render_host(ptd_pt* h, const ptd_camera* cam, int i
     if (!h || !host_tensor) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_render_host: null argument");
     ptd_status rc = ptd_pt_render(h, cam, iter, nullptr, nullptr);
     if (rc != PTD_OK) return rc;
-    CUDA_TRY(cudaMemcpy(host_tensor, h->d_gbuf_own, sizeof(float) * 10 * (size_t)h->P, cudaMemcpyDeviceToHost));   // pathtrace.cu:525
+    CUDA_TRY(cudaMemcpy(host_tensor, h->d_gbuf_own, sizeof(float) * 10 * (size_t)h->Pfull, cudaMemcpyDeviceToHost));   // pathtrace.cu:525
     return PTD_OK;
 }
 
 extern "C" ptd_status ptd_pt_export_rgba8(ptd_pt* h, int iter, unsigned char* pbo, void* stream_) {
     if (!h || !pbo || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_export_rgba8: bad argument");
     CUDA_TRY(cudaSetDevice(h->device));
-    dim3 b(8, 8), g((h->W + 7) / 8, (h->H + 7) / 8);
-    export_rgba8<<<g, b, 0, (cudaStream_t)stream_>>>(h->d_image, h->W, h->H, iter, (uchar4*)pbo);
+    dim3 b(8, 8), g((h->W + 7) / 8, (h->rows + 7) / 8);
+    export_rgba8<<<g, b, 0, (cudaStream_t)stream_>>>(h->d_image, h->W, h->rows, iter, (uchar4*)pbo + (size_t)h->row0 * h->W);
     CUDA_TRY(cudaGetLastError());
     return PTD_OK;
 }

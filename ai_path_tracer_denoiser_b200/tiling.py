@@ -1,0 +1,65 @@
+"""Row-strip tiling of one frame over the GPUs of a box: one process per GPU (torchrun), torch.distributed only for the
+host-side plumbing (exchanging the strips' IPC blobs once at start-up, barriers); the data path is libptd.so's kernels
+storing halo rows / live counts straight into the neighbours' memory over NVLink (include/ptd.h, "row-strip mode").
+
+    rank r owns padded rows [row0, row0 + rows) of the frame (32-row groups split evenly, SURVEY.md 8e / decision D7):
+      path tracer strip   image rows  [row0, min(row0 + rows, H))
+      denoiser strip      padded rows [row0, row0 + rows)
+"""
+import numpy as np
+
+from . import capi
+
+
+def strip_rows(H, world, rank):
+    """((dn_row0, dn_rows), (pt_row0, pt_rows)) of `rank`."""
+    r0, rows = capi.strip_partition(H, world, rank)
+    return (r0, rows), (r0, min(r0 + rows, H) - r0)
+
+
+def exchange_blobs(blob, dist=None, world=1):
+    """All-gather one bytes blob per rank (host side, any backend).  Returns the list in rank order."""
+    if dist is None or world == 1:
+        return [blob]
+    import torch
+    t = torch.frombuffer(bytearray(blob), dtype=torch.uint8).clone()
+    dev = None
+    if dist.get_backend() == "nccl":
+        dev = torch.device("cuda", torch.cuda.current_device())
+        t = t.to(dev)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    return [bytes(o.cpu().numpy().tobytes()) for o in out]
+
+
+def neighbours(blobs, rank):
+    """(up, down) blobs of `rank` (None at the frame border)."""
+    return (blobs[rank - 1] if rank > 0 else None), (blobs[rank + 1] if rank + 1 < len(blobs) else None)
+
+
+class StripPipeline:
+    """Path tracer + denoiser of this rank's strip, connected to the other ranks' strips."""
+
+    def __init__(self, scene, weights_path, rank, world, device, dist=None, dn_flags=capi.DN_TF32):
+        cam = scene.camera[0]
+        self.W, self.H = int(cam["res"][0]), int(cam["res"][1])
+        self.rank, self.world = rank, world
+        self.dn_rows, self.pt_rows = strip_rows(self.H, world, rank)
+        if world == 1:
+            self.pt = capi.PathTracer(scene, device=device)
+            self.dn = capi.Denoiser(weights_path, self.H, self.W, device=device, flags=dn_flags)
+            return
+        self.pt = capi.PathTracer(scene, device=device, strip=self.pt_rows)
+        self.dn = capi.Denoiser(weights_path, self.H, self.W, device=device, flags=dn_flags, strip=self.dn_rows)
+        pt_blobs = exchange_blobs(self.pt.export_info(), dist, world)
+        dn_blobs = exchange_blobs(self.dn.export_info(), dist, world)
+        self.pt.connect(pt_blobs, rank)
+        up, down = neighbours(dn_blobs, rank)
+        self.dn.connect(up, down)
+        if dist is not None:
+            dist.barrier()
+
+    def frame(self, cam, gbuf_ptr, rgb_ptr, reset, stream=None):
+        """One frame of the render loop for this strip (asynchronous on `stream`)."""
+        self.pt.render(gbuf_ptr, cam=np.ascontiguousarray(cam), iter=1, stream=stream)
+        self.dn.forward(gbuf_ptr, rgb_ptr, reset, stream=stream)

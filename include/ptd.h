@@ -89,6 +89,17 @@ enum {
 /* Uploads the scene once (the reference re-uploads every frame, main.cpp:143-146) and builds the BVH. */
 ptd_status ptd_pt_create(const ptd_scene*, int device, unsigned flags, ptd_pt** out);
 void ptd_pt_destroy(ptd_pt*);
+/* Row-strip mode (multi-GPU): the handle traces image rows [row0, row0 + rows) only and writes those rows of the FRAME-sized
+ * G-buffer.  Results are bit-identical to the untiled render: the frame-wide compacted index that seeds the reference's RNG
+ * (pathtrace.cu:351) is rebuilt on the device from live counts the strips mail each other over NVLink.  Setup: every rank
+ * exports a ptd_pt_strip_info_size()-byte blob, the ranks all-gather them (host side) and each passes the concatenation, in
+ * strip order, to ptd_pt_strip_connect.  All ranks must render the same camera / iter in the same order.  No material sort. */
+ptd_status ptd_pt_create_strip(const ptd_scene*, int device, unsigned flags, int row0, int rows, ptd_pt** out);
+int ptd_pt_strip_info_size(void);
+ptd_status ptd_pt_strip_export(ptd_pt*, void* info_out, int capacity);
+ptd_status ptd_pt_strip_connect(ptd_pt*, const void* infos_in_strip_order, int nranks, int my_rank);
+/* Strips living in ONE process (tests; single-process multi-GPU): issues the iteration bounce by bounce across the handles. */
+ptd_status ptd_pt_render_group(ptd_pt** strips, int n, const ptd_camera* cam, int iter, float* const* gbuffers_dev, void* const* streams);
 /* One 1-spp iteration == pathtrace(pbo, frame, iter) (pathtrace.cu:422-528) for camera `cam` (NULL = the scene's).
  * Writes the 10-plane fp32 G-buffer [10][H][W] (pathtrace.cu:81-94,295-304,379-387; x-mirrored like the
  * reference) to device memory.  iter == 1 starts a new accumulation (what pathtraceInit's memsets do). Asynchronous. */

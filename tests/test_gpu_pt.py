@@ -167,3 +167,70 @@ def test_full_size_properties_720p():
     t2 = pt.render_host()                                   # fixed seed: every frame identical (main.cpp:164 camchanged)
     assert t1.tobytes() == t2.tobytes()
     assert np.isfinite(t1).all()
+
+
+def pt_strip_rows(capi, H, n):
+    """Image rows of the n strips: the denoiser's 32-row-aligned partition of the padded frame, clipped to H."""
+    parts = [capi.strip_partition(H, n, i) for i in range(n)]
+    return [(r0, min(r0 + rows, H) - r0) for r0, rows in parts]
+
+
+@pytest.mark.parametrize("scene,W,H,n", [("hall_64x48.txt", 96, 80, 3), ("cornell_specular_64x48.txt", 64, 72, 2)])
+def test_row_strips_equal_the_full_frame(scene, W, H, n):
+    """Multi-GPU tiling of the path tracer on ONE device: row strips, each its own handle; the frame-wide compacted index of the
+    RNG seed is rebuilt from the live counts the strips mail each other.  Everything must be bit-identical to the untiled
+    render: the G-buffer, the live counts (summed) and the concatenated per-bounce PathSegment arrays."""
+    capi = _capi()
+    import torch
+    sc = capi.Scene(path=os.path.join(SCENES, scene))
+    sc.set_resolution(W, H)
+    cam = capi.frame_camera(sc.camera[0], 5)
+    sc.set_camera(cam)
+    full = capi.PathTracer(sc, flags=capi.PT_TRACE)
+    ref = full.render_host()
+    ref_counts, run = full.live_counts()
+    rows = pt_strip_rows(capi, H, n)
+    assert sum(r for _, r in rows) == H
+    strips = [capi.PathTracer(sc, flags=capi.PT_TRACE, strip=r) for r in rows]
+    infos = [s.export_info() for s in strips]
+    for i, s in enumerate(strips):
+        s.connect(infos, i)
+    g = torch.zeros(10 * H * W, dtype=torch.float32, device="cuda")
+    for rep in range(2):                                           # second frame: the mailboxes carry a new epoch
+        g.zero_()
+        capi.PathTracer.render_group(strips, [g.data_ptr()] * n)
+        torch.cuda.synchronize()
+        assert g.cpu().numpy().reshape(10, H, W).tobytes() == ref.tobytes()
+    counts = [s.live_counts()[0] for s in strips]
+    assert [sum(c[b] for c in counts) for b in range(run)] == ref_counts[:run]
+    for b in range(run):
+        cat = np.concatenate([s.dump_paths(b) for s in strips])
+        _same(cat, full.dump_paths(b), "bounce %d paths (strips concatenated)" % b)
+
+
+def test_strip_pipeline_equals_full_pipeline(tmp_path):
+    """Path trace strips feeding denoiser strips (each strip only ever sees its own G-buffer rows) == the untiled frame loop."""
+    capi = _capi()
+    import torch
+    from ai_path_tracer_denoiser_b200 import weights
+    wfile = weights.save_weights(weights.synthetic_state_dict(1234), str(tmp_path / "w.ptdw"))
+    W, H, n = 96, 80, 3
+    sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
+    sc.set_resolution(W, H)
+    full_pt, full_dn = capi.PathTracer(sc), capi.Denoiser(wfile, H, W, flags=capi.DN_TF32)
+    parts = [capi.strip_partition(H, n, i) for i in range(n)]
+    pts = [capi.PathTracer(sc, strip=r) for r in pt_strip_rows(capi, H, n)]
+    dns = [capi.Denoiser(wfile, H, W, flags=capi.DN_TF32, strip=p) for p in parts]
+    pinfo, dinfo = [s.export_info() for s in pts], [s.export_info() for s in dns]
+    for i in range(n):
+        pts[i].connect(pinfo, i)
+        dns[i].connect(dinfo[i - 1] if i > 0 else None, dinfo[i + 1] if i + 1 < n else None)
+    gs = [torch.zeros(10 * H * W, dtype=torch.float32, device="cuda") for _ in range(n)]     # one G-buffer per strip: only its rows are filled
+    out = torch.zeros(3 * H * W, dtype=torch.float32, device="cuda")
+    for k in range(3):
+        cam = capi.frame_camera(sc.camera[0], k)
+        ref = full_dn.forward_host(full_pt.render_host(cam), reset=(k == 0))
+        capi.PathTracer.render_group(pts, [g.data_ptr() for g in gs], cam=cam)
+        capi.Denoiser.forward_group(dns, [g.data_ptr() for g in gs], [out.data_ptr()] * n, k == 0)
+        torch.cuda.synchronize()
+        assert out.cpu().numpy().reshape(3, H, W).tobytes() == ref.tobytes(), k
