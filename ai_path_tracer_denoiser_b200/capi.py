@@ -145,9 +145,12 @@ class Scene:
                                           int(a.get("iterations", 1)), C.byref(self.h)), "ptd_scene_from_arrays")
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().ptd_scene_free(self.h)
-            self.h = None
+        try:
+            if getattr(self, "h", None):
+                lib().ptd_scene_free(self.h)
+                self.h = None
+        except Exception:      # interpreter shutdown: module globals may already be gone
+            pass
 
     def counts(self):
         c = (C.c_int * 5)()
@@ -237,9 +240,12 @@ class PathTracer:
         check(lib().ptd_pt_render_group(hs, n, camp, iter, g, st), "ptd_pt_render_group")
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().ptd_pt_destroy(self.h)
-            self.h = None
+        try:
+            if getattr(self, "h", None):
+                lib().ptd_pt_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
     def render_host(self, cam=None, iter=1):
         """== pathtrace(pbo, 0, iter) + the D2H of host_tensor (pathtrace.cu:525). Returns float32 [10,H,W]."""
@@ -334,9 +340,12 @@ class Denoiser:
         check(lib().ptd_dn_strip_connect(self.h, up, down), "ptd_dn_strip_connect")
 
     def __del__(self):
-        if getattr(self, "h", None):
-            lib().ptd_dn_destroy(self.h)
-            self.h = None
+        try:
+            if getattr(self, "h", None):
+                lib().ptd_dn_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
 
     def forward_host(self, gbuf, reset):
         gbuf = np.ascontiguousarray(gbuf, np.float32)

@@ -129,3 +129,17 @@ def test_row_strips_equal_the_full_frame(nstrips, wfile):
         torch.cuda.synchronize()
         y = out.cpu().numpy().reshape(3, H, W)
         assert y.tobytes() == ref.tobytes(), (j, float(np.abs(y - ref).max()))
+
+
+def test_multi_process_strips_bit_exact_when_two_gpus():
+    """One process per GPU (torchrun), strips connected through CUDA IPC: tools/check_strips_multi.py.  Needs >= 2 GPUs."""
+    capi = _capi()
+    if capi.device_count() < 2:
+        pytest.skip("needs two GPUs (runs under `gpurun --gpus 2`)")
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29533", os.path.join(root, "tools", "check_strips_multi.py")], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("BIT-EXACT") == 2
