@@ -690,6 +690,52 @@ void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out) {
             }
         }
     }
+    // ---- collapse to the 4-wide layout: repeatedly open the child with the largest box until four children (or only leaves) ----
+    {
+        out.wide4.clear(); out.max_depth4 = 0;
+        auto area_of = [&](int ni) { Box b; for (int a = 0; a < 3; ++a) { b.lo[a] = out.nodes[ni].bmin[a]; b.hi[a] = out.nodes[ni].bmax[a]; } return box_area(b); };
+        auto leaf_code = [&](int ni) { const PtdBvhNode& c = out.nodes[ni]; return ~((c.first << 4) | (c.count - 1)); };
+        struct Job { int bin, slot_node, slot, depth; };      // binary node to turn into a wide node; where its index must be written
+        std::vector<Job> jobs;
+        auto emit = [&](int bin, int depth) -> int {           // creates the wide node of binary interior node `bin`, queues its interior children
+            const int me = (int)out.wide4.size();
+            out.wide4.push_back(PtdBvh4());
+            out.max_depth4 = std::max(out.max_depth4, depth);
+            int kids[4], nk = 0;
+            if (out.nodes[bin].count != 0) kids[nk++] = bin;   // the whole mesh is one leaf
+            else { kids[nk++] = out.nodes[bin].first; kids[nk++] = out.nodes[bin].first + 1; }
+            while (nk < 4) {
+                int best = -1; float ba = -1.f;
+                for (int k = 0; k < nk; ++k) if (out.nodes[kids[k]].count == 0) { float a = area_of(kids[k]); if (a > ba) { ba = a; best = k; } }
+                if (best < 0) break;
+                const int open = kids[best];
+                kids[best] = out.nodes[open].first; kids[nk++] = out.nodes[open].first + 1;
+            }
+            PtdBvh4& w = out.wide4[me];
+            for (int k = 0; k < 4; ++k) {
+                int code = 0;
+                if (k < nk) {
+                    const PtdBvhNode& c = out.nodes[kids[k]];
+                    w.f[k] = c.bmin[0]; w.f[4 + k] = c.bmax[0]; w.f[8 + k] = c.bmin[1]; w.f[12 + k] = c.bmax[1]; w.f[16 + k] = c.bmin[2]; w.f[20 + k] = c.bmax[2];
+                    if (c.count != 0) code = leaf_code(kids[k]);
+                    else jobs.push_back(Job{kids[k], me, k, depth + 1});
+                } else {
+                    w.f[k] = w.f[8 + k] = w.f[16 + k] = FLT_MAX; w.f[4 + k] = w.f[12 + k] = w.f[20 + k] = -FLT_MAX;
+                    code = ~0;                                  // never reached
+                }
+                memcpy(&w.f[24 + k], &code, 4);
+                w.f[28 + k] = 0.f;
+            }
+            return me;
+        };
+        emit(0, 1);
+        while (!jobs.empty()) {
+            Job j = jobs.back();
+            jobs.pop_back();
+            const int idx = emit(j.bin, j.depth);
+            memcpy(&out.wide4[j.slot_node].f[24 + j.slot], &idx, 4);
+        }
+    }
     out.tris.resize(order.size());
     for (size_t k = 0; k < order.size(); ++k) {
         const ptd_face& f = faces[order[k]];

@@ -44,9 +44,16 @@ struct PtdBvhTri {
 //   n2 = (c0.lo.z, c0.hi.z, c1.lo.z, c1.hi.z)   n3 = (child0, child1, -, -) as ints
 // child >= 0: index of an interior node; child < 0: leaf, ~child = (first << 4) | (count - 1) into the leaf-ordered triangles.
 struct PtdBvhWide { float f[16]; };
+// 4-wide traversal layout (128 B per interior node), collapsed from the binary tree: a ray's traversal is a chain of DEPENDENT
+// node loads (it is latency bound, not bandwidth bound), and four children per step halve the length of that chain.
+//   f[0..3] lo.x of children 0..3, f[4..7] hi.x, f[8..11] lo.y, f[12..15] hi.y, f[16..19] lo.z, f[20..23] hi.z,
+//   f[24..27] child codes as ints (same coding as above; an unused slot has an inverted box and is never hit), f[28..31] pad
+struct PtdBvh4 { float f[32]; };
 struct PtdBvh {
     std::vector<PtdBvhNode> nodes;
     std::vector<PtdBvhWide> wide;
+    std::vector<PtdBvh4> wide4;
+    int max_depth4 = 0;
     std::vector<PtdBvhTri> tris;
     int leaves = 0, max_leaf = 0, max_depth = 0;
 };

@@ -27,7 +27,7 @@
 
 #define PT_BLOCK 128
 #define PT_WORDS 11                 // sizeof(PathSegment) / 4
-#define PT_STACK 64
+#define PT_STACK 96
 #define PT_MAX_RANKS 8
 
 #define CUDA_TRY(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { ptd_set_error("%s:%d %s: %s", __FILE__, __LINE__, #x, cudaGetErrorString(e_)); return PTD_ERR_CUDA; } } while (0)
@@ -105,7 +105,12 @@ __device__ __forceinline__ Ray camera_ray(const ptd_camera& cam, int W, int iter
 // converged.  The result is the reference's 36-byte ShadeableIntersection record at slot `idx`, i.e. this kernel and
 // pt_shade exchange exactly the data computeIntersections and shadeMaterial exchange.
 #define TR_BLOCK 128
+#ifndef TR_REFILL
 #define TR_REFILL 22
+#endif
+#ifndef TR_MIN_BLOCKS
+#define TR_MIN_BLOCKS 8
+#endif
 #define PT_SENTINEL 0x76543210
 
 struct TraceOut {
@@ -135,7 +140,7 @@ __device__ __forceinline__ void write_miss(const TraceOut& o, int idx) {
 }
 
 template <bool FIRST>
-__global__ void __launch_bounds__(TR_BLOCK) pt_trace(const PtKernelParams p) {
+__global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKernelParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ptd_geom* s_geoms = reinterpret_cast<ptd_geom*>(smem_raw);
     const unsigned FULL = 0xffffffffu;
@@ -164,6 +169,7 @@ __global__ void __launch_bounds__(TR_BLOCK) pt_trace(const PtKernelParams p) {
     int best_face = -1;
     bool hit_face = false, geom_hit = false, outside = true;
     int node = PT_SENTINEL, leaf = 0, sp = 0, tri = 0, tri_end = 0;
+    int nearx = 0, neary = 0, nearz = 0;
     int stack[PT_STACK];
 
     for (;;) {
@@ -209,6 +215,7 @@ __global__ void __launch_bounds__(TR_BLOCK) pt_trace(const PtKernelParams p) {
                             idiry = 1.0f / (fabsf(ray.d.y) > ooeps ? ray.d.y : copysignf(ooeps, ray.d.y));
                             idirz = 1.0f / (fabsf(ray.d.z) > ooeps ? ray.d.z : copysignf(ooeps, ray.d.z));
                             oodx = ray.o.x * idirx; oody = ray.o.y * idiry; oodz = ray.o.z * idirz;
+                            nearx = idirx < 0.0f; neary = idiry < 0.0f; nearz = idirz < 0.0f;     // 0: the lo plane is entered first, 1: the hi plane
                             stack[0] = PT_SENTINEL; sp = 0; node = 0;
                         } else {                                                       // PTD_PT_NO_BVH: the reference's loop, test aid
                             for (int f = 0; f < p.nfaces; ++f) {
@@ -233,32 +240,34 @@ __global__ void __launch_bounds__(TR_BLOCK) pt_trace(const PtKernelParams p) {
                 const bool can_step = node >= 0 && node != PT_SENTINEL;
                 if (!__any_sync(FULL, can_step && searching)) break;
                 if (can_step) {
-                    // (256-bit LDG.E.ENL2.256 loads were measured SLOWER here than four 128-bit read-only loads: 3.70 vs 3.55 ms/frame)
-                    const float4* np = p.nodes + 4 * (size_t)node;
-                    const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), cn = __ldg(np + 3);
-                    // slabs; the 1e-5 relative slack keeps the (already padded) boxes conservative against the rounding of these products
-                    const float c0lox = n0.x * idirx - oodx, c0hix = n0.y * idirx - oodx, c0loy = n0.z * idiry - oody, c0hiy = n0.w * idiry - oody;
-                    const float c0loz = n2.x * idirz - oodz, c0hiz = n2.y * idirz - oodz;
-                    const float c1lox = n1.x * idirx - oodx, c1hix = n1.y * idirx - oodx, c1loy = n1.z * idiry - oody, c1hiy = n1.w * idiry - oody;
-                    const float c1loz = n2.z * idirz - oodz, c1hiz = n2.w * idirz - oodz;
-                    const float c0min = fmaxf(fmaxf(fminf(c0lox, c0hix), fminf(c0loy, c0hiy)), fmaxf(fminf(c0loz, c0hiz), 0.0f));
-                    const float c0max = fminf(fminf(fmaxf(c0lox, c0hix), fmaxf(c0loy, c0hiy)), fmaxf(c0loz, c0hiz));
-                    const float c1min = fmaxf(fmaxf(fminf(c1lox, c1hix), fminf(c1loy, c1hiy)), fmaxf(fminf(c1loz, c1hiz), 0.0f));
-                    const float c1max = fminf(fminf(fmaxf(c1lox, c1hix), fmaxf(c1loy, c1hiy)), fmaxf(c1loz, c1hiz));
+                    // 4-wide node (128 B): seven 16-byte read-only loads issued together.  (256-bit LDG.E.ENL2.256 loads were measured
+                    // slower than 128-bit ones; 32-byte 16-bit-quantised nodes were slower too: the chain of dependent loads, not
+                    // L1 request throughput, bounds this kernel - hence four children per step.)
+                    const float4* np = p.nodes + 8 * (size_t)node;
+                    const float4 nx = __ldg(np + nearx), fx = __ldg(np + (nearx ^ 1)), ny = __ldg(np + 2 + neary), fy = __ldg(np + 2 + (neary ^ 1));
+                    const float4 nz = __ldg(np + 4 + nearz), fz = __ldg(np + 4 + (nearz ^ 1)), cc = __ldg(np + 6);
+                    // slabs with the near / far plane picked per ray by the direction signs; the 1e-5 relative slack keeps the (already
+                    // padded) boxes conservative against the rounding of these products
                     const float tlim = t_min * 1.00001f;
-                    const bool h0 = c0min * 0.99999f <= c0max * 1.00001f && c0min * 0.99999f <= tlim;
-                    const bool h1 = c1min * 0.99999f <= c1max * 1.00001f && c1min * 0.99999f <= tlim;
-                    const int child0 = __float_as_int(cn.x), child1 = __float_as_int(cn.y);
-                    if (!h0 && !h1) {
-                        node = stack[sp--];
-                    } else {
-                        node = h0 ? child0 : child1;
-                        if (h0 && h1) {
-                            int other = child1;
-                            if (c1min < c0min) { other = node; node = child1; }
-                            stack[++sp] = other;
-                        }
+                    float d0, d1, d2, d3;
+#define PT_SLAB(k, d)                                                                                                        \
+                    {                                                                                                        \
+                        const float tn = fmaxf(fmaxf(nx.k * idirx - oodx, ny.k * idiry - oody), fmaxf(nz.k * idirz - oodz, 0.0f)); \
+                        const float tf = fminf(fminf(fx.k * idirx - oodx, fy.k * idiry - oody), fz.k * idirz - oodz);        \
+                        d = (tn * 0.99999f <= tf * 1.00001f && tn * 0.99999f <= tlim) ? tn : FLT_MAX;                        \
                     }
+                    PT_SLAB(x, d0) PT_SLAB(y, d1) PT_SLAB(z, d2) PT_SLAB(w, d3)
+#undef PT_SLAB
+                    int c0 = __float_as_int(cc.x), c1 = __float_as_int(cc.y), c2 = __float_as_int(cc.z), c3 = __float_as_int(cc.w);
+                    // sort the four (entry distance, child) pairs ascending: 5-comparator network
+#define PT_CSWAP(da, ca, db, cb) { const bool sw = db < da; const float td = sw ? db : da; db = sw ? da : db; da = td; const int tcn = sw ? cb : ca; cb = sw ? ca : cb; ca = tcn; }
+                    PT_CSWAP(d0, c0, d1, c1) PT_CSWAP(d2, c2, d3, c3) PT_CSWAP(d0, c0, d2, c2) PT_CSWAP(d1, c1, d3, c3) PT_CSWAP(d1, c1, d2, c2)
+#undef PT_CSWAP
+                    // the nearest hit child is visited next, the others wait on the stack, farthest at the bottom
+                    if (d3 < FLT_MAX) stack[++sp] = c3;
+                    if (d2 < FLT_MAX) stack[++sp] = c2;
+                    if (d1 < FLT_MAX) stack[++sp] = c1;
+                    node = d0 < FLT_MAX ? c0 : stack[sp--];
                     if (node < 0 && leaf >= 0) {            // first leaf found: postpone it and keep walking (speculatively)
                         searching = false;
                         leaf = node;
@@ -451,30 +460,42 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
     int warp_off = 0, block_kept = 0;
 #pragma unroll
     for (int w = 0; w < PT_BLOCK / 32; ++w) { if (w < warp) warp_off += s_warp_kept[w]; block_kept += s_warp_kept[w]; }
-    if (tid == 0) {
-        // decoupled look-back: state 1 = tile aggregate, 2 = inclusive prefix (value in the low 32 bits)
+    if (warp == 0) {
+        // decoupled look-back, one WARP wide: state 1 = tile aggregate, 2 = inclusive prefix (value in the low 32 bits).  Each trip
+        // reads the 32 predecessors' states at once; with ~1000 tiles in flight a one-thread walk was a chain of hundreds of
+        // dependent L2 reads and left the rest of the block at the barrier (ncu: stall_barrier 19.6 of 33 warps per issue).
         int excl = 0;
         if (tile == 0) {
-            st_status(&p.status[0], (2ull << 32) | (unsigned)block_kept);
+            if (lane == 0) st_status(&p.status[0], (2ull << 32) | (unsigned)block_kept);
         } else {
-            st_status(&p.status[tile], (1ull << 32) | (unsigned)block_kept);
-            int j = tile - 1;
+            if (lane == 0) st_status(&p.status[tile], (1ull << 32) | (unsigned)block_kept);
+            int j = tile - 1;                                              // nearest predecessor of this window
             for (;;) {
-                unsigned long long s = ld_status(&p.status[j]);
-                unsigned st = (unsigned)(s >> 32);
-                if (st == 0) continue;
-                excl += (int)(unsigned)s;
-                if (st == 2) break;
-                --j;
+                const int t = j - lane;
+                const unsigned long long sv = t >= 0 ? ld_status(&p.status[t]) : (2ull << 32);   // before tile 0: prefix 0
+                const unsigned st = (unsigned)(sv >> 32);
+                const unsigned has_prefix = __ballot_sync(0xffffffffu, st == 2u);
+                const unsigned not_ready = __ballot_sync(0xffffffffu, st == 0u);
+                const int first_prefix = has_prefix ? __ffs(has_prefix) - 1 : 31;
+                const unsigned needed = first_prefix == 31 ? 0xffffffffu : ((2u << first_prefix) - 1u);   // lanes 0 .. first_prefix
+                if (not_ready & needed) continue;                           // a predecessor has not published yet: look again
+                int v = lane <= first_prefix ? (int)(unsigned)sv : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                excl += v;
+                if (has_prefix) break;
+                j -= 32;
             }
-            st_status(&p.status[tile], (2ull << 32) | (unsigned)(excl + block_kept));
+            if (lane == 0) st_status(&p.status[tile], (2ull << 32) | (unsigned)(excl + block_kept));
         }
-        s_excl = excl;
-        if (base + PT_BLOCK >= n) {                                                       // last tile publishes the live count
-            p.counts[p.bounce + 1] = excl + block_kept;
-            const unsigned long long m = ((unsigned long long)p.epoch << 32) | (unsigned)(excl + block_kept);
-            for (int r = p.rank + 1; r < p.nranks; ++r)                                    // ... and mails it to the strips below (NVLink peer stores)
-                if (p.peer_mail[r]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_mail[r] + (size_t)(p.bounce + 1) * PT_MAX_RANKS + p.rank), "l"(m) : "memory");
+        if (lane == 0) {
+            s_excl = excl;
+            if (base + PT_BLOCK >= n) {                                                       // last tile publishes the live count
+                p.counts[p.bounce + 1] = excl + block_kept;
+                const unsigned long long m = ((unsigned long long)p.epoch << 32) | (unsigned)(excl + block_kept);
+                for (int r = p.rank + 1; r < p.nranks; ++r)                                    // ... and mails it to the strips below (NVLink peer stores)
+                    if (p.peer_mail[r]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_mail[r] + (size_t)(p.bounce + 1) * PT_MAX_RANKS + p.rank), "l"(m) : "memory");
+            }
         }
     }
     const int local_rank = warp_off + lane_rank;
@@ -650,9 +671,9 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
         PtdBvh bvh;
         ptd_build_bvh(sc->faces, bvh);
         h->bvh_nodes = (int)bvh.nodes.size(); h->bvh_leaves = bvh.leaves; h->bvh_max_leaf = bvh.max_leaf; h->bvh_max_depth = bvh.max_depth;
-        if (bvh.max_depth > PT_STACK) { ptd_set_error("ptd_pt_create: BVH depth %d exceeds traversal stack %d", bvh.max_depth, PT_STACK); ptd_pt_destroy(h); return PTD_ERR_UNSUPPORTED; }
-        ALLOC(h->d_nodes, sizeof(PtdBvhWide) * bvh.wide.size());
-        UPLOAD(h->d_nodes, bvh.wide.data(), sizeof(PtdBvhWide) * bvh.wide.size());
+        if (3 * bvh.max_depth4 + 2 > PT_STACK) { ptd_set_error("ptd_pt_create: BVH depth %d exceeds traversal stack %d", bvh.max_depth4, PT_STACK); ptd_pt_destroy(h); return PTD_ERR_UNSUPPORTED; }
+        ALLOC(h->d_nodes, sizeof(PtdBvh4) * bvh.wide4.size());
+        UPLOAD(h->d_nodes, bvh.wide4.data(), sizeof(PtdBvh4) * bvh.wide4.size());
         ALLOC(h->d_tris, sizeof(PtdBvhTri) * bvh.tris.size());
         UPLOAD(h->d_tris, bvh.tris.data(), sizeof(PtdBvhTri) * bvh.tris.size());
     }
