@@ -27,6 +27,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <cstdint>
 #include <cstring>
 #include <vector>
@@ -45,12 +46,16 @@
 #define TC_ACC_COLS 128
 #define TC_SMEM_BUDGET (200 * 1024)
 
-// An activation tensor in HBM: [nq = cp/4][rows + 2][W][4] fp32, image row r at buffer row r + 1 (rows 0 and rows + 1 are aprons)
+// An activation tensor in HBM: channel VECTORS of 16 bytes - [cp*esize/16][rows + 2][W][16 B] - i.e. quads of fp32 ("CHW4", esize 4)
+// or octets of fp16 ("CHW8", esize 2); image row r at buffer row r + 1 (rows 0 and rows + 1 are aprons).  Both element types share
+// the byte geometry (one pixel of one vector = 16 B), so addresses are computed in float units for both: vector v, pixel (y, x)
+// lives at base + v * quad_stride() + ((y + 1) * W + x) * 4.
 struct DnTensor {
     float* base = nullptr;
-    int cp = 0, rows = 0, W = 0;
-    __host__ __device__ size_t quad_stride() const { return (size_t)(rows + 2) * W * 4; }
-    __host__ __device__ size_t floats() const { return (size_t)(cp / 4) * quad_stride(); }
+    int cp = 0, rows = 0, W = 0, esize = 4;
+    __host__ __device__ int nvec() const { return cp * esize / 16; }
+    __host__ __device__ size_t quad_stride() const { return (size_t)(rows + 2) * W * 4; }      // floats (= 16-byte units * 4) between vectors
+    __host__ __device__ size_t floats() const { return (size_t)nvec() * quad_stride(); }
 };
 
 struct TcConvDesc {
@@ -77,7 +82,9 @@ struct TcStripLink {
 struct __align__(64) TcParams {
     CUtensorMap mapA0, mapA1;
     const float* wpack;                  // packed weights, stage-major
-    int n0, n1;                          // 16-channel chunks of source 0 / source 1
+    int n0, n1;                          // chunks (4 channel vectors = 16 fp32 / 32 fp16 channels) of source 0 / source 1
+    int v0, v1;                          // channel vectors of source 0 / source 1 (the last chunk of a source may hold only 2)
+    int half;                            // fp16 storage + kind::f16 (1) or fp32 storage + kind::tf32 (0)
     int ntaps, nphases;
     int dy[4][9], dx[4][9];
     int tiles_x, tiles_y, total_items;
@@ -188,16 +195,28 @@ __device__ __forceinline__ bool elect_one() {            // one lane of the (con
         "}" : "=r"(pred));
     return pred != 0;
 }
-__device__ __forceinline__ void mma_tf32_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        ".reg .b64 da, db;\n\t"
-        "mov.b64 da, {%1, %2};\n\t"
-        "mov.b64 db, {%3, %4};\n\t"
-        "setp.ne.b32 p, %6, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
-        "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+template <bool HALF>
+__device__ __forceinline__ void mma_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+    if (HALF)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+            "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            ".reg .b64 da, db;\n\t"
+            "mov.b64 da, {%1, %2};\n\t"
+            "mov.b64 db, {%3, %4};\n\t"
+            "setp.ne.b32 p, %6, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], da, db, %5, p;\n\t"
+            "}" ::"r"(tmem_d), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
 }  // namespace tc
 
@@ -205,12 +224,30 @@ namespace tc {
 }  // namespace tc
 
 namespace tc {
+// 16 consecutive output channels [c0, c0 + 16) of one pixel -> the tensor's channel vectors (row: address of the pixel in vector 0)
+__device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, const float* o) {
+    if (t.esize == 4) {
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd)
+            *reinterpret_cast<float4*>(row + (size_t)(c0 / 4 + qd) * t.quad_stride()) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
+    } else {
+#pragma unroll
+        for (int oc = 0; oc < 2; ++oc) {
+            uint4 v;
+            __half2 h0 = __floats2half2_rn(o[8 * oc], o[8 * oc + 1]), h1 = __floats2half2_rn(o[8 * oc + 2], o[8 * oc + 3]);
+            __half2 h2 = __floats2half2_rn(o[8 * oc + 4], o[8 * oc + 5]), h3 = __floats2half2_rn(o[8 * oc + 6], o[8 * oc + 7]);
+            v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1); v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
+            *reinterpret_cast<uint4*>(row + (size_t)(c0 / 8 + oc) * t.quad_stride()) = v;
+        }
+    }
+}
 // K-major no-swizzle descriptors, split into 32-bit words: lo = start >> 4 | (LBO >> 4) << 16, hi = SBO >> 4 | version 1 << 14
-template <int NTAPS>
+template <int NTAPS, bool HALF>
 __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full, uint64_t* empty,
                                          uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int lane) {
-    // instruction descriptor: D = f32, A = B = tf32, both K-major, N = coutp, M = 128
-    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.coutp >> 3) << 17) | ((128u >> 4) << 24);
+    // instruction descriptor: D = f32, A = B = tf32 (format 2) or f16 (format 0), both K-major, N = coutp, M = 128
+    const uint32_t fmt = HALF ? 0u : 2u;
+    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.coutp >> 3) << 17) | ((128u >> 4) << 24);
     const uint32_t a_hi = (uint32_t)(TC_ROW_PITCH >> 4) | (1u << 14);          // SBO = halo row pitch
     const uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);                  // SBO = next 8 output channels
     const uint32_t a_lbo = (uint32_t)(TC_QUAD_PITCH >> 4) << 16;              // LBO = next channel quad
@@ -234,13 +271,13 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
             fence_after_sync();
             const uint32_t a_base = (sa0 + (uint32_t)stage * (TC_A_BYTES >> 4)) | a_lbo;
             const uint32_t b_base = (sb0 + (p.resident ? (uint32_t)(ph * nchunks + c) : (uint32_t)stage) * b_stage16) | b_lbo;
+            // a source's last chunk may hold only two channel vectors (one K step); the other two are TMA zero fill
+            const bool two = (c < p.n0 ? p.v0 - 4 * c : p.v1 - 4 * (c - p.n0)) > 2;
             if (elect_one()) {
 #pragma unroll
                 for (int t = 0; t < NTAPS; ++t) {
-#pragma unroll
-                    for (int j = 0; j < 2; ++j)
-                        mma_tf32_w(d_tmem, a_base + aoff[t] + (uint32_t)j * (2u * TC_QUAD_PITCH >> 4), a_hi,
-                                   b_base + (uint32_t)(t * 2 + j) * b_kstep, b_hi, idesc, (t | j) ? 1u : (c ? 1u : 0u));
+                    mma_w<HALF>(d_tmem, a_base + aoff[t], a_hi, b_base + (uint32_t)(t * 2) * b_kstep, b_hi, idesc, t ? 1u : (c ? 1u : 0u));
+                    if (two) mma_w<HALF>(d_tmem, a_base + aoff[t] + (2u * TC_QUAD_PITCH >> 4), a_hi, b_base + (uint32_t)(t * 2 + 1) * b_kstep, b_hi, idesc, 1u);
                 }
                 mma_commit(&empty[stage]);                                    // frees the smem stage when the MMAs retire
                 if (c == nchunks - 1) mma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
@@ -254,6 +291,7 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
 }  // namespace tc
 
 // shared memory carve-up (offsets from the 1024-aligned base): [A stage 0..S) | B (resident: whole layer; streamed: S stages) | barriers
+template <bool HALF>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -323,8 +361,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (tc::elect_one()) {
                     tc::mbar_expect_tx(&full[stage], stage_tx);
                     // halo tile origin: pixel (x0 - 1, y0 - 1) = buffer row y0 (apron offset +1); x < 0 / x >= W are zero filled
-                    if (c < p.n0) tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, &p.mapA0, &full[stage], (x0 - 1) * 4, y0, c * 4);
-                    else tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, &p.mapA1, &full[stage], (x0 - 1) * 4, y0, (c - p.n0) * 4);
+                    if (c < p.n0) tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, &p.mapA0, &full[stage], (x0 - 1) * (HALF ? 8 : 4), y0, c * 4);
+                    else tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, &p.mapA1, &full[stage], (x0 - 1) * (HALF ? 8 : 4), y0, (c - p.n0) * 4);
                     if (!p.resident)
                         tc::bulk_load(smem_b + (size_t)stage * p.b_stage_bytes, (const uint8_t*)p.wpack + (size_t)(ph * nchunks + c) * p.b_stage_bytes,
                                       p.b_stage_bytes, &full[stage]);
@@ -338,15 +376,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         //       one elected lane issues.  One tcgen05.mma costs a handful of uniform-datapath adds here - issued from divergent
         //       code the same loop cost ~135 cycles per MMA (R2UR + ELECT sequences) and was the kernel's bottleneck.
         if (p.resident) { tc::mbar_wait(wfull, 0); tc::fence_after_sync(); }
-        if (p.ntaps == 9) tc::mma_role<9>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, lane);
-        else tc::mma_role<4>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, lane);
+        if (p.ntaps == 9) tc::mma_role<9, HALF>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, lane);
+        else tc::mma_role<4, HALF>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, lane);
     } else if (warp >= 4) {
         // ===== epilogue: TMEM -> registers -> bias/BN/LeakyReLU -> CHW4 ============================================
         const int q = warp & 3;                                    // TMEM lane quarter this warp may read
         const int half = (warp - 4) >> 2;                          // which of the alternating 16-column chunks this warp takes
         const int m = q * 32 + lane;                               // pixel of the tile == TMEM lane
         const int ty = m >> 3, tx = m & 7;
-        const size_t oqs = p.out.quad_stride(), pqs = p.pool_out.quad_stride();
         int acc = 0; uint32_t acc_phase = 0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const int ph = item % p.nphases, tile = item / p.nphases;
@@ -369,25 +406,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     float v = fmaf(__uint_as_float(r[j]), k.x, k.y);
                     v = fmaxf(v, 0.1f * v);                        // LeakyReLU(0.1)
                     v = fmaf(v, k.z, k.w);
-                    o[j] = p.round_out ? tc::round_tf32(v) : v;
+                    o[j] = (!HALF && p.round_out) ? tc::round_tf32(v) : v;        // fp16 storage rounds in the conversion
                 }
                 if (valid) {
-#pragma unroll
-                    for (int qd = 0; qd < 4; ++qd)
-                        *reinterpret_cast<float4*>(orow + (size_t)(c0 / 4 + qd) * oqs) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
+                    tc::store16(p.out, orow, c0, o);
                     // row-strip mode: our first / last row is the neighbour's bottom / top apron row - stored straight over NVLink
-                    if (oy == 0 && p.link.out_up.base) {
-                        float* d = p.link.out_up.base + ((size_t)(p.link.out_up.rows + 1) * p.out.W + ox) * 4;
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd)
-                            *reinterpret_cast<float4*>(d + (size_t)(c0 / 4 + qd) * p.link.out_up.quad_stride()) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
-                    }
-                    if (oy == p.out.rows - 1 && p.link.out_down.base) {
-                        float* d = p.link.out_down.base + (size_t)ox * 4;
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd)
-                            *reinterpret_cast<float4*>(d + (size_t)(c0 / 4 + qd) * p.link.out_down.quad_stride()) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
-                    }
+                    if (oy == 0 && p.link.out_up.base)
+                        tc::store16(p.link.out_up, p.link.out_up.base + ((size_t)(p.link.out_up.rows + 1) * p.out.W + ox) * 4, c0, o);
+                    if (oy == p.out.rows - 1 && p.link.out_down.base)
+                        tc::store16(p.link.out_down, p.link.out_down.base + (size_t)ox * 4, c0, o);
                 }
                 if (prow) {                                        // MaxPool2d(2): partners are lanes ^1 (x) and ^8 (y)
 #pragma unroll
@@ -396,21 +423,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         o[j] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
                     }
                     if (valid && !(tx & 1) && !(ty & 1)) {
-#pragma unroll
-                        for (int qd = 0; qd < 4; ++qd)
-                            *reinterpret_cast<float4*>(prow + (size_t)(c0 / 4 + qd) * pqs) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
-                        if ((y >> 1) == 0 && p.link.pool_up.base) {
-                            float* d = p.link.pool_up.base + ((size_t)(p.link.pool_up.rows + 1) * p.pool_out.W + (x >> 1)) * 4;
-#pragma unroll
-                            for (int qd = 0; qd < 4; ++qd)
-                                *reinterpret_cast<float4*>(d + (size_t)(c0 / 4 + qd) * p.link.pool_up.quad_stride()) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
-                        }
-                        if ((y >> 1) == p.pool_out.rows - 1 && p.link.pool_down.base) {
-                            float* d = p.link.pool_down.base + (size_t)(x >> 1) * 4;
-#pragma unroll
-                            for (int qd = 0; qd < 4; ++qd)
-                                *reinterpret_cast<float4*>(d + (size_t)(c0 / 4 + qd) * p.link.pool_down.quad_stride()) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
-                        }
+                        tc::store16(p.pool_out, prow, c0, o);
+                        if ((y >> 1) == 0 && p.link.pool_up.base)
+                            tc::store16(p.link.pool_up, p.link.pool_up.base + ((size_t)(p.link.pool_up.rows + 1) * p.pool_out.W + (x >> 1)) * 4, c0, o);
+                        if ((y >> 1) == p.pool_out.rows - 1 && p.link.pool_down.base)
+                            tc::store16(p.link.pool_down, p.link.pool_down.base + (size_t)(x >> 1) * 4, c0, o);
                     }
                 }
             }
@@ -469,11 +486,12 @@ static float host_round_tf32(float x) {            // round-to-nearest (ties awa
 static ptd_status tc_make_map_act(CUtensorMap* map, const DnTensor& t) {
     PFN_encodeTiled enc = tc_get_encode();
     if (!enc) PTD_FAIL(PTD_ERR_CUDA, "cuTensorMapEncodeTiled entry point not available");
-    cuuint64_t dims[3] = {(cuuint64_t)t.W * 4, (cuuint64_t)t.rows + 2, (cuuint64_t)t.cp / 4};
+    const cuuint64_t epv = 16 / t.esize;                     // elements per 16-byte channel vector
+    cuuint64_t dims[3] = {(cuuint64_t)t.W * epv, (cuuint64_t)t.rows + 2, (cuuint64_t)t.nvec()};
     cuuint64_t strides[2] = {(cuuint64_t)t.W * 16, (cuuint64_t)(t.rows + 2) * t.W * 16};
-    cuuint32_t box[3] = {TC_HALO_W * 4, TC_HALO_H, 4};
+    cuuint32_t box[3] = {(cuuint32_t)(TC_HALO_W * epv), TC_HALO_H, 4};
     cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)t.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+    CUresult r = enc(map, t.esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)t.base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                      CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) PTD_FAIL(PTD_ERR_CUDA, "cuTensorMapEncodeTiled(activation %dx%dx%d) failed: %d", t.rows, t.W, t.cp, (int)r);
     return PTD_OK;
@@ -487,9 +505,14 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     const int c0p = d.src0.cp, c1p = d.src1.base ? d.src1.cp : 0;
     if (coutp % 16 || coutp < 16 || coutp > TC_ACC_COLS || c0p % 16 || c1p % 16 || c0p + c1p != cinp)
         PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: channel padding %d/%d -> %d unsupported", c0p, c1p, coutp);
+    const bool half = d.src0.esize == 2;
+    if (d.src1.base && d.src1.esize != d.src0.esize) PTD_FAIL(PTD_ERR_ARG, "tc conv: concat sources differ in element type");
+    const int CH = half ? 32 : 16;                           // channels per chunk (4 channel vectors)
     TcParams& p = plan.p;
     memset(&p, 0, sizeof p);
-    p.n0 = c0p / 16; p.n1 = c1p / 16;
+    p.half = half ? 1 : 0;
+    p.v0 = d.src0.nvec(); p.v1 = d.src1.base ? d.src1.nvec() : 0;
+    p.n0 = (c0p + CH - 1) / CH; p.n1 = (c1p + CH - 1) / CH;
     const int nch = p.n0 + p.n1;
     const int Hs = d.src0.rows, Ws = d.src0.W;
     if (d.upsample ? (d.out.rows != 2 * Hs || d.out.W != 2 * Ws) : (d.out.rows != Hs || d.out.W != Ws))
@@ -503,8 +526,10 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     p.total_items = p.tiles_x * p.tiles_y * p.nphases;
     p.b_stage_bytes = (uint32_t)(p.ntaps * coutp * 64);
     p.w_total_bytes = (uint32_t)(p.nphases * nch) * p.b_stage_bytes;
-    // packed weights: [phase][chunk][tap][kstep j][k quad][n / 8][n % 8][4 floats]  (see make_desc_nosw)
+    // packed weights: [phase][chunk][tap][kstep j][k vector][n][16 bytes = 4 tf32 / 8 fp16]  (see make_desc_nosw); built as 16-bit
+    // or 32-bit words in one byte buffer
     std::vector<float> pack((size_t)p.w_total_bytes / 4, 0.f);
+    __half* pack_h = reinterpret_cast<__half*>(pack.data());
     for (int ph = 0; ph < p.nphases; ++ph) {
         for (int t = 0; t < p.ntaps; ++t) {
             int kys[3], kxs[3], nky = 0, nkx = 0;
@@ -525,9 +550,12 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
                     float s = 0.f;
                     for (int i = 0; i < nky; ++i)
                         for (int j = 0; j < nkx; ++j) s += w9[((size_t)(kys[i] * 3 + kxs[j]) * cinp + c) * coutp + n];
-                    const int chunk = c / 16, kstep = (c % 16) / 8, kq = (c % 8) / 4, ke = c % 4;
-                    const size_t off = ((((size_t)(ph * nch + chunk) * p.ntaps + t) * 2 + kstep) * 2 + kq) * (size_t)coutp * 4 + (size_t)n * 4 + ke;
-                    pack[off] = host_round_tf32(s);
+                    // position of padded-concat channel c: source, chunk of that source, K step, vector, element
+                    const int cl = c < c0p ? c : c - c0p, chunk = (c < c0p ? 0 : p.n0) + cl / CH, r = cl % CH;
+                    const int epv = CH / 4, kstep = r / (2 * epv), kq = (r % (2 * epv)) / epv, ke = r % epv;
+                    const size_t off = (((((size_t)(ph * nch + chunk) * p.ntaps + t) * 2 + kstep) * 2 + kq) * (size_t)coutp + (size_t)n) * epv + ke;
+                    if (half) pack_h[off] = __float2half_rn(s);
+                    else pack[off] = host_round_tf32(s);
                 }
         }
     }
@@ -559,7 +587,8 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     plan.grid = p.total_items < sms ? p.total_items : sms;
     plan.smem = (size_t)p.stages * TC_A_BYTES + ((b_bytes + 15) & ~(size_t)15) + 1024 + 256 + TC_ACC_COLS * 16;
-    if (cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess)
+    if (cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess)
         PTD_FAIL(PTD_ERR_CUDA, "tc conv: cannot reserve shared memory: %s", cudaGetErrorString(cudaGetLastError()));
     plan.valid = 1;
     return PTD_OK;
@@ -567,7 +596,8 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
 
 inline ptd_status tc_conv_launch(TcConvPlan& plan, cudaStream_t st, int* launches, bool* pooled) {
     if (!plan.valid) PTD_FAIL(PTD_ERR_STATE, "tc conv: plan not built");
-    conv_tc_kernel<<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.p);
+    if (plan.p.half) conv_tc_kernel<true><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.p);
+    else conv_tc_kernel<false><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.p);
     if (launches) ++*launches;
     if (pooled) *pooled = plan.p.pool_out.base != nullptr;
     return PTD_OK;

@@ -16,6 +16,7 @@
 //   PTD_DN_FP32  conv3x3_fp32   - implicit-GEMM on CUDA cores (FFMA), strict-parity path;
 //   PTD_DN_TF32  dn_conv_tc.cuh - TMA-staged tiles + tcgen05.mma kind::tf32 with TMEM accumulators.
 #include <cuda_runtime.h>
+#include <cuda_fp16.h>
 #include <unistd.h>
 #include <algorithm>
 #include <cstdint>
@@ -170,19 +171,13 @@ __global__ void pack_gbuffer(const float* __restrict__ g, int H, int W, int row0
                     for (int c = 0; c < 10; ++c) v[c] = tc::round_tf32(v[c]);
                 }
             }
-            float* d = out.base + ((size_t)br * Wp + x) * 4;
+            if (out.esize == 2) {
 #pragma unroll
-            for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(d + (size_t)q * out.quad_stride()) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            if (br == 1 && link.up.base) {
-                float* pd = link.up.base + ((size_t)(link.up.rows + 1) * Wp + x) * 4;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(pd + (size_t)q * link.up.quad_stride()) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int c = 0; c < 10; ++c) v[c] = fminf(fmaxf(v[c], -65504.f), 65504.f);       // fp16 range (the depth plane is unbounded)
             }
-            if (br == out.rows && link.down.base) {
-                float* pd = link.down.base + (size_t)x * 4;
-#pragma unroll
-                for (int q = 0; q < 4; ++q) *reinterpret_cast<float4*>(pd + (size_t)q * link.down.quad_stride()) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
-            }
+            tc::store16(out, out.base + ((size_t)br * Wp + x) * 4, 0, v);
+            if (br == 1 && link.up.base) tc::store16(link.up, link.up.base + ((size_t)(link.up.rows + 1) * Wp + x) * 4, 0, v);
+            if (br == out.rows && link.down.base) tc::store16(link.down, link.down.base + (size_t)x * 4, 0, v);
         }
     }
     if (link.done) {
@@ -213,7 +208,8 @@ __global__ void chw4_to_nchw(const DnTensor in, int C, float* __restrict__ out) 
     const int H = in.rows, W = in.W;
     if (i >= (size_t)C * H * W) return;
     const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)(i / ((size_t)W * H));
-    out[i] = in.base[(size_t)(c >> 2) * in.quad_stride() + ((size_t)(y + 1) * W + x) * 4 + (c & 3)];
+    if (in.esize == 4) out[i] = in.base[(size_t)(c >> 2) * in.quad_stride() + ((size_t)(y + 1) * W + x) * 4 + (c & 3)];
+    else out[i] = __half2float(reinterpret_cast<const __half*>(in.base + (size_t)(c >> 3) * in.quad_stride() + ((size_t)(y + 1) * W + x) * 4)[c & 7]);
 }
 
 // ---- weights ---------------------------------------------------------------------------------------------------------
@@ -319,11 +315,11 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     *out = nullptr;
     if (ptd_device_count() <= device || device < 0) PTD_FAIL(PTD_ERR_CUDA, "ptd_dn_create: CUDA device %d not available (no CPU fallback exists)", device);
     if (flags == PTD_DN_3XTF32) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_dn_create: PTD_DN_3XTF32 is not built yet");
-    if (flags != PTD_DN_FP32 && flags != PTD_DN_TF32) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: unknown flags %u", flags);
+    if (flags != PTD_DN_FP32 && flags != PTD_DN_TF32 && flags != PTD_DN_F16) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: unknown flags %u", flags);
     const int Hp = (H + 31) / 32 * 32, Wp = (W + 31) / 32 * 32;
     if (!strip) { row0 = 0; rows = Hp; }
     if (row0 < 0 || rows <= 0 || row0 % 32 || rows % 32 || row0 + rows > Hp) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create_strip: rows [%d, %d) must be multiples of 32 inside the padded frame of %d rows", row0, row0 + rows, Hp);
-    if (strip && flags != PTD_DN_TF32) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_dn_create_strip: row strips need the tensor-core engine (PTD_DN_TF32)");
+    if (strip && flags == PTD_DN_FP32) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_dn_create_strip: row strips need a tensor-core engine (PTD_DN_TF32 / PTD_DN_F16)");
     std::map<std::string, std::vector<float>> sd;
     ptd_status rc = read_ptdw(weights_path, sd);
     if (rc != PTD_OK) return rc;
@@ -345,9 +341,10 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
 
     // ---- activation arena: every tensor the convs read or write, one allocation (one IPC handle per strip) ----
     size_t arena_bytes = 0;
-    auto tnew = [&](int c, int lvl) -> int {
+    const int act_esize = flags == PTD_DN_F16 ? 2 : 4;       // fp16 activations everywhere but the network's output
+    auto tnew = [&](int c, int lvl, int esize = 0) -> int {
         DnTensor t;
-        t.cp = cpad(c); t.rows = rows >> lvl; t.W = Wp >> lvl;
+        t.cp = cpad(c); t.rows = rows >> lvl; t.W = Wp >> lvl; t.esize = esize ? esize : act_esize;
         h->tensors.push_back(t);
         h->tensor_off.push_back(arena_bytes);
         arena_bytes += (t.floats() * 4 + 1023) & ~(size_t)1023;
@@ -364,7 +361,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     }
     const int decC[5] = {76, 57, 43, 32, 3};          // dec5 .. dec1 outputs, at levels 4 .. 0
     int dc1[5], dc2[5];
-    for (int i = 0; i < 5; ++i) { dc1[i] = tnew(decC[i], 4 - i); dc2[i] = tnew(decC[i], 4 - i); }
+    for (int i = 0; i < 5; ++i) { dc1[i] = tnew(decC[i], 4 - i); dc2[i] = tnew(decC[i], 4 - i, i == 4 ? 4 : 0); }   // the denoised frame stays fp32
     h->t_final = dc2[4];
     if ((int)h->tensors.size() > DN_MAX_TENSORS) { ptd_set_error("ptd_dn_create: tensor table overflow"); return fail(PTD_ERR_STATE); }
     h->flags_off = arena_bytes;
@@ -428,7 +425,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
         cudaMemcpy(L.d_scale, scale.data(), coutp * 4, cudaMemcpyHostToDevice);
         cudaMemcpy(L.d_shift, shift.data(), coutp * 4, cudaMemcpyHostToDevice);
         cudaMemcpy(L.d_bias, bias.data(), coutp * 4, cudaMemcpyHostToDevice);
-        if (flags == PTD_DN_TF32) {
+        if (flags != PTD_DN_FP32) {
             float* dd = nullptr;
             DALLOC(dd, 64);
             L.d_done = (uint32_t*)dd;
@@ -543,7 +540,8 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
         cudaEventRecord(h->events[name ? nmark : 0], st);
         if (name) h->launch_names.push_back(name);
     };
-    const bool tf32 = h->flags == PTD_DN_TF32;
+    const bool tf32 = h->flags == PTD_DN_TF32;               // fp32 storage, operands rounded to tf32 at the producer
+    const bool tensor = h->flags != PTD_DN_FP32;
     if (first <= -1) {                                                  // stage -1: start of the frame
         h->epoch += 1;
         h->launches = 0;
@@ -575,7 +573,7 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
             return id;
         };
         const int s0 = res(L.src0), s1 = L.src1 == -1 ? -1 : res(L.src1), o = res(L.out);
-        if (tf32) {
+        if (tensor) {
             TcConvPlan& plan = L.tc[h->parity];
             TcStripLink& k = plan.p.link;
             memset(&k, 0, sizeof k);

@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="tf32", choices=["tf32", "fp32"])
+    ap.add_argument("--mode", default="tf32", choices=["tf32", "f16", "fp32"])
     ap.add_argument("--config", default="C3", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -206,10 +206,10 @@ def main():
     # N > 1: ONE frame sequence, every frame tiled in row strips over the N GPUs (path tracer and denoiser), halo rows and live
     # counts exchanged by the kernels themselves over NVLink peer memory (ai_path_tracer_denoiser_b200/tiling.py)
     from ai_path_tracer_denoiser_b200 import tiling
-    if world > 1 and args.mode != "tf32":
-        raise SystemExit("bench.py: row strips need --mode tf32")
+    if world > 1 and args.mode == "fp32":
+        raise SystemExit("bench.py: row strips need --mode tf32 or f16")
     pipe = tiling.StripPipeline(sc, wfile, rank, world, local, dist if world > 1 else None,
-                                capi.DN_TF32 if args.mode == "tf32" else capi.DN_FP32)
+                                {"tf32": capi.DN_TF32, "f16": capi.DN_F16, "fp32": capi.DN_FP32}[args.mode])
     pt, dn = pipe.pt, pipe.dn
     Hp, Wp = dn.padded_size()
     stream = torch.cuda.Stream()
@@ -280,7 +280,7 @@ def main():
     conv_idx = [i for i, (n, _) in enumerate(dn_named) if n in table]
     conv_ms = float(sum(dn_ms[i] for i in conv_idx))
     conv_flops = sum(table[dn_named[i][0]][0] for i in conv_idx)
-    conv_bytes = sum(table[dn_named[i][0]][1] for i in conv_idx)
+    conv_bytes = sum(table[dn_named[i][0]][1] for i in conv_idx) * (0.5 if args.mode == "f16" else 1.0)   # fp16 activations: 2 B per element
     other_dn_ms = float(sum(dn_ms)) - conv_ms
     pt_total_ms = float(sum(pt_ms))
     trace_ms, shade_ms = float(sum(pt_ms[0::2])), float(sum(pt_ms[1::2]))             # launch order: pt_trace, pt_shade per bounce
@@ -290,8 +290,9 @@ def main():
     trace_bytes = 36.0 * Pl + sum(80.0 * n for n in ll[1:]) + 16.0 * Pl
     shade_bytes = 36.0 * Pl + sum(80.0 * n for n in ll[1:]) + sum(44.0 * n for n in ll[1:]) + 12.0 * Pl + 24.0 * Pl
     pt_bytes = trace_bytes + shade_bytes
-    tf32_peak = peaks["bf16"] / 2.0                     # kind::tf32 issues at half the bf16 rate; no separate measured figure exists
-    conv_kernel = "conv_tc_kernel" if args.mode == "tf32" else "conv3x3_fp32"
+    # kind::tf32 issues at half the bf16 rate (no separate measured figure exists); kind::f16 at the bf16 rate
+    tf32_peak = peaks["bf16"] / (1.0 if args.mode == "f16" else 2.0)
+    conv_kernel = "conv_tc_kernel" if args.mode != "fp32" else "conv3x3_fp32"
     kernels = [
         dict(kernel=conv_kernel, launches=len(conv_idx), ms=conv_ms, share=conv_ms / (pt_total_ms + float(sum(dn_ms))),
              tflops=conv_flops / (conv_ms * 1e-3) / 1e12, gbs=conv_bytes / (conv_ms * 1e-3) / 1e9),
@@ -314,6 +315,9 @@ def main():
         g = trace_bytes / (trace_ms * 1e-3) / 1e9
         roof = dict(bound="hbm", kernel="pt_trace", achieved=g, peak=peaks["hbm"], unit="GB/s", frac=g / peaks["hbm"], traffic=None,
                     note="BVH traversal is latency/divergence bound, not HBM bound: see mrays_per_s in kernels[] and DESIGN.md")
+    roof["conv"] = dict(kernel=conv_kernel, ms=conv_ms, tflops=conv_flops / (conv_ms * 1e-3) / 1e12, tensor_peak_tflops=tf32_peak,
+                        tensor_frac=conv_flops / (conv_ms * 1e-3) / 1e12 / tf32_peak, gbs=conv_bytes / (conv_ms * 1e-3) / 1e9,
+                        hbm_frac=conv_bytes / (conv_ms * 1e-3) / 1e9 / peaks["hbm"])
     roof["peak_source"] = peaks["source"] + ("; tf32 peak = measured bf16 burst / 2" if roof["bound"] == "tensor" or "tensor_tflops" in roof else "")
     roof["per_layer_ms"] = {n: round(float(m), 4) for (n, _), m in zip(dn_named, dn_ms)}
     roof["per_bounce_ms"] = {"pt_trace": [round(float(m), 4) for m in pt_ms[0::2]], "pt_shade": [round(float(m), 4) for m in pt_ms[1::2]]}
@@ -356,7 +360,8 @@ def main():
 
     out = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-           "dtype": "tf32 conv operands, f32 accumulate/storage; f32 path trace" if args.mode == "tf32" else "f32",
+           "dtype": {"tf32": "tf32 conv operands, f32 accumulate/storage; f32 path trace", "f16": "f16 conv operands/activation storage, f32 accumulate, f32 frame; f32 path trace",
+                     "fp32": "f32"}[args.mode],
            "data": "synthetic",
            "config": {"workload": "%s: %s" % (args.config, desc), "frames": "camera pan phi_k = phi_0 + 0.002 k, recurrent hidden state carried",
                       "triangles": nfaces, "live_paths_per_bounce": live[:run], "denoiser_padded": [Hp, Wp], "weights": "synthetic seed 1234 (no checkpoint ships)",
