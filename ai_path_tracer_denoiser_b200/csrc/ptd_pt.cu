@@ -246,15 +246,17 @@ __global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKern
                     const float4* np = p.nodes + 8 * (size_t)node;
                     const float4 nx = __ldg(np + nearx), fx = __ldg(np + (nearx ^ 1)), ny = __ldg(np + 2 + neary), fy = __ldg(np + 2 + (neary ^ 1));
                     const float4 nz = __ldg(np + 4 + nearz), fz = __ldg(np + 4 + (nearz ^ 1)), cc = __ldg(np + 6);
-                    // slabs with the near / far plane picked per ray by the direction signs; the 1e-5 relative slack keeps the (already
-                    // padded) boxes conservative against the rounding of these products
+                    // slabs with the near / far plane picked per ray by the direction signs.  Conservative by construction: every box
+                    // is padded by 3e-5 x the scene extent (ptd_build_bvh), i.e. by >= 3e-5 * S * |1/d| in ray-parameter units, while
+                    // the rounding of fma(plane, 1/d, -o/d) is <= 1.2e-7 * |o| * |1/d| with |o| <= S inside the scene - a 250x margin.
+                    // The best-t bound comes from the (differently rounded) triangle test, hence its own 1e-5 relative slack.
                     const float tlim = t_min * 1.00001f;
                     float d0, d1, d2, d3;
 #define PT_SLAB(k, d)                                                                                                        \
                     {                                                                                                        \
                         const float tn = fmaxf(fmaxf(nx.k * idirx - oodx, ny.k * idiry - oody), fmaxf(nz.k * idirz - oodz, 0.0f)); \
                         const float tf = fminf(fminf(fx.k * idirx - oodx, fy.k * idiry - oody), fz.k * idirz - oodz);        \
-                        d = (tn * 0.99999f <= tf * 1.00001f && tn * 0.99999f <= tlim) ? tn : FLT_MAX;                        \
+                        d = (tn <= tf && tn <= tlim) ? tn : FLT_MAX;                                                         \
                     }
                     PT_SLAB(x, d0) PT_SLAB(y, d1) PT_SLAB(z, d2) PT_SLAB(w, d3)
 #undef PT_SLAB
@@ -597,6 +599,7 @@ struct ptd_pt {
     int* d_keys = nullptr; int* d_hist = nullptr; int sort_blocks = 0;
     ptd_path_segment* d_trace_paths = nullptr; ptd_intersection* d_trace_isx = nullptr;
     int final_buf = 0, cur = 0, nmark = 0;
+    cudaStream_t host_stream[2] = {nullptr, nullptr}; cudaEvent_t host_event = nullptr;   // ptd_pt_render_host
     int launches = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> events;
@@ -618,6 +621,7 @@ extern "C" void ptd_pt_destroy(ptd_pt* h) {
     cudaFree(h->d_dead); cudaFree(h->d_isx); cudaFree(h->d_image); cudaFree(h->d_gbuf_own); cudaFree(h->d_ctl); cudaFree(h->d_keys); cudaFree(h->d_hist);
     cudaFree(h->d_trace_paths); cudaFree(h->d_trace_isx); cudaFree(h->d_mail);
     for (int r = 0; r < PT_MAX_RANKS; ++r) if (h->peer_mail[r] && h->peer_ipc[r]) cudaIpcCloseMemHandle(h->peer_mail[r]);
+    if (h->host_stream[0]) { cudaStreamDestroy(h->host_stream[0]); cudaStreamDestroy(h->host_stream[1]); cudaEventDestroy(h->host_event); }
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     delete h;
 }
@@ -853,10 +857,28 @@ extern "C" ptd_status ptd_pt_strip_connect(ptd_pt* h, const void* infos, int nra
 }
 
 extern "C" ptd_status ptd_pt_render_host(ptd_pt* h, const ptd_camera* cam, int iter, float* host_tensor) {
-    if (!h || !host_tensor) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_render_host: null argument");
-    ptd_status rc = ptd_pt_render(h, cam, iter, nullptr, nullptr);
+    if (!h || !host_tensor || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_render_host: bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->host_stream[0]) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream[0], cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream[1], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->host_event, cudaEventDisableTiming));
+    }
+    // The normal / depth / albedo planes (7 of the 10) are final after the first bounce (pathtrace.cu:295-304, :379-387): their copy
+    // to the caller's host_tensor (pathtrace.cu:525) overlaps bounces 1..depth-1; only the radiance planes wait for the last bounce.
+    const size_t plane = sizeof(float) * (size_t)h->Pfull;
+    ptd_status rc = pt_run(h, cam, iter, nullptr, h->host_stream[0], 0, 1);
     if (rc != PTD_OK) return rc;
-    CUDA_TRY(cudaMemcpy(host_tensor, h->d_gbuf_own, sizeof(float) * 10 * (size_t)h->Pfull, cudaMemcpyDeviceToHost));   // pathtrace.cu:525
+    const bool early = iter == 1;                                       // later iterations do not rewrite those planes at all
+    CUDA_TRY(cudaEventRecord(h->host_event, h->host_stream[0]));
+    CUDA_TRY(cudaStreamWaitEvent(h->host_stream[1], h->host_event, 0));
+    CUDA_TRY(cudaMemcpyAsync(host_tensor + 3 * (size_t)h->Pfull, h->d_gbuf_own + 3 * (size_t)h->Pfull, 7 * plane, cudaMemcpyDeviceToHost, h->host_stream[1]));
+    (void)early;
+    rc = pt_run(h, cam, iter, nullptr, h->host_stream[0], 1, h->depth);
+    if (rc != PTD_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(host_tensor, h->d_gbuf_own, 3 * plane, cudaMemcpyDeviceToHost, h->host_stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(h->host_stream[1]));
+    CUDA_TRY(cudaStreamSynchronize(h->host_stream[0]));
     return PTD_OK;
 }
 
