@@ -100,7 +100,7 @@ class ClockSampler:
 
 def make_scene(config, W, H):
     from ai_path_tracer_denoiser_b200 import scenegen
-    d = os.path.join(tempfile.gettempdir(), "ptd_bench_scenes")
+    d = os.path.join(tempfile.gettempdir(), "ptd_bench_scenes_r%s" % os.environ.get("RANK", "0"))     # one directory per rank: no file races under torchrun
     os.makedirs(d, exist_ok=True)
     path, desc = scenegen.make_config(d, config)
     return path, desc
