@@ -315,6 +315,12 @@ def main():
         g = trace_bytes / (trace_ms * 1e-3) / 1e9
         roof = dict(bound="hbm", kernel="pt_trace", achieved=g, peak=peaks["hbm"], unit="GB/s", frac=g / peaks["hbm"], traffic=None,
                     note="BVH traversal is latency/divergence bound, not HBM bound: see mrays_per_s in kernels[] and DESIGN.md")
+    try:                                                 # DRAM traffic per launch of the dominant kernel, from the committed ncu capture
+        tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+        roof["traffic"] = tr[roof["kernel"]]["dram_bytes_per_launch"]
+        roof["traffic_note"] = "%s; %s" % (tr[roof["kernel"]]["launch"], tr["source"])
+    except Exception:
+        pass
     roof["conv"] = dict(kernel=conv_kernel, ms=conv_ms, tflops=conv_flops / (conv_ms * 1e-3) / 1e12, tensor_peak_tflops=tf32_peak,
                         tensor_frac=conv_flops / (conv_ms * 1e-3) / 1e12 / tf32_peak, gbs=conv_bytes / (conv_ms * 1e-3) / 1e9,
                         hbm_frac=conv_bytes / (conv_ms * 1e-3) / 1e9 / peaks["hbm"])
