@@ -53,6 +53,7 @@
 struct DnTensor {
     float* base = nullptr;
     int cp = 0, rows = 0, W = 0, esize = 4;
+    size_t lo_off = 0;                   // PTD_DN_3XTF32: floats from the tf32-rounded "hi" copy to the residual "lo" copy (0 = none)
     __host__ __device__ int nvec() const { return cp * esize / 16; }
     __host__ __device__ size_t quad_stride() const { return (size_t)(rows + 2) * W * 4; }      // floats (= 16-byte units * 4) between vectors
     __host__ __device__ size_t floats() const { return (size_t)nvec() * quad_stride(); }
@@ -81,7 +82,9 @@ struct TcStripLink {
 
 struct __align__(64) TcParams {
     CUtensorMap mapA0, mapA1;
-    const float* wpack;                  // packed weights, stage-major
+    CUtensorMap mapA0lo, mapA1lo;        // PTD_DN_3XTF32: the residual copies of the sources
+    int x3;                              // 3xTF32: every chunk runs three passes, (A hi, B hi), (A hi, B lo), (A lo, B hi)
+    const float* wpack;                  // packed weights, stage-major (3xTF32: per chunk the hi block then the lo block)
     int n0, n1;                          // chunks (4 channel vectors = 16 fp32 / 32 fp16 channels) of source 0 / source 1
     int v0, v1;                          // channel vectors of source 0 / source 1 (the last chunk of a source may hold only 2)
     int half;                            // fp16 storage + kind::f16 (1) or fp32 storage + kind::tf32 (0)
@@ -226,7 +229,17 @@ namespace tc {
 namespace tc {
 // 16 consecutive output channels [c0, c0 + 16) of one pixel -> the tensor's channel vectors (row: address of the pixel in vector 0)
 __device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, const float* o) {
-    if (t.esize == 4) {
+    if (t.lo_off) {                                        // 3xTF32: hi = tf32(v), lo = tf32(v - hi)
+#pragma unroll
+        for (int qd = 0; qd < 4; ++qd) {
+            float hi[4], lo[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { hi[e] = round_tf32(o[4 * qd + e]); lo[e] = round_tf32(o[4 * qd + e] - hi[e]); }   // RN, not the MMA's truncation
+            float* d = row + (size_t)(c0 / 4 + qd) * t.quad_stride();
+            *reinterpret_cast<float4*>(d) = make_float4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<float4*>(d + t.lo_off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    } else if (t.esize == 4) {
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd)
             *reinterpret_cast<float4*>(row + (size_t)(c0 / 4 + qd) * t.quad_stride()) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
@@ -253,7 +266,7 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
     const uint32_t a_lbo = (uint32_t)(TC_QUAD_PITCH >> 4) << 16;              // LBO = next channel quad
     const uint32_t b_lbo = (uint32_t)p.coutp << 16;                           // (coutp * 16 B) >> 4: next k quad of the same tap
     const uint32_t b_kstep = (uint32_t)p.coutp * 2u;                          // (coutp * 32 B) >> 4: one K = 8 step
-    const int nchunks = p.n0 + p.n1;
+    const int nchunks = p.n0 + p.n1, npass = p.x3 ? 3 : 1;
     const uint32_t sa0 = smem_u32(smem_a) >> 4, sb0 = smem_u32(smem_b) >> 4;
     const uint32_t b_stage16 = p.b_stage_bytes >> 4;
     int stage = 0; uint32_t phase = 0;
@@ -266,21 +279,24 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         fence_after_sync();
         const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)acc * TC_ACC_COLS;   // provably warp-uniform
-        for (int c = 0; c < nchunks; ++c) {
+        for (int e = 0; e < nchunks * npass; ++e) {
+            const int c = e / npass, pass = e - c * npass;
             mbar_wait(&full[stage], phase);
             fence_after_sync();
             const uint32_t a_base = (sa0 + (uint32_t)stage * (TC_A_BYTES >> 4)) | a_lbo;
-            const uint32_t b_base = (sb0 + (p.resident ? (uint32_t)(ph * nchunks + c) : (uint32_t)stage) * b_stage16) | b_lbo;
+            // resident weights: block (phase, chunk) [x3: hi block, lo block]; passes 0 and 2 use the hi block, pass 1 the lo block
+            const uint32_t b_blk = p.x3 ? (uint32_t)((ph * nchunks + c) * 2 + (pass == 1 ? 1 : 0)) : (uint32_t)(ph * nchunks + c);
+            const uint32_t b_base = (sb0 + (p.resident ? b_blk : (uint32_t)stage) * b_stage16) | b_lbo;
             // a source's last chunk may hold only two channel vectors (one K step); the other two are TMA zero fill
             const bool two = (c < p.n0 ? p.v0 - 4 * c : p.v1 - 4 * (c - p.n0)) > 2;
             if (elect_one()) {
 #pragma unroll
                 for (int t = 0; t < NTAPS; ++t) {
-                    mma_w<HALF>(d_tmem, a_base + aoff[t], a_hi, b_base + (uint32_t)(t * 2) * b_kstep, b_hi, idesc, t ? 1u : (c ? 1u : 0u));
+                    mma_w<HALF>(d_tmem, a_base + aoff[t], a_hi, b_base + (uint32_t)(t * 2) * b_kstep, b_hi, idesc, t ? 1u : (e ? 1u : 0u));
                     if (two) mma_w<HALF>(d_tmem, a_base + aoff[t] + (2u * TC_QUAD_PITCH >> 4), a_hi, b_base + (uint32_t)(t * 2 + 1) * b_kstep, b_hi, idesc, 1u);
                 }
                 mma_commit(&empty[stage]);                                    // frees the smem stage when the MMAs retire
-                if (c == nchunks - 1) mma_commit(&tmem_full[acc]);            // accumulator complete -> epilogue
+                if (e == nchunks * npass - 1) mma_commit(&tmem_full[acc]);    // accumulator complete -> epilogue
             }
             __syncwarp();
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -312,6 +328,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&p.mapA0);
         if (p.n1) tc::prefetch_tmap(&p.mapA1);
+        if (p.x3) { tc::prefetch_tmap(&p.mapA0lo); if (p.n1) tc::prefetch_tmap(&p.mapA1lo); }
     }
     if (warp == 1 && lane == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
@@ -356,16 +373,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const int ph = item % p.nphases, tile = item / p.nphases;
             const int x0 = (tile % p.tiles_x) * TC_TILE_W, y0 = (tile / p.tiles_x) * TC_TILE_H;
-            for (int c = 0; c < nchunks; ++c) {
+            const int npass = p.x3 ? 3 : 1;
+            for (int e = 0; e < nchunks * npass; ++e) {
+                const int c = e / npass, pass = e - c * npass;
                 tc::mbar_wait(&empty[stage], phase ^ 1);
                 if (tc::elect_one()) {
                     tc::mbar_expect_tx(&full[stage], stage_tx);
                     // halo tile origin: pixel (x0 - 1, y0 - 1) = buffer row y0 (apron offset +1); x < 0 / x >= W are zero filled
-                    if (c < p.n0) tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, &p.mapA0, &full[stage], (x0 - 1) * (HALF ? 8 : 4), y0, c * 4);
-                    else tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, &p.mapA1, &full[stage], (x0 - 1) * (HALF ? 8 : 4), y0, (c - p.n0) * 4);
-                    if (!p.resident)
-                        tc::bulk_load(smem_b + (size_t)stage * p.b_stage_bytes, (const uint8_t*)p.wpack + (size_t)(ph * nchunks + c) * p.b_stage_bytes,
-                                      p.b_stage_bytes, &full[stage]);
+                    const CUtensorMap* map = c < p.n0 ? (pass == 2 ? &p.mapA0lo : &p.mapA0) : (pass == 2 ? &p.mapA1lo : &p.mapA1);
+                    tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, map, &full[stage], (x0 - 1) * (HALF ? 8 : 4), y0, (c < p.n0 ? c : c - p.n0) * 4);
+                    if (!p.resident) {
+                        const size_t blk = p.x3 ? (size_t)((ph * nchunks + c) * 2 + (pass == 1 ? 1 : 0)) : (size_t)(ph * nchunks + c);
+                        tc::bulk_load(smem_b + (size_t)stage * p.b_stage_bytes, (const uint8_t*)p.wpack + blk * p.b_stage_bytes, p.b_stage_bytes, &full[stage]);
+                    }
                 }
                 __syncwarp();
                 if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -406,7 +426,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     float v = fmaf(__uint_as_float(r[j]), k.x, k.y);
                     v = fmaxf(v, 0.1f * v);                        // LeakyReLU(0.1)
                     v = fmaf(v, k.z, k.w);
-                    o[j] = (!HALF && p.round_out) ? tc::round_tf32(v) : v;        // fp16 storage rounds in the conversion
+                    o[j] = (!HALF && p.round_out && !p.x3) ? tc::round_tf32(v) : v;   // fp16 storage rounds in the conversion, 3xTF32 splits in store16
                 }
                 if (valid) {
                     tc::store16(p.out, orow, c0, o);
@@ -524,8 +544,11 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     p.out = d.out; p.pool_out = d.pool_out;
     p.tiles_x = (Ws + TC_TILE_W - 1) / TC_TILE_W; p.tiles_y = (Hs + TC_TILE_H - 1) / TC_TILE_H;
     p.total_items = p.tiles_x * p.tiles_y * p.nphases;
+    p.x3 = d.src0.lo_off ? 1 : 0;
+    if (p.x3 && (half || (d.src1.base && !d.src1.lo_off))) PTD_FAIL(PTD_ERR_ARG, "tc conv: 3xTF32 needs fp32 hi/lo sources");
+    const int nblk = p.x3 ? 2 : 1;                           // weight blocks per (phase, chunk): hi [, lo]
     p.b_stage_bytes = (uint32_t)(p.ntaps * coutp * 64);
-    p.w_total_bytes = (uint32_t)(p.nphases * nch) * p.b_stage_bytes;
+    p.w_total_bytes = (uint32_t)(p.nphases * nch * nblk) * p.b_stage_bytes;
     // packed weights: [phase][chunk][tap][kstep j][k vector][n][16 bytes = 4 tf32 / 8 fp16]  (see make_desc_nosw); built as 16-bit
     // or 32-bit words in one byte buffer
     std::vector<float> pack((size_t)p.w_total_bytes / 4, 0.f);
@@ -553,9 +576,13 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
                     // position of padded-concat channel c: source, chunk of that source, K step, vector, element
                     const int cl = c < c0p ? c : c - c0p, chunk = (c < c0p ? 0 : p.n0) + cl / CH, r = cl % CH;
                     const int epv = CH / 4, kstep = r / (2 * epv), kq = (r % (2 * epv)) / epv, ke = r % epv;
-                    const size_t off = (((((size_t)(ph * nch + chunk) * p.ntaps + t) * 2 + kstep) * 2 + kq) * (size_t)coutp + (size_t)n) * epv + ke;
+                    const size_t off = (((((size_t)((ph * nch + chunk) * nblk) * p.ntaps + t) * 2 + kstep) * 2 + kq) * (size_t)coutp + (size_t)n) * epv + ke;
                     if (half) pack_h[off] = __float2half_rn(s);
-                    else pack[off] = host_round_tf32(s);
+                    else {
+                        const float hi = host_round_tf32(s);
+                        pack[off] = hi;
+                        if (p.x3) pack[off + (size_t)p.b_stage_bytes / 4] = host_round_tf32(s - hi);   // the lo block follows the hi block
+                    }
                 }
         }
     }
@@ -571,6 +598,13 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     if (rc != PTD_OK) return rc;
     if (p.n1) { rc = tc_make_map_act(&p.mapA1, d.src1); if (rc != PTD_OK) return rc; }
     else p.mapA1 = p.mapA0;
+    p.mapA0lo = p.mapA0; p.mapA1lo = p.mapA1;
+    if (p.x3) {
+        DnTensor t = d.src0; t.base += t.lo_off;
+        rc = tc_make_map_act(&p.mapA0lo, t);
+        if (rc != PTD_OK) return rc;
+        if (p.n1) { t = d.src1; t.base += t.lo_off; rc = tc_make_map_act(&p.mapA1lo, t); if (rc != PTD_OK) return rc; }
+    }
     // shared memory plan: resident weights when they leave room for >= 4 A stages
     const size_t budget = TC_SMEM_BUDGET;
     if ((size_t)p.w_total_bytes + 4 * TC_A_BYTES <= budget) {

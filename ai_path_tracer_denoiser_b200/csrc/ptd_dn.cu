@@ -208,7 +208,10 @@ __global__ void chw4_to_nchw(const DnTensor in, int C, float* __restrict__ out) 
     const int H = in.rows, W = in.W;
     if (i >= (size_t)C * H * W) return;
     const int x = (int)(i % W), y = (int)((i / W) % H), c = (int)(i / ((size_t)W * H));
-    if (in.esize == 4) out[i] = in.base[(size_t)(c >> 2) * in.quad_stride() + ((size_t)(y + 1) * W + x) * 4 + (c & 3)];
+    if (in.esize == 4) {
+        const size_t o = (size_t)(c >> 2) * in.quad_stride() + ((size_t)(y + 1) * W + x) * 4 + (c & 3);
+        out[i] = in.lo_off ? in.base[o] + in.base[o + in.lo_off] : in.base[o];
+    }
     else out[i] = __half2float(reinterpret_cast<const __half*>(in.base + (size_t)(c >> 3) * in.quad_stride() + ((size_t)(y + 1) * W + x) * 4)[c & 7]);
 }
 
@@ -314,8 +317,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     if (!weights_path || !out || H <= 0 || W <= 0) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: bad argument");
     *out = nullptr;
     if (ptd_device_count() <= device || device < 0) PTD_FAIL(PTD_ERR_CUDA, "ptd_dn_create: CUDA device %d not available (no CPU fallback exists)", device);
-    if (flags == PTD_DN_3XTF32) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_dn_create: PTD_DN_3XTF32 is not built yet");
-    if (flags != PTD_DN_FP32 && flags != PTD_DN_TF32 && flags != PTD_DN_F16) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: unknown flags %u", flags);
+    if (flags != PTD_DN_FP32 && flags != PTD_DN_TF32 && flags != PTD_DN_F16 && flags != PTD_DN_3XTF32) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: unknown flags %u", flags);
     const int Hp = (H + 31) / 32 * 32, Wp = (W + 31) / 32 * 32;
     if (!strip) { row0 = 0; rows = Hp; }
     if (row0 < 0 || rows <= 0 || row0 % 32 || rows % 32 || row0 + rows > Hp) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create_strip: rows [%d, %d) must be multiples of 32 inside the padded frame of %d rows", row0, row0 + rows, Hp);
@@ -345,9 +347,11 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     auto tnew = [&](int c, int lvl, int esize = 0) -> int {
         DnTensor t;
         t.cp = cpad(c); t.rows = rows >> lvl; t.W = Wp >> lvl; t.esize = esize ? esize : act_esize;
+        const bool pair = flags == PTD_DN_3XTF32 && esize == 0;        // hi copy followed by the lo copy
+        if (pair) t.lo_off = (t.floats() + 255) & ~(size_t)255;
         h->tensors.push_back(t);
         h->tensor_off.push_back(arena_bytes);
-        arena_bytes += (t.floats() * 4 + 1023) & ~(size_t)1023;
+        arena_bytes += (((pair ? t.lo_off + t.floats() : t.floats())) * 4 + 1023) & ~(size_t)1023;
         return (int)h->tensors.size() - 1;
     };
     h->t_in16 = tnew(10, 0);
@@ -523,6 +527,7 @@ static DnTensor peer_tensor(const ptd_dn* h, int dir, int id) {
     DnTensor t = h->tensors[id];
     t.base = (float*)(h->peer_arena[dir] + h->peer_info[dir].tensor_off[id]);
     t.rows = h->peer_info[dir].tensor_rows[id];
+    if (t.lo_off) t.lo_off = (t.floats() + 255) & ~(size_t)255;       // the neighbour's hi -> lo distance follows ITS row count
     return t;
 }
 static uint32_t* peer_flag(const ptd_dn* h, int dir, int id, int from) {
@@ -549,7 +554,7 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
         if (reset_hidden)                                               // forward(x, j == 0): model.py:121-128
             for (int l = 0; l < 6; ++l) {
                 const DnTensor& t = h->tensors[h->t_hidden[l][h->parity]];
-                CUDA_TRY(cudaMemsetAsync(t.base, 0, t.floats() * 4, st));
+                CUDA_TRY(cudaMemsetAsync(t.base, 0, (t.lo_off ? t.lo_off + t.floats() : t.floats()) * 4, st));
             }
         const DnTensor& in = h->tensors[h->t_in16];
         const size_t n = (size_t)(in.rows + 2) * in.W;

@@ -174,7 +174,7 @@ def main():
     ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default="tf32", choices=["tf32", "f16", "fp32"])
+    ap.add_argument("--mode", default="tf32", choices=["tf32", "f16", "3xtf32", "fp32"])
     ap.add_argument("--config", default="C3", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -209,7 +209,7 @@ def main():
     if world > 1 and args.mode == "fp32":
         raise SystemExit("bench.py: row strips need --mode tf32 or f16")
     pipe = tiling.StripPipeline(sc, wfile, rank, world, local, dist if world > 1 else None,
-                                {"tf32": capi.DN_TF32, "f16": capi.DN_F16, "fp32": capi.DN_FP32}[args.mode])
+                                {"tf32": capi.DN_TF32, "f16": capi.DN_F16, "3xtf32": capi.DN_3XTF32, "fp32": capi.DN_FP32}[args.mode])
     pt, dn = pipe.pt, pipe.dn
     Hp, Wp = dn.padded_size()
     stream = torch.cuda.Stream()
@@ -367,6 +367,7 @@ def main():
     out = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": {"tf32": "tf32 conv operands, f32 accumulate/storage; f32 path trace", "f16": "f16 conv operands/activation storage, f32 accumulate, f32 frame; f32 path trace",
+                     "3xtf32": "3xtf32 (hi/lo split) conv operands, f32 accumulate/storage; f32 path trace",
                      "fp32": "f32"}[args.mode],
            "data": "synthetic",
            "config": {"workload": "%s: %s" % (args.config, desc), "frames": "camera pan phi_k = phi_0 + 0.002 k, recurrent hidden state carried",
