@@ -270,13 +270,62 @@ bool parse_triple(const char*& p, int nv, int nt, int nn, ObjIdx* out) {
     return true;
 }
 
-ptd_status load_obj(ptd_scene& sc, const std::string& path, int materialid, const M4& transform) {
+std::string dirname_of(const std::string& p) {
+    size_t k = p.find_last_of('/');
+    return k == std::string::npos ? std::string(".") : p.substr(0, k);
+}
+
+// Extension (README "experimental MTL parsing"; the reference loads the OBJ's materials and then ignores them,
+// scene.cpp:259-266,314): with `USEMTL 1` in the MESH block, `mtllib` / `usemtl` statements give every face its own material.
+struct ObjMtl { std::string name; ptd_material m; };
+bool load_mtl(const std::string& path, std::vector<ObjMtl>& out) {
+    std::ifstream f(path.c_str());
+    if (!f.is_open()) return false;
+    std::string line;
+    int illum = 2; float ke[3] = {0, 0, 0};
+    auto finish = [&]() {
+        if (out.empty()) return;
+        ptd_material& m = out.back().m;
+        // illum 3 / 5: mirror reflection; 4 / 6 / 7: glass (refraction + Fresnel reflection); Ke: emitter
+        m.hasReflective = (illum == 3 || illum == 5) ? 1.f : 0.f;
+        m.hasRefractive = (illum == 4 || illum == 6 || illum == 7) ? 1.f : 0.f;
+        const float e = std::max(ke[0], std::max(ke[1], ke[2]));
+        if (e > 0.f) { m.emittance = e; m.color = v3(ke[0] / e, ke[1] / e, ke[2] / e); }
+    };
+    while (safeGetline(f, line) && (f.good() || !line.empty())) {
+        std::vector<std::string> t = tokenize(line);
+        if (t.empty()) continue;
+        if (t[0] == "newmtl") {
+            finish();
+            ObjMtl m;
+            m.name = t.size() > 1 ? t[1] : "";
+            memset(&m.m, 0, sizeof m.m);
+            m.m.color = v3(1, 1, 1); m.m.indexOfRefraction = 1.f;
+            out.push_back(m);
+            illum = 2; ke[0] = ke[1] = ke[2] = 0.f;
+        } else if (out.empty()) {
+            continue;
+        } else if (t[0] == "Kd") out.back().m.color = tok3(t);
+        else if (t[0] == "Ks") out.back().m.specular_color = tok3(t);
+        else if (t[0] == "Ns") out.back().m.specular_exponent = tokf(t, 1);
+        else if (t[0] == "Ni") out.back().m.indexOfRefraction = tokf(t, 1);
+        else if (t[0] == "illum") illum = toki(t, 1);
+        else if (t[0] == "Ke") { ke[0] = tokf(t, 1); ke[1] = tokf(t, 2); ke[2] = tokf(t, 3); }
+    }
+    finish();
+    return true;
+}
+
+// face_mtl (optional): receives, per appended face, the index into `mtls` selected by the last `usemtl`, or -1
+ptd_status load_obj(ptd_scene& sc, const std::string& path, int materialid, const M4& transform,
+                    std::vector<ObjMtl>* mtls = nullptr, std::vector<int>* face_mtl = nullptr) {
     std::ifstream f(path.c_str());
     if (!f.is_open()) PTD_FAIL(PTD_ERR_IO, "cannot open OBJ file '%s'", path.c_str());
     std::vector<float> V, N;
     std::string line;
     std::vector<ObjIdx> poly;
     long lineno = 0;
+    int cur_mtl = -1;
     while (safeGetline(f, line) && (f.good() || !line.empty())) {
         ++lineno;
         const char* p = line.c_str();
@@ -291,6 +340,13 @@ ptd_status load_obj(ptd_scene& sc, const std::string& path, int materialid, cons
             float x = 0, y = 0, z = 0;
             parse_real(p, &x); parse_real(p, &y); parse_real(p, &z);
             N.push_back(x); N.push_back(y); N.push_back(z);
+        } else if (mtls && strncmp(p, "mtllib", 6) == 0 && (p[6] == ' ' || p[6] == '\t')) {
+            std::vector<std::string> t = tokenize(line);
+            if (t.size() > 1) load_mtl(dirname_of(path) + "/" + t[1], *mtls);
+        } else if (mtls && strncmp(p, "usemtl", 6) == 0 && (p[6] == ' ' || p[6] == '\t')) {
+            std::vector<std::string> t = tokenize(line);
+            cur_mtl = -1;
+            for (size_t k = 0; t.size() > 1 && k < mtls->size(); ++k) if ((*mtls)[k].name == t[1]) cur_mtl = (int)k;
         } else if (p[0] == 'f' && (p[1] == ' ' || p[1] == '\t')) {
             p += 2;
             poly.clear();
@@ -327,16 +383,13 @@ ptd_status load_obj(ptd_scene& sc, const std::string& path, int materialid, cons
                 }
                 face.materialid = materialid;
                 sc.faces.push_back(face);
+                if (face_mtl) face_mtl->push_back(cur_mtl);
             }
         }
     }
     return PTD_OK;
 }
 
-std::string dirname_of(const std::string& p) {
-    size_t k = p.find_last_of('/');
-    return k == std::string::npos ? std::string(".") : p.substr(0, k);
-}
 }  // namespace
 
 // scene.cpp:142-152: derived camera fields (fov uses tan of the FULL fovy, sic)
@@ -359,6 +412,7 @@ extern "C" ptd_status ptd_scene_load(const char* path, ptd_scene** out) {
     memset(&sc->mesh_box, 0, sizeof sc->mesh_box);
     memset(&sc->camera, 0, sizeof sc->camera);
     bool have_camera = false;
+    std::vector<ObjMtl> mesh_mtls; std::vector<int> mesh_face_mtl;      // USEMTL extension, resolved after the whole file is read
     std::string line;
     ptd_status rc = PTD_OK;
     while (in.good() && rc == PTD_OK) {
@@ -450,6 +504,7 @@ extern "C" ptd_status ptd_scene_load(const char* path, ptd_scene** out) {
             safeGetline(in, line);
             if (!line.empty() && in.good()) materialid = toki(tokenize(line), 1);
             ptd_vec3 tr = v3(0, 0, 0), ro = v3(0, 0, 0), sca = v3(0, 0, 0);
+            bool use_mtl = false;
             safeGetline(in, line);
             while (!line.empty() && in.good()) {
                 std::vector<std::string> t = tokenize(line);
@@ -457,6 +512,7 @@ extern "C" ptd_status ptd_scene_load(const char* path, ptd_scene** out) {
                     if (t[0] == "TRANS") tr = tok3(t);
                     else if (t[0] == "ROTAT") ro = tok3(t);
                     else if (t[0] == "SCALE") sca = tok3(t);
+                    else if (t[0] == "USEMTL") use_mtl = toki(t, 1) != 0;     // extension; the reference ignores unknown keywords here
                 }
                 safeGetline(in, line);
             }
@@ -464,8 +520,15 @@ extern "C" ptd_status ptd_scene_load(const char* path, ptd_scene** out) {
             // the reference resolves PATH against the process cwd; we also try the scene file's directory
             std::string p1 = obj, p2 = dirname_of(path) + "/" + obj;
             std::ifstream probe(p1.c_str());
-            rc = load_obj(*sc, probe.is_open() ? p1 : p2, materialid, T);
+            rc = load_obj(*sc, probe.is_open() ? p1 : p2, materialid, T, use_mtl ? &mesh_mtls : nullptr, use_mtl ? &mesh_face_mtl : nullptr);
         }
+    }
+    if (rc == PTD_OK && !mesh_mtls.empty()) {
+        // MTL materials go behind every MATERIAL block of the scene file (their ids are positions in the file, wherever MESH stands)
+        const int base = (int)sc->materials.size();
+        for (const ObjMtl& m : mesh_mtls) sc->materials.push_back(m.m);
+        for (size_t i = 0; i < mesh_face_mtl.size() && i < sc->faces.size(); ++i)
+            if (mesh_face_mtl[i] >= 0) sc->faces[i].materialid = base + mesh_face_mtl[i];
     }
     if (rc == PTD_OK && !have_camera) { ptd_set_error("%s: no CAMERA block", path); rc = PTD_ERR_PARSE; }
     if (rc != PTD_OK) { delete sc; return rc; }

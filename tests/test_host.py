@@ -123,3 +123,29 @@ def test_compute_entry_points_fail_loudly_without_a_device(tmp_path):
         capi.Denoiser(w, 48, 64)
     with pytest.raises(capi.PtdError, match="no CPU fallback"):
         capi.Denoiser(w, 64, 64, strip=(0, 32))
+
+
+def test_usemtl_extension_assigns_per_face_materials(tmp_path):
+    """`USEMTL 1` in the MESH block (ignored by the reference's parser): mtllib / usemtl give every face its own material, appended
+    behind the scene file's MATERIAL blocks; without the keyword the mesh keeps the single `material k` of the reference."""
+    (tmp_path / "m.mtl").write_text("newmtl red\nKd 0.8 0.1 0.1\nKs 0.5 0.5 0.5\nNs 32\nillum 2\n\nnewmtl mirror\nKd 0.9 0.9 0.9\nKs 1 1 1\nillum 3\n\n"
+                                    "newmtl glass\nKd 1 1 1\nKs 1 1 1\nNi 1.5\nillum 7\n\nnewmtl lamp\nKd 1 1 1\nKe 4 4 2\n")
+    (tmp_path / "m.obj").write_text("mtllib m.mtl\nv 0 0 0\nv 1 0 0\nv 0 1 0\nv 1 1 0\nvn 0 0 1\nf 1//1 2//1 3//1\nusemtl red\nf 2//1 4//1 3//1\n"
+                                    "usemtl mirror\nf 1//1 2//1 4//1\nusemtl glass\nf 1//1 4//1 3//1\nusemtl lamp\nf 2//1 3//1 4//1\nusemtl nosuch\nf 1//1 3//1 2//1\n")
+    head = "MATERIAL 0\nRGB 1 1 1\nSPECEX 0\nSPECRGB 0 0 0\nREFL 0\nREFR 0\nREFRIOR 0\nEMITTANCE 5\n\n"
+    tail = ("MATERIAL 1\nRGB .5 .5 .5\nSPECEX 0\nSPECRGB 0 0 0\nREFL 0\nREFR 0\nREFRIOR 0\nEMITTANCE 0\n\n"
+            "CAMERA\nRES 32 32\nFOVY 45\nITERATIONS 1\nDEPTH 4\nFILE x\nEYE 0 0 5\nLOOKAT 0 0 0\nUP 0 1 0\n\n")
+    mesh = "MESH 0\nPATH %s\nmaterial 1\nTRANS 0 0 0\nROTAT 0 0 0\nSCALE 1 1 1\n%s\n"
+    (tmp_path / "plain.txt").write_text(head + mesh % (tmp_path / "m.obj", "") + tail)
+    (tmp_path / "mtl.txt").write_text(head + mesh % (tmp_path / "m.obj", "USEMTL 1\n") + tail)     # MESH stands BEFORE material 1
+    plain = capi.Scene(path=str(tmp_path / "plain.txt")).arrays()
+    assert len(plain["materials"]) == 2 and list(plain["faces"]["mat"]) == [1] * 6
+    a = capi.Scene(path=str(tmp_path / "mtl.txt")).arrays()
+    assert len(a["materials"]) == 6                                   # 2 from the scene file + 4 from the MTL, in that order
+    assert list(a["faces"]["mat"]) == [1, 2, 3, 4, 5, 1]              # before any usemtl / unknown name: the block's `material 1`
+    assert a["faces"]["v"].tobytes() == plain["faces"]["v"].tobytes() and a["materials"][:2].tobytes() == plain["materials"].tobytes()
+    red, mirror, glass, lamp = a["materials"][2:]
+    assert np.allclose(red["color"], [0.8, 0.1, 0.1]) and red["specex"] == 32 and red["refl"] == 0 and red["refr"] == 0 and red["emit"] == 0
+    assert mirror["refl"] == 1 and mirror["refr"] == 0 and np.allclose(mirror["speccolor"], 1)
+    assert glass["refr"] == 1 and glass["ior"] == np.float32(1.5)
+    assert lamp["emit"] == 4 and np.allclose(lamp["color"], [1, 1, 0.5])
