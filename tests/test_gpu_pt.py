@@ -257,7 +257,7 @@ def test_per_face_mtl_materials(tmp_path):
     txt = open(os.path.join(SCENES, "hall_64x48.txt")).read()
     import re
     txt = re.sub(r"PATH \S+", "PATH %s" % (tmp_path / "hall.obj"), txt)
-    txt = txt.replace("SCALE       1 1 1\n", "SCALE       1 1 1\nUSEMTL 1\n") if "SCALE       1 1 1\n" in txt else re.sub(r"(SCALE[^\n]*\n)(\s*\n|$)", r"\1USEMTL 1\n\2", txt, count=0)
+    txt = txt.rstrip() + "\nUSEMTL 1\n"                      # the MESH block is the file's last block
     (tmp_path / "hall_mtl.txt").write_text(txt)
     sc = capi.Scene(path=str(tmp_path / "hall_mtl.txt"))
     A = sc.arrays()
