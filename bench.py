@@ -150,7 +150,7 @@ def run_reference(args, W, H, config):
     # measured 6.6 P for the enclosed hall) - the reference arm must not touch our kernels, so it uses the conservative P * depth bound / 2
     P = W * H
     live = [P] + [int(P * 0.8)] * 7 if nfaces else [P, int(.46 * P), int(.32 * P), int(.25 * P), int(.2 * P), int(.17 * P), int(.14 * P), int(.11 * P)]
-    row_stride = max(1, H // 8) if nfaces else max(1, H // 64)
+    row_stride = max(1, H // 64) if nfaces else max(1, H // 256)
     times = []
     for k in range(args.warmup + args.steps):
         cam = capi.frame_camera(sc.camera[0], k)
@@ -171,8 +171,8 @@ def run_reference(args, W, H, config):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=30)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--mode", default="tf32", choices=["tf32", "f16", "3xtf32", "fp32"])
     ap.add_argument("--config", default="C3", choices=["C2", "C3", "C4", "C5"])
@@ -381,7 +381,7 @@ def main():
            "roofline": roof, "clocks": clocks}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        row_stride = max(1, H // 8) if nfaces else max(1, H // 64)
+        row_stride = max(1, H // 64) if nfaces else max(1, H // 256)
         pt_s, dn_s, rays = cpu_reference_frame(scene_path, cams[args.warmup], live[:run], H, W, threads, row_stride)
         out["cpu_baseline"] = {"value": 1.0 / (pt_s + dn_s), "unit": "frames/s", "cores": threads, "kind": "reference(path trace: oracle/_ref)+port(denoiser: oracle/dn_oracle.py)",
                                "sample": "brute-force first-bounce intersect of every %d-th row (%d rays x %d faces) scaled to this frame's %d live path-bounces -> %.1f s; one %dx%d torch-CPU forward -> %.2f s" % (
