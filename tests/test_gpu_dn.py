@@ -147,3 +147,37 @@ def test_multi_process_strips_bit_exact_when_two_gpus():
                         "--master-port", "29533", os.path.join(root, "tools", "check_strips_multi.py")], capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert r.stdout.count("BIT-EXACT") == 2
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("H,W", [(1, 1), (33, 31), (40, 200)])
+def test_edge_sizes(H, W, mode, wfile):
+    """Degenerate and ragged frame sizes: 1 x 1 (one 32 x 32 padded tile), one pixel past a 32-multiple, wide and flat."""
+    capi = _capi()
+    from ai_path_tracer_denoiser_b200 import weights
+    from oracle.dn_oracle import DenoiserOracle, synthetic_gbuffer
+    O = DenoiserOracle(weights.synthetic_state_dict(1234))
+    dn = capi.Denoiser(wfile, H, W, flags=_mode(capi, mode))
+    for j in range(2):
+        x = synthetic_gbuffer(H, W, seed=4, frame=j)
+        ma, rl = _err(dn.forward_host(x, reset=(j == 0)), O.forward(x, reset=(j == 0)))
+        assert ma <= TOL[mode][0] and rl <= TOL[mode][1], (j, ma, rl)
+
+
+def test_errors_are_reported_not_thrown(tmp_path, wfile):
+    """Bad weight files / arguments come back as status codes with a message (the reference would throw or exit)."""
+    capi = _capi()
+    bad = tmp_path / "bad.ptdw"
+    bad.write_bytes(b"NOPE" + b"\0" * 64)
+    with pytest.raises(capi.PtdError, match="bad magic"):
+        capi.Denoiser(str(bad), 32, 32)
+    with pytest.raises(capi.PtdError, match="cannot open"):
+        capi.Denoiser(str(tmp_path / "missing.ptdw"), 32, 32)
+    trunc = tmp_path / "trunc.ptdw"
+    trunc.write_bytes(open(wfile, "rb").read()[:4096])
+    with pytest.raises(capi.PtdError, match="truncated|missing"):
+        capi.Denoiser(str(trunc), 32, 32)
+    with pytest.raises(capi.PtdError):
+        capi.Denoiser(wfile, 64, 64, strip=(0, 48))          # strips must be multiples of 32 rows
+    with pytest.raises(capi.PtdError, match="tensor-core"):
+        capi.Denoiser(wfile, 64, 64, flags=capi.DN_FP32, strip=(0, 32))

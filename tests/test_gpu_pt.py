@@ -272,3 +272,74 @@ def test_per_face_mtl_materials(tmp_path):
     for n_o, n_g in zip(a["counts"], ora["counts"]):
         assert abs(n_o - n_g) <= max(2, 0.005 * n_g)
     assert np.isclose(a["tensor"][3:], ora["tensor"][3:], rtol=0, atol=1e-4).mean() >= 0.999
+
+
+def _ref_and_ours(capi, scene_name, cam_edit=None, depth=None, iter=1, res=None):
+    """Render the same scene / camera with oracle A (reference kernels) and with libptd.so; returns (ref, ours, pt)."""
+    from oracle import reflib
+    if not reflib.available(""):
+        pytest.fail("oracle/_ref/libref_pt.so missing on the GPU box")
+    R = reflib.RefLib("")
+    path = os.path.join(SCENES, scene_name)
+    s = R.load_scene(path)
+    sc = capi.Scene(path=path)
+    cam = capi.frame_camera(sc.camera[0], 3)
+    if res is not None:                                   # smaller than the file's 64x48, so the reference's buffers still fit
+        sc.set_resolution(*res)
+        cam = capi.frame_camera(sc.camera[0], 3)
+    if cam_edit is not None:
+        cam = cam_edit(cam)
+    if depth is not None:
+        R.set_depth(s, depth)
+        sc.set_depth(depth)
+    R.set_camera(s, cam)
+    ref = R.gpu_render(s, iter=iter, trace=True)
+    sc.set_camera(cam)
+    pt = capi.PathTracer(sc, flags=capi.PT_TRACE | capi.PT_KEEP_TERMINATED)
+    tensor = pt.render_host(iter=iter)
+    counts, run = pt.live_counts()
+    return ref, dict(tensor=tensor, counts=counts[:run], image=pt.dump_image(), final=pt.dump_final_paths(), pt=pt), pt
+
+
+@pytest.mark.parametrize("scene", ["cornell_specular_64x48.txt", "hall_64x48.txt"])
+def test_edge_odd_resolution_bit_exact(scene):
+    """37 x 23: not a multiple of any tile size (ragged last tile in every kernel)."""
+    capi = _capi()
+    ref, ours, pt = _ref_and_ours(capi, scene, res=(37, 23))
+    assert [b["n"] for b in ref["trace"]] == ours["counts"]
+    for b in range(len(ours["counts"])):
+        _same(pt.dump_paths(b), ref["trace"][b]["paths"], "bounce %d paths" % b)
+    assert ours["tensor"].tobytes() == ref["tensor"].tobytes() and ours["image"].tobytes() == ref["image"].tobytes()
+    _same(ours["final"], ref["final_paths"], "final paths")
+
+
+def test_edge_depth_one_and_all_rays_miss():
+    capi = _capi()
+    ref, ours, pt = _ref_and_ours(capi, "cornell_64x48.txt", depth=1)
+    assert ours["counts"] == [64 * 48] and ours["tensor"].tobytes() == ref["tensor"].tobytes()
+
+    def look_away(cam):                                   # turn the camera around: nothing but the void in view
+        cam = cam.copy()
+        cam["view"] = -cam["view"]
+        cam["right"] = -cam["right"]
+        return cam
+    ref, ours, pt = _ref_and_ours(capi, "cornell_64x48.txt", cam_edit=look_away)
+    assert [b["n"] for b in ref["trace"]] == ours["counts"] == [64 * 48]      # every path dies at bounce 0: the next bounce sees n == 0
+    assert ours["tensor"].tobytes() == ref["tensor"].tobytes() and not ours["tensor"].any()
+    _same(ours["final"], ref["final_paths"], "final paths")
+
+
+def test_edge_second_iteration_and_accumulation():
+    """iter == 2: another RNG stream, no first-hit planes (pathtrace.cu:295,379 guards), radiance = image / 2; and iter 1 followed
+    by iter 2 on one handle accumulates like the reference's dev_image."""
+    capi = _capi()
+    ref2, ours2, _ = _ref_and_ours(capi, "cornell_specular_64x48.txt", iter=2)
+    assert ours2["tensor"].tobytes() == ref2["tensor"].tobytes() and ours2["image"].tobytes() == ref2["image"].tobytes()
+    assert not ours2["tensor"][3:].any()
+    ref1, ours1, pt = _ref_and_ours(capi, "cornell_specular_64x48.txt", iter=1)
+    t12 = pt.render_host(iter=2)                          # same handle: accumulates onto iteration 1's image
+    acc = (ref1["image"] + ref2["image"]).astype(np.float32)
+    assert pt.dump_image().tobytes() == acc.tobytes()
+    expect = (acc / np.float32(2)).astype(np.float32).reshape(48, 64, 3)[:, ::-1].transpose(2, 0, 1)     # x-mirrored planes 0-2
+    assert t12[:3].tobytes() == np.ascontiguousarray(expect).tobytes()
+    assert t12[3:].tobytes() == ours1["tensor"][3:].tobytes()       # first-hit planes keep iteration 1's values

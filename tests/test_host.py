@@ -149,3 +149,33 @@ def test_usemtl_extension_assigns_per_face_materials(tmp_path):
     assert mirror["refl"] == 1 and mirror["refr"] == 0 and np.allclose(mirror["speccolor"], 1)
     assert glass["refr"] == 1 and glass["ior"] == np.float32(1.5)
     assert lamp["emit"] == 4 and np.allclose(lamp["color"], [1, 1, 0.5])
+
+
+def test_header_is_plain_c_and_links(tmp_path):
+    """include/ptd.h must be usable from C (the boundary is a C ABI): compile a C99 translation unit against it and link libptd.so."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text('#include "ptd.h"\n#include <stdio.h>\n'
+                   'int main(void) { ptd_scene* s = 0; ptd_status rc = ptd_scene_load("/nonexistent/scene.txt", &s);\n'
+                   '  printf("%d %d %d %s\\n", ptd_version(), ptd_sizeof(0), rc, ptd_last_error()); return rc == PTD_ERR_IO ? 0 : 1; }\n')
+    exe = tmp_path / "abi"
+    gcc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    libdir = os.path.join(ROOT, "ai_path_tracer_denoiser_b200")
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                           "-L", libdir, "-lptd", "-Wl,-rpath," + libdir])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout + out.stderr
+    assert out.stdout.split()[:3] == ["100", "44", "-2"] and "cannot open scene file" in out.stdout
+
+
+def test_cli_usage_and_no_device_message():
+    """`ptd_cli` keeps the reference's command line (main.cpp:50-56): usage text without arguments; without a GPU it fails loudly."""
+    import subprocess
+    exe = os.path.join(ROOT, "ai_path_tracer_denoiser_b200", "ptd_cli")
+    r = subprocess.run([exe], capture_output=True, text=True)
+    assert r.returncode == 1 and "SCENEFILE.txt" in r.stdout
+    r = subprocess.run([exe, "/nonexistent.txt"], capture_output=True, text=True)
+    assert r.returncode == 2 and "cannot open scene file" in r.stderr
+    if capi.device_count() == 0:
+        r = subprocess.run([exe, os.path.join(SCENES, "cornell_64x48.txt")], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stderr
