@@ -25,7 +25,9 @@
 #include "ptd_internal.h"
 #include "pt_math.cuh"
 
-#define PT_BLOCK 128
+#ifndef PT_BLOCK
+#define PT_BLOCK 512
+#endif
 #define PT_WORDS 11                 // sizeof(PathSegment) / 4
 #define PT_STACK 96
 #define PT_MAX_RANKS 8

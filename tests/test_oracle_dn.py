@@ -45,3 +45,24 @@ def test_pad_crop_and_reset():
     assert y0.shape == (3, 40, 50)
     assert np.array_equal(y0, y2) and not np.array_equal(y0, y1)                   # hidden state matters
     assert O.hidden[0].shape == (1, 32, 64, 64) and O.hidden[5].shape == (1, 101, 2, 2)
+
+
+def test_checkpoint_export_round_trip(tmp_path):
+    """tools/export_weights.py: a `{'net': state_dict}` checkpoint as train.py writes it (train.py:108-112) -> PTDW -> same tensors."""
+    import subprocess
+    import sys
+    import torch
+    from ai_path_tracer_denoiser_b200 import weights
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sd = {k: torch.as_tensor(np.asarray(v)) for k, v in weights.synthetic_state_dict(7).items()}
+    torch.save({"net": sd}, str(tmp_path / "model_3.pt"))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "export_weights.py"), str(tmp_path / "model_3.pt"), str(tmp_path / "w.ptdw")],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    back = weights.load_weights(str(tmp_path / "w.ptdw"))
+    assert len(back) >= 28 * 6 and set(back) <= set(sd)               # integer bookkeeping tensors (num_batches_tracked) may be dropped
+    assert all(np.array_equal(np.asarray(back[k]), sd[k].numpy()) for k in back)
+    torch.save({"net": {"foo": torch.zeros(1)}}, str(tmp_path / "bad.pt"))
+    r = subprocess.run([sys.executable, os.path.join(root, "tools", "export_weights.py"), str(tmp_path / "bad.pt"), str(tmp_path / "x.ptdw")],
+                       capture_output=True, text=True)
+    assert r.returncode == 2 and "lacks" in r.stdout
