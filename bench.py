@@ -196,6 +196,8 @@ def main():
         raise SystemExit("bench.py: no CUDA device - the product has no CPU fallback")
     torch.cuda.set_device(local)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"            # NCCL prints its version banner to STDOUT; the contract is ONE JSON line there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     P = W * H
     scene_path, desc = make_scene(args.config, W, H)
@@ -364,6 +366,28 @@ def main():
         e2e_s = float(t.item())
     e2e_fps = args.steps / e2e_s
 
+    # ---- context for N > 1: the same GPUs as N independent frame sequences (no tiling, no coupling), aggregate frames/s ----
+    replicas = None
+    if world > 1:
+        rpt = capi.PathTracer(sc, device=local)
+        rdn = capi.Denoiser(wfile, H, W, device=local, flags={"tf32": capi.DN_TF32, "f16": capi.DN_F16, "3xtf32": capi.DN_3XTF32}[args.mode])
+        def rstep(k, reset):
+            capi.check(L.ptd_pt_render(rpt.h, cams[k].ctypes.data, 1, C.c_void_p(gbuf.data_ptr()), sptr), "ptd_pt_render")
+            capi.check(L.ptd_dn_forward(rdn.h, C.c_void_p(gbuf.data_ptr()), C.c_void_p(rgb.data_ptr()), 1 if reset else 0, sptr), "ptd_dn_forward")
+        for k in range(3):
+            rstep(k, k == 0)
+        sync_all()
+        r0e, r1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        r0e.record(stream)
+        nrep = min(args.steps, 50)
+        for k in range(nrep):
+            rstep(3 + k, False)
+        r1e.record(stream)
+        sync_all()
+        t = torch.tensor([r0e.elapsed_time(r1e)], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        replicas = {"value": world * nrep / (float(t.item()) * 1e-3), "unit": "frames/s (aggregate of %d independent untiled frame sequences, one per GPU)" % world}
+
     out = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": {"tf32": "tf32 conv operands, f32 accumulate/storage; f32 path trace", "f16": "f16 conv operands/activation storage, f32 accumulate, f32 frame; f32 path trace",
@@ -379,6 +403,8 @@ def main():
            "gpu_launches": launches_per_step * args.steps,
            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
            "roofline": roof, "clocks": clocks}
+    if replicas:
+        out["replicas"] = replicas
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         row_stride = max(1, H // 64) if nfaces else max(1, H // 256)

@@ -181,3 +181,24 @@ def test_errors_are_reported_not_thrown(tmp_path, wfile):
         capi.Denoiser(wfile, 64, 64, strip=(0, 48))          # strips must be multiples of 32 rows
     with pytest.raises(capi.PtdError, match="tensor-core"):
         capi.Denoiser(wfile, 64, 64, flags=capi.DN_FP32, strip=(0, 32))
+
+
+def test_long_sequence_300_frames_is_stable(wfile):
+    """BASELINE config 3: a 300-frame sequence with the recurrent state carried and never reset.  Output stays finite and bounded,
+    and tracks the fp32 CPU oracle (checked every 60 frames) with no error growth."""
+    capi = _capi()
+    from ai_path_tracer_denoiser_b200 import weights
+    from oracle.dn_oracle import DenoiserOracle, synthetic_gbuffer
+    H, W = 64, 96
+    O = DenoiserOracle(weights.synthetic_state_dict(1234))
+    dn = capi.Denoiser(wfile, H, W, flags=capi.DN_TF32)
+    errs = []
+    for j in range(300):
+        x = synthetic_gbuffer(H, W, seed=9, frame=j % 17)           # a short loop of inputs, a long recurrence
+        ref = O.forward(x, reset=(j == 0))
+        y = dn.forward_host(x, reset=(j == 0))
+        if j % 60 == 59 or j == 0:
+            assert np.isfinite(y).all() and np.abs(y).max() < 50
+            errs.append(_err(y, ref))
+    assert all(ma <= TOL["tf32"][0] and rl <= TOL["tf32"][1] for ma, rl in errs), errs
+    assert errs[-1][1] <= 3 * errs[0][1] + 1e-4, errs                # no growth through the recurrence
