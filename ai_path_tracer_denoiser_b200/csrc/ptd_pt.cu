@@ -70,12 +70,9 @@ __device__ __forceinline__ void consider_face(float t, int face, float bx, float
     }
 }
 
-// conservative slab test against a geom's padded world box: false only when the ray certainly misses the geom
-__device__ __forceinline__ bool ray_may_hit_box(const Ray& ray, const ptd_aabb& b) {
-    const float ooeps = 1e-30f;
-    const float idx = 1.0f / (fabsf(ray.d.x) > ooeps ? ray.d.x : copysignf(ooeps, ray.d.x));
-    const float idy = 1.0f / (fabsf(ray.d.y) > ooeps ? ray.d.y : copysignf(ooeps, ray.d.y));
-    const float idz = 1.0f / (fabsf(ray.d.z) > ooeps ? ray.d.z : copysignf(ooeps, ray.d.z));
+// conservative slab test against a geom's padded world box: false only when the ray certainly misses the geom.
+// (idx, idy, idz) = the ray's clamped inverse direction, computed once per ray.
+__device__ __forceinline__ bool ray_may_hit_box(const Ray& ray, float idx, float idy, float idz, const ptd_aabb& b) {
     const float x0 = (b.lb.x - ray.o.x) * idx, x1 = (b.ub.x - ray.o.x) * idx;
     const float y0 = (b.lb.y - ray.o.y) * idy, y1 = (b.ub.y - ray.o.y) * idy;
     const float z0 = (b.lb.z - ray.o.z) * idz, z1 = (b.ub.z - ray.o.z) * idz;
@@ -198,9 +195,13 @@ __global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKern
                     t_min = FLT_MAX; best_face = -1; hit_face = false; outside = true; bbx = bby = 0.f;
                     v3 ip = V(0, 0, 0), normal = V(0, 0, 0), tip = V(0, 0, 0), tn = V(0, 0, 0);
                     int materialid = -1;
+                    const float ooeps = 1e-30f;                                           // clamped inverse direction, shared with the BVH slabs
+                    const float rix = 1.0f / (fabsf(ray.d.x) > ooeps ? ray.d.x : copysignf(ooeps, ray.d.x));
+                    const float riy = 1.0f / (fabsf(ray.d.y) > ooeps ? ray.d.y : copysignf(ooeps, ray.d.y));
+                    const float riz = 1.0f / (fabsf(ray.d.z) > ooeps ? ray.d.z : copysignf(ooeps, ray.d.z));
                     for (int g = 0; g < p.ngeoms; ++g) {
                         const ptd_geom* ge = &geoms[g];
-                        if (!ray_may_hit_box(ray, gbounds[g])) continue;              // a certain miss leaves t, outside untouched in the reference too
+                        if (!ray_may_hit_box(ray, rix, riy, riz, gbounds[g])) continue;   // a certain miss leaves t, outside untouched in the reference too
                         float t = 0.f;
                         if (ge->type == PTD_CUBE) t = boxIntersectionTest(ge, ray, tip, tn, outside);
                         else if (ge->type == PTD_SPHERE) t = sphereIntersectionTest(ge, ray, tip, tn, outside);
@@ -212,10 +213,7 @@ __global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKern
                     node = PT_SENTINEL; leaf = 0;
                     if (p.nfaces && RayAABBintersect(ray, p.mesh_box)) {               // RAY_CULLING true, :258
                         if (p.use_bvh) {
-                            const float ooeps = 1e-30f;
-                            idirx = 1.0f / (fabsf(ray.d.x) > ooeps ? ray.d.x : copysignf(ooeps, ray.d.x));
-                            idiry = 1.0f / (fabsf(ray.d.y) > ooeps ? ray.d.y : copysignf(ooeps, ray.d.y));
-                            idirz = 1.0f / (fabsf(ray.d.z) > ooeps ? ray.d.z : copysignf(ooeps, ray.d.z));
+                            idirx = rix; idiry = riy; idirz = riz;
                             oodx = ray.o.x * idirx; oody = ray.o.y * idiry; oodz = ray.o.z * idirz;
                             nearx = idirx < 0.0f; neary = idiry < 0.0f; nearz = idirz < 0.0f;     // 0: the lo plane is entered first, 1: the hi plane
                             stack[0] = PT_SENTINEL; sp = 0; node = 0;
