@@ -63,3 +63,52 @@ class StripPipeline:
         """One frame of the render loop for this strip (asynchronous on `stream`)."""
         self.pt.render(gbuf_ptr, cam=np.ascontiguousarray(cam), iter=1, stream=stream)
         self.dn.forward(gbuf_ptr, rgb_ptr, reset, stream=stream)
+
+
+class FrameLoop:
+    """The render loop (the reference's runCuda(), main.cpp:120-168) on top of a StripPipeline: frame k = path trace with camera k,
+    then the denoiser with the hidden state of frame k - 1.
+
+    pipelined=True runs the two hot paths on two CUDA streams with a double-buffered G-buffer: the path trace of frame k + 1 (which
+    depends on nothing but its camera) overlaps the denoiser of frame k.  Per-frame latency is unchanged, throughput rises wherever
+    one of the two leaves the GPU idle - above all in the multi-GPU strip mode, where both are chains of short, latency-bound
+    kernels.  Frames are still produced in order and the recurrent state is carried exactly as in the serial loop (the denoiser
+    stream is sequential), so the output is bit-identical to the serial loop's."""
+
+    def __init__(self, pipe, pipelined=True):
+        import ctypes
+        import torch
+        self._C, self._torch = ctypes, torch
+        self.pipe, self.pipelined = pipe, pipelined
+        P = pipe.W * pipe.H
+        self.s_pt = torch.cuda.Stream()
+        self.s_dn = torch.cuda.Stream() if pipelined else self.s_pt
+        n = 2 if pipelined else 1
+        self.gbuf = [torch.zeros(10 * P, dtype=torch.float32, device="cuda") for _ in range(n)]
+        self.rgb = torch.zeros(3 * P, dtype=torch.float32, device="cuda")
+        self.ev_pt = [torch.cuda.Event() for _ in range(n)]
+        self.ev_dn = [None] * n
+        self.k = 0
+
+    def frame(self, cam, reset):
+        """Enqueue one frame (asynchronous).  Returns the index of the G-buffer it uses."""
+        C, torch = self._C, self._torch
+        i = self.k % len(self.gbuf)
+        g = C.c_void_p(self.gbuf[i].data_ptr())
+        if self.pipelined and self.ev_dn[i] is not None:
+            self.s_pt.wait_event(self.ev_dn[i])                 # the denoiser of frame k - 2 has consumed this G-buffer
+        self.pipe.pt.render(g, cam=np.ascontiguousarray(cam), iter=1, stream=C.c_void_p(self.s_pt.cuda_stream))
+        if self.pipelined:
+            self.ev_pt[i].record(self.s_pt)
+            self.s_dn.wait_event(self.ev_pt[i])
+        self.pipe.dn.forward(g, C.c_void_p(self.rgb.data_ptr()), reset, stream=C.c_void_p(self.s_dn.cuda_stream))
+        if self.pipelined:
+            if self.ev_dn[i] is None:
+                self.ev_dn[i] = torch.cuda.Event()
+            self.ev_dn[i].record(self.s_dn)
+        self.k += 1
+        return i
+
+    def synchronize(self):
+        self.s_pt.synchronize()
+        self.s_dn.synchronize()
