@@ -20,6 +20,7 @@
 #include <cuda_runtime.h>
 #include <unistd.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 #include "ptd_internal.h"
@@ -709,6 +710,7 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
         int sms = 148, per_sm = 8;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pt_trace<false>, TR_BLOCK, (sizeof(ptd_geom) + sizeof(ptd_aabb)) * std::min(h->ngeoms, 64));
+        if (const char* e = getenv("PTD_TRACE_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // tuning knob: leave room for a concurrent kernel
         h->trace_blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (h->P + TR_BLOCK - 1) / TR_BLOCK));   // persistent: every resident warp pulls rays
     }
     CUDA_TRY(cudaDeviceSynchronize());
