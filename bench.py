@@ -359,13 +359,21 @@ def main():
         h2d, d2h = 40 * P, 52 * P
     else:
         r0, nr = pipe.pt_rows
-        host_rgb = torch.empty(3, nr * W, dtype=torch.float32).pin_memory()
+        host_rgb = [torch.empty(3, nr * W, dtype=torch.float32).pin_memory() for _ in range(2)]
         rgb3 = rgb.view(3, P)
+        copied = [torch.cuda.Event(), torch.cuda.Event()]
+        e2e_k = [0]
         def e2e_step(k, reset):
+            # frame k is enqueued and its rows are read back behind it on the denoiser stream; the host then waits for frame k - 1's
+            # rows, so every frame reaches pinned host memory and the device never idles while the host waits
+            i = e2e_k[0] & 1
             loop.frame(cams[k], reset)
             with torch.cuda.stream(loop.s_dn):
-                host_rgb.copy_(rgb3[:, r0 * W:(r0 + nr) * W], non_blocking=True)
-            loop.s_dn.synchronize()                       # the frame is on the host; the next frame's path trace may already be running
+                host_rgb[i].copy_(rgb3[:, r0 * W:(r0 + nr) * W], non_blocking=True)
+                copied[i].record(loop.s_dn)
+            if e2e_k[0] > 0:
+                copied[i ^ 1].synchronize()
+            e2e_k[0] += 1
         h2d, d2h = 84, 12 * P
     for k in range(3):
         e2e_step(k, k == 0)
