@@ -1,7 +1,7 @@
 // ptd_cli - headless drop-in for the reference executable's frame loop (Inference/src/main.cpp:47-87, :120-168).
 //
 //   ptd_cli SCENEFILE.txt [--weights model.ptdw] [--frames N] [--dphi RAD] [--mode tf32|f16|fp32|3xtf32] [--sort-material]
-//           [--res W H] [--depth D] [--out PREFIX] [--device K] [--host-roundtrip] [--reset-every N] [--quiet]
+//           [--res W H] [--depth D] [--out PREFIX] [--device K] [--host-roundtrip] [--serial] [--reset-every N] [--quiet]
 //
 // `ptd_cli SCENEFILE.txt` is the reference's command line (main.cpp:50-56).  Every frame repeats runCuda(): the orbit camera is
 // rebuilt from (zoom, phi, theta) (main.cpp:122-140), a fresh 1-spp iteration is traced (iteration == 1 every frame because
@@ -9,6 +9,9 @@
 // main.cpp:40-42), the G-buffer goes through the recurrent denoiser with the hidden state carried frame to frame.  There is
 // no window: the mouse drag of main.cpp:193-223 is replaced by a constant phi step per frame (--dphi) and
 // cv::imshow (main.cpp:89-100) by optional PNG / PFM dumps (--out).  Host C++ only; all GPU work goes through include/ptd.h.
+// Default data flow: everything stays on the device and the path trace of frame k + 1 runs on its own stream, overlapping the
+// denoiser of frame k (two G-buffers, two events per frame; --serial puts both on one stream, --host-roundtrip reproduces the
+// reference's PCIe round trip through host_tensor).
 #include <cuda_runtime.h>
 #include <chrono>
 #include <cstdint>
@@ -109,14 +112,14 @@ static bool write_pfm(const std::string& path, const float* rgb, int W, int H) {
 int main(int argc, char** argv) {
     if (argc < 2) {
         printf("Usage: %s SCENEFILE.txt [--weights model.ptdw] [--frames N] [--dphi RAD] [--mode tf32|f16|fp32|3xtf32] [--sort-material]\n"
-               "       [--res W H] [--depth D] [--out PREFIX] [--device K] [--host-roundtrip] [--reset-every N] [--quiet]\n", argv[0]);   // main.cpp:50-53
+               "       [--res W H] [--depth D] [--out PREFIX] [--device K] [--host-roundtrip] [--serial] [--reset-every N] [--quiet]\n", argv[0]);   // main.cpp:50-53
         return 1;
     }
     const char* scene_file = argv[1];
     std::string weights, out_prefix, mode = "tf32";
     int frames = 1, device = 0, res_w = 0, res_h = 0, depth = 0, reset_every = 0;
     float dphi = 0.002f;
-    bool sort_material = false, host_roundtrip = false, quiet = false;
+    bool sort_material = false, host_roundtrip = false, quiet = false, serial = false;
     for (int i = 2; i < argc; ++i) {
         std::string a = argv[i];
         auto need = [&](int n) { if (i + n >= argc) { fprintf(stderr, "ptd_cli: %s needs %d value(s)\n", a.c_str(), n); exit(1); } };
@@ -130,6 +133,7 @@ int main(int argc, char** argv) {
         else if (a == "--out") { need(1); out_prefix = argv[++i]; }
         else if (a == "--device") { need(1); device = atoi(argv[++i]); }
         else if (a == "--host-roundtrip") host_roundtrip = true;
+        else if (a == "--serial") serial = true;
         else if (a == "--reset-every") { need(1); reset_every = atoi(argv[++i]); }
         else if (a == "--quiet") quiet = true;
         else { fprintf(stderr, "ptd_cli: unknown option %s\n", a.c_str()); return 1; }
@@ -162,30 +166,44 @@ int main(int argc, char** argv) {
     if (!dn && !quiet) printf("no --weights: path trace only (the reference's DENOISE_RENDER false, main.cpp:42)\n");
 
     cudaSetDevice(device);
-    float *d_gbuf = nullptr, *d_rgb = nullptr;
-    cudaStream_t stream;
-    if (cudaStreamCreate(&stream) != cudaSuccess || cudaMalloc((void**)&d_gbuf, 40 * P) != cudaSuccess || cudaMalloc((void**)&d_rgb, 12 * P) != cudaSuccess) {
+    const bool pipelined = !serial && !host_roundtrip && dn != nullptr;
+    float *d_gbuf[2] = {nullptr, nullptr}, *d_rgb = nullptr;
+    cudaStream_t stream, s_pt;                         // `stream`: denoiser (and everything, when serial); s_pt: path trace when pipelined
+    cudaEvent_t ev_pt[2], ev_dn[2];
+    bool dn_recorded[2] = {false, false};
+    if (cudaStreamCreate(&stream) != cudaSuccess || cudaStreamCreate(&s_pt) != cudaSuccess || cudaMalloc((void**)&d_gbuf[0], 40 * P) != cudaSuccess ||
+        cudaMalloc((void**)&d_gbuf[1], 40 * P) != cudaSuccess || cudaMalloc((void**)&d_rgb, 12 * P) != cudaSuccess) {
         fprintf(stderr, "ptd_cli: device allocation failed\n");
         return 2;
     }
+    for (int i = 0; i < 2; ++i) { cudaEventCreateWithFlags(&ev_pt[i], cudaEventDisableTiming); cudaEventCreateWithFlags(&ev_dn[i], cudaEventDisableTiming); }
     std::vector<float> h_gbuf(host_roundtrip || !out_prefix.empty() ? 10 * P : 0), h_rgb(3 * P);
     const auto t0 = std::chrono::steady_clock::now();
     for (int frame = 0; frame < frames; ++frame) {
         ptd_camera c = *cam;
         ptd_camera_orbit(&c, zoom, phi + dphi * (float)frame, theta);                          // runCuda(): main.cpp:122-140
         const int reset = frame == 0 || (reset_every > 0 && frame % reset_every == 0);        // forward(x, j == 0)
+        const int gi = pipelined ? (frame & 1) : 0;
         if (host_roundtrip) {
             // the reference's exact data flow: G-buffer D2H (pathtrace.cu:525), H2D again + output D2H (main.cpp:104-105,91)
             if (ptd_pt_render_host(pt, &c, 1, h_gbuf.data()) != PTD_OK) return fail("ptd_pt_render_host");
             if (dn && ptd_dn_forward_host(dn, h_gbuf.data(), h_rgb.data(), reset) != PTD_OK) return fail("ptd_dn_forward_host");
+        } else if (pipelined) {
+            if (dn_recorded[gi]) cudaStreamWaitEvent(s_pt, ev_dn[gi], 0);                      // frame - 2's denoiser is done with this G-buffer
+            if (ptd_pt_render(pt, &c, 1, d_gbuf[gi], s_pt) != PTD_OK) return fail("ptd_pt_render");
+            cudaEventRecord(ev_pt[gi], s_pt);
+            cudaStreamWaitEvent(stream, ev_pt[gi], 0);
+            if (ptd_dn_forward(dn, d_gbuf[gi], d_rgb, reset, stream) != PTD_OK) return fail("ptd_dn_forward");
+            cudaEventRecord(ev_dn[gi], stream);
+            dn_recorded[gi] = true;
         } else {
-            if (ptd_pt_render(pt, &c, 1, d_gbuf, stream) != PTD_OK) return fail("ptd_pt_render");
-            if (dn && ptd_dn_forward(dn, d_gbuf, d_rgb, reset, stream) != PTD_OK) return fail("ptd_dn_forward");
+            if (ptd_pt_render(pt, &c, 1, d_gbuf[0], stream) != PTD_OK) return fail("ptd_pt_render");
+            if (dn && ptd_dn_forward(dn, d_gbuf[0], d_rgb, reset, stream) != PTD_OK) return fail("ptd_dn_forward");
         }
         if (!out_prefix.empty()) {
             if (!host_roundtrip) {
                 cudaStreamSynchronize(stream);
-                cudaMemcpy(h_gbuf.data(), d_gbuf, 40 * P, cudaMemcpyDeviceToHost);
+                cudaMemcpy(h_gbuf.data(), d_gbuf[gi], 40 * P, cudaMemcpyDeviceToHost);
                 if (dn) cudaMemcpy(h_rgb.data(), d_rgb, 12 * P, cudaMemcpyDeviceToHost);
             }
             char name[64];
@@ -194,6 +212,7 @@ int main(int argc, char** argv) {
             if (dn) { write_png(out_prefix + name + "_denoised.png", h_rgb.data(), W, H); write_pfm(out_prefix + name + "_denoised.pfm", h_rgb.data(), W, H); }
         }
     }
+    cudaStreamSynchronize(s_pt);
     if (cudaStreamSynchronize(stream) != cudaSuccess) { fprintf(stderr, "ptd_cli: CUDA error: %s\n", cudaGetErrorString(cudaGetLastError())); return 2; }
     const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     if (!quiet) {
@@ -204,7 +223,8 @@ int main(int argc, char** argv) {
         for (int b = 0; b < run; ++b) printf(" %d", live[b]);
         printf("\n");
     }
-    cudaFree(d_gbuf); cudaFree(d_rgb); cudaStreamDestroy(stream);
+    cudaFree(d_gbuf[0]); cudaFree(d_gbuf[1]); cudaFree(d_rgb); cudaStreamDestroy(stream); cudaStreamDestroy(s_pt);
+    for (int i = 0; i < 2; ++i) { cudaEventDestroy(ev_pt[i]); cudaEventDestroy(ev_dn[i]); }
     ptd_dn_destroy(dn);
     ptd_pt_destroy(pt);
     ptd_scene_free(scene);

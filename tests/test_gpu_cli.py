@@ -27,7 +27,7 @@ def _png_size(path):
     return struct.unpack(">II", b[16:24])
 
 
-@pytest.mark.parametrize("roundtrip", [False, True])
+@pytest.mark.parametrize("roundtrip", [[], ["--host-roundtrip"], ["--serial"]], ids=["pipelined", "host-roundtrip", "serial"])
 def test_cli_frame_loop_matches_the_c_abi(tmp_path, roundtrip):
     from ai_path_tracer_denoiser_b200 import capi, weights
     if capi.device_count() < 1:
@@ -35,7 +35,7 @@ def test_cli_frame_loop_matches_the_c_abi(tmp_path, roundtrip):
     wfile = weights.save_weights(weights.synthetic_state_dict(1234), str(tmp_path / "w.ptdw"))
     scene = os.path.join(SCENES, "cornell_specular_64x48.txt")
     exe = os.path.join(ROOT, "ai_path_tracer_denoiser_b200", "ptd_cli")
-    cmd = [exe, scene, "--weights", wfile, "--frames", "3", "--mode", "tf32", "--out", str(tmp_path / "f")] + (["--host-roundtrip"] if roundtrip else [])
+    cmd = [exe, scene, "--weights", wfile, "--frames", "3", "--mode", "tf32", "--out", str(tmp_path / "f")] + roundtrip
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "3 frame(s)" in r.stdout
