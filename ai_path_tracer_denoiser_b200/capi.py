@@ -101,7 +101,7 @@ def lib():
         L.ptd_dn_create_strip.argtypes = [C.c_char_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint, C.POINTER(C.c_void_p)]
         L.ptd_dn_strip_partition.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]
         L.ptd_dn_strip_export.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
-        L.ptd_dn_strip_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ptd_dn_strip_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         L.ptd_dn_forward_group.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib = L
     return _lib
@@ -336,8 +336,9 @@ class Denoiser:
         check(lib().ptd_dn_strip_export(self.h, buf, n), "ptd_dn_strip_export")
         return buf.raw
 
-    def connect(self, up=None, down=None):
-        check(lib().ptd_dn_strip_connect(self.h, up, down), "ptd_dn_strip_connect")
+    def connect(self, infos, my_rank):
+        """infos: the exported blobs of ALL strips in strip order (top first)."""
+        check(lib().ptd_dn_strip_connect(self.h, b"".join(infos), len(infos), my_rank), "ptd_dn_strip_connect")
 
     def __del__(self):
         try:

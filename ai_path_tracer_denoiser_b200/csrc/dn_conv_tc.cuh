@@ -67,6 +67,7 @@ struct TcConvDesc {
     const float* scale; const float* shift; const float* bias;
     bool round_out = true;               // round stored activations to tf32 (all layers but the last)
     const float* shared_wpack = nullptr; // reuse another plan's packed weights (same layer, other hidden-state parity)
+    int src_yoff = 0;                    // row-strip mode: first source row of this strip's tile domain inside the (replicated, full-height) sources
 };
 
 // Row-strip (multi-GPU) coupling of one conv launch, see ptd_dn.cu "row strips".  All pointers may be null (single GPU).
@@ -78,6 +79,12 @@ struct TcStripLink {
     uint32_t wait_epoch[4];
     uint32_t* done;                      // local CTA-completion counter of this layer (monotonic)
     uint32_t epoch;                      // frame sequence number written to the flags
+    // gather (the level where tiling ends, ptd_dn.cu "replicated levels"): the pooled output is a full-height tensor that EVERY strip
+    // holds; this strip's pooled rows (from row pool_yoff on) are stored into all of them
+    float* gather_base[8];               // the other strips' copies of pool_out (peer memory); null = none / self
+    uint32_t* gather_sig[8];             // their "rows of strip r have arrived" flags
+    const uint32_t* gather_wait[8];      // local flags a CONSUMER of a gathered source waits for (all other strips)
+    int pool_yoff;
 };
 
 struct __align__(64) TcParams {
@@ -91,7 +98,8 @@ struct __align__(64) TcParams {
     int ntaps, nphases;
     int dy[4][9], dx[4][9];
     int tiles_x, tiles_y, total_items;
-    int Hs, Ws;                          // tile domain (= source resolution)
+    int Hs, Ws;                          // tile domain (= this strip's rows at source resolution)
+    int src_yoff;                        // tile row y reads source image row y + src_yoff (replicated full-height sources)
     int out_mul;                         // 1, or 2 for the upsampling layers
     int coutp;
     int stages, resident;                // smem pipeline depth; weights resident in smem (1) or streamed per stage (0)
@@ -359,6 +367,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         bool waited = false;
         for (int i = 0; i < 4; ++i)
             if (p.link.wait[i]) { while ((int)(tc::ld_acquire_sys(p.link.wait[i]) - p.link.wait_epoch[i]) < 0) { } waited = true; }
+        for (int i = 0; i < 8; ++i)
+            if (p.link.gather_wait[i]) { while ((int)(tc::ld_acquire_sys(p.link.gather_wait[i]) - p.link.epoch) < 0) { } waited = true; }
         if (waited) asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (TMA) reads
         if (p.resident && tc::elect_one()) {                         // the layer's whole weight set, once per CTA
             tc::mbar_expect_tx(wfull, p.w_total_bytes);
@@ -372,7 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const uint32_t stage_tx = TC_A_BYTES + (p.resident ? 0u : p.b_stage_bytes);
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
             const int ph = item % p.nphases, tile = item / p.nphases;
-            const int x0 = (tile % p.tiles_x) * TC_TILE_W, y0 = (tile / p.tiles_x) * TC_TILE_H;
+            const int x0 = (tile % p.tiles_x) * TC_TILE_W, y0 = (tile / p.tiles_x) * TC_TILE_H + p.src_yoff;
             const int npass = p.x3 ? 3 : 1;
             for (int e = 0; e < nchunks * npass; ++e) {
                 const int c = e / npass, pass = e - c * npass;
@@ -411,7 +421,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             const bool valid = x < p.Ws && y < p.Hs;
             const int oy = p.out_mul * y + (p.nphases > 1 ? (ph >> 1) : 0), ox = p.out_mul * x + (p.nphases > 1 ? (ph & 1) : 0);
             float* orow = p.out.base + ((size_t)(oy + 1) * p.out.W + ox) * 4;
-            float* prow = p.pool_out.base ? p.pool_out.base + ((size_t)((y >> 1) + 1) * p.pool_out.W + (x >> 1)) * 4 : nullptr;
+            const size_t poff = ((size_t)((y >> 1) + p.link.pool_yoff + 1) * p.pool_out.W + (x >> 1)) * 4;
+            float* prow = p.pool_out.base ? p.pool_out.base + poff : nullptr;
             tc::mbar_wait(&tmem_full[acc], acc_phase);
             tc::fence_after_sync();
             const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_ACC_COLS;
@@ -444,6 +455,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     }
                     if (valid && !(tx & 1) && !(ty & 1)) {
                         tc::store16(p.pool_out, prow, c0, o);
+#pragma unroll 1
+                        for (int r = 0; r < 8; ++r)
+                            if (p.link.gather_base[r]) { DnTensor t = p.pool_out; t.base = p.link.gather_base[r]; tc::store16(t, t.base + poff, c0, o); }
                         if ((y >> 1) == 0 && p.link.pool_up.base)
                             tc::store16(p.link.pool_up, p.link.pool_up.base + ((size_t)(p.link.pool_up.rows + 1) * p.pool_out.W + (x >> 1)) * 4, c0, o);
                         if ((y >> 1) == p.pool_out.rows - 1 && p.link.pool_down.base)
@@ -468,6 +482,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             __threadfence_system();
             for (int i = 0; i < 4; ++i)
                 if (p.link.sig[i]) tc::st_release_sys(p.link.sig[i], p.link.epoch);
+            for (int i = 0; i < 8; ++i)
+                if (p.link.gather_sig[i]) tc::st_release_sys(p.link.gather_sig[i], p.link.epoch);
         }
     }
     if (warp == 2) {
@@ -534,11 +550,12 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     p.v0 = d.src0.nvec(); p.v1 = d.src1.base ? d.src1.nvec() : 0;
     p.n0 = (c0p + CH - 1) / CH; p.n1 = (c1p + CH - 1) / CH;
     const int nch = p.n0 + p.n1;
-    const int Hs = d.src0.rows, Ws = d.src0.W;
-    if (d.upsample ? (d.out.rows != 2 * Hs || d.out.W != 2 * Ws) : (d.out.rows != Hs || d.out.W != Ws))
-        PTD_FAIL(PTD_ERR_ARG, "tc conv: source %dx%d does not match output %dx%d", Hs, Ws, d.out.rows, d.out.W);
-    if (d.src1.base && (d.src1.rows != Hs || d.src1.W != Ws)) PTD_FAIL(PTD_ERR_ARG, "tc conv: concat sources differ in size");
-    p.Hs = Hs; p.Ws = Ws; p.out_mul = d.upsample ? 2 : 1;
+    // tile domain = the output's rows at source resolution; the sources hold at least rows [src_yoff, src_yoff + Hs)
+    const int Hs = d.upsample ? d.out.rows / 2 : d.out.rows, Ws = d.src0.W;
+    if ((d.upsample ? d.out.W != 2 * Ws : d.out.W != Ws) || d.src_yoff < 0 || d.src0.rows < Hs + d.src_yoff)
+        PTD_FAIL(PTD_ERR_ARG, "tc conv: source %dx%d (+%d) does not cover output %dx%d", d.src0.rows, Ws, d.src_yoff, d.out.rows, d.out.W);
+    if (d.src1.base && (d.src1.rows != d.src0.rows || d.src1.W != Ws)) PTD_FAIL(PTD_ERR_ARG, "tc conv: concat sources differ in size");
+    p.Hs = Hs; p.Ws = Ws; p.out_mul = d.upsample ? 2 : 1; p.src_yoff = d.src_yoff;
     p.nphases = d.upsample ? 4 : 1; p.ntaps = d.upsample ? 4 : 9;
     p.coutp = coutp; p.scale = d.scale; p.shift = d.shift; p.bias = d.bias; p.lrelu_first = d.lrelu_first; p.round_out = d.round_out;
     p.out = d.out; p.pool_out = d.pool_out;

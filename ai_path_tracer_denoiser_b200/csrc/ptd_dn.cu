@@ -248,7 +248,14 @@ static ptd_status read_ptdw(const char* path, std::map<std::string, std::vector<
 // the first load.  Flags carry the frame sequence number, so nothing is ever reset.  The six hidden states are double
 // buffered (frame k reads parity k & 1, writes the other): a neighbour that runs ahead can then never overwrite an apron
 // row that is still being read.  One strip covering the whole frame is the single-GPU case: aprons stay zero.
+// Replicated levels: tiling stops at level DN_REPL_LEVEL (1/8 resolution).  Below it a strip would be a handful of rows and every
+// layer would pay a cross-GPU wait for almost no work, so levels >= DN_REPL_LEVEL (encoder 4-5, bottleneck, decoder 5-4: 13 of the
+// 28 convs, 3 % of the FLOPs) are computed IN FULL by every strip: encoder 3's fused max-pool stores its rows of the level-3 input
+// into every strip's full-height tensor ("gather": peer stores to all strips + one flag per source strip), the 13 convs then run
+// without any exchange, and decoder 3 reads its rows of the replicated level-3 tensors back into the strip (src_yoff).
 #define DN_MAX_TENSORS 48
+#define DN_MAX_RANKS 8
+#define DN_REPL_LEVEL 3
 struct ptd_strip_info {                      // POD, exchanged between the ranks as bytes (ptd_dn_strip_export / _connect)
     unsigned char ipc[64];                   // cudaIpcMemHandle_t of the activation arena
     unsigned long long arena;                // the arena's address in the owner's process (same-process connections)
@@ -256,6 +263,7 @@ struct ptd_strip_info {                      // POD, exchanged between the ranks
     unsigned long long tensor_off[DN_MAX_TENSORS];   // byte offset of tensor i in the arena
     int tensor_rows[DN_MAX_TENSORS];
     unsigned long long flags_off;            // uint32 flags[ntensors][2] (from up, from down), 32-byte stride
+    unsigned long long gflags_off;           // uint32 gather flags[DN_MAX_RANKS] (rows of strip r have arrived), 32-byte stride
 };
 
 struct DnLayer {
@@ -284,11 +292,15 @@ struct ptd_dn {
     float* d_gbuf = nullptr; float* d_rgb = nullptr;   // staging for the host-pointer entry point
     struct Pool { int in[2], out; };
     std::vector<Pool> pools;        // pools[k] follows layer 3k+2 (CUDA-core engine only; the TC engine pools in its epilogue)
-    // neighbours
-    unsigned char* peer_arena[2] = {nullptr, nullptr};     // up, down
-    bool peer_ipc[2] = {false, false};
-    ptd_strip_info peer_info[2];
-    bool has_peer[2] = {false, false};
+    // the other strips of the frame, by rank (top strip = 0); up = rank - 1, down = rank + 1
+    int rank = 0, nranks = 1;
+    unsigned char* peer_arena[DN_MAX_RANKS] = {nullptr};
+    bool peer_ipc[DN_MAX_RANKS] = {false};
+    ptd_strip_info peer_info[DN_MAX_RANKS];
+    bool has_peer[2] = {false, false};                     // a strip above / below exists
+    size_t gflags_off = 0;
+    int t_gather = -1;                                     // the gathered tensor (pooled output of encoder DN_REPL_LEVEL, full height)
+    std::vector<int> tensor_level; std::vector<char> tensor_full;
     uint32_t epoch = 0;
     uint32_t* d_pack_done = nullptr;
     int parity = 0;
@@ -303,7 +315,7 @@ struct ptd_dn {
 extern "C" void ptd_dn_destroy(ptd_dn* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    for (int d = 0; d < 2; ++d) if (h->peer_arena[d] && h->peer_ipc[d]) cudaIpcCloseMemHandle(h->peer_arena[d]);
+    for (int d = 0; d < DN_MAX_RANKS; ++d) if (h->peer_arena[d] && h->peer_ipc[d]) cudaIpcCloseMemHandle(h->peer_arena[d]);
     for (auto& L : h->layers) { tc_plan_destroy(L.tc[0]); tc_plan_destroy(L.tc[1]); }
     for (void* p : h->allocs) cudaFree(p);
     cudaFree(h->arena);
@@ -346,7 +358,9 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     const int act_esize = flags == PTD_DN_F16 ? 2 : 4;       // fp16 activations everywhere but the network's output
     auto tnew = [&](int c, int lvl, int esize = 0) -> int {
         DnTensor t;
-        t.cp = cpad(c); t.rows = rows >> lvl; t.W = Wp >> lvl; t.esize = esize ? esize : act_esize;
+        const bool full = strip && lvl >= DN_REPL_LEVEL;               // replicated level: every strip holds the whole tensor
+        t.cp = cpad(c); t.rows = (full ? Hp : rows) >> lvl; t.W = Wp >> lvl; t.esize = esize ? esize : act_esize;
+        h->tensor_level.push_back(lvl); h->tensor_full.push_back(full ? 1 : 0);
         const bool pair = flags == PTD_DN_3XTF32 && esize == 0;        // hi copy followed by the lo copy
         if (pair) t.lo_off = (t.floats() + 255) & ~(size_t)255;
         h->tensors.push_back(t);
@@ -370,6 +384,9 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     if ((int)h->tensors.size() > DN_MAX_TENSORS) { ptd_set_error("ptd_dn_create: tensor table overflow"); return fail(PTD_ERR_STATE); }
     h->flags_off = arena_bytes;
     arena_bytes += h->tensors.size() * 2 * 32 + 1024;
+    h->gflags_off = arena_bytes;
+    arena_bytes += DN_MAX_RANKS * 32 + 1024;
+    h->t_gather = strip ? pooled[DN_REPL_LEVEL - 1] : -1;
     if (cudaMalloc((void**)&h->arena, arena_bytes) != cudaSuccess) { ptd_set_error("ptd_dn_create: cudaMalloc(%zu B activation arena) failed: %s", arena_bytes, cudaGetErrorString(cudaGetLastError())); return fail(PTD_ERR_CUDA); }
     h->arena_bytes = arena_bytes;
     cudaMemset(h->arena, 0, arena_bytes);
@@ -390,7 +407,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
         L.spec = specs[li];
         const DnLayerSpec& s = specs[li];
         const int lvl = s.level;
-        L.H = rows >> lvl; L.W = Wp >> lvl;
+        L.H = ((strip && lvl >= DN_REPL_LEVEL) ? Hp : rows) >> lvl; L.W = Wp >> lvl;
         L.src1 = -1; L.pool = -1;
         if (s.kind == DN_L1) { L.src0 = lvl == 0 ? h->t_in16 : pooled[lvl - 1]; L.out = out1[lvl]; }
         else if (s.kind == DN_L2A) { L.src0 = out1[lvl]; L.src1 = HR(lvl); L.out = mid[lvl]; }
@@ -444,6 +461,9 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
                 d.scale = L.d_scale; d.shift = L.d_shift; d.bias = L.d_bias;
                 d.round_out = li + 1 < specs.size();
                 d.shared_wpack = parity ? L.tc[0].d_wpack : nullptr;
+                // a strip-resident output computed from replicated (full-height) sources: decoder DN_REPL_LEVEL reads rows from row0 >> level on
+                const int s0id = resolve(L.src0, parity);
+                if (h->tensor_full[s0id] && !h->tensor_full[resolve(L.out, parity)]) d.src_yoff = row0 >> h->tensor_level[s0id];
                 rc = tc_plan_create(d, w9, cinp, L.tc[parity], h->allocs);
                 if (rc != PTD_OK) return fail(rc);
             }
@@ -487,51 +507,68 @@ extern "C" ptd_status ptd_dn_strip_export(ptd_dn* h, void* info_out, int capacit
     info.ntensors = (int)h->tensors.size();
     for (size_t i = 0; i < h->tensors.size(); ++i) { info.tensor_off[i] = h->tensor_off[i]; info.tensor_rows[i] = h->tensors[i].rows; }
     info.flags_off = h->flags_off;
+    info.gflags_off = h->gflags_off;
     memcpy(info_out, &info, sizeof info);
     return PTD_OK;
 }
-// up / down: ptd_strip_info of the strips above / below (null = frame border).  Same process: the pointer is used directly
-// (peer access is enabled when the devices differ); other process: the arena is opened through CUDA IPC.
-extern "C" ptd_status ptd_dn_strip_connect(ptd_dn* h, const void* up, const void* down) {
-    if (!h) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: null handle");
+// infos: the exported blobs of ALL strips of the frame in strip order (top strip first), back to back; my_rank: this handle's
+// position.  Same process: the pointers are used directly (peer access is enabled when the devices differ); other process: the
+// arenas are opened through CUDA IPC.  The strips above / below receive halo rows, every strip receives the gathered level.
+extern "C" ptd_status ptd_dn_strip_connect(ptd_dn* h, const void* infos, int nranks, int my_rank) {
+    if (!h || !infos || nranks < 1 || nranks > DN_MAX_RANKS || my_rank < 0 || my_rank >= nranks) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: bad argument (at most %d strips)", DN_MAX_RANKS);
     CUDA_TRY(cudaSetDevice(h->device));
-    const void* src[2] = {up, down};
-    for (int d = 0; d < 2; ++d) {
-        if (h->peer_arena[d] && h->peer_ipc[d]) cudaIpcCloseMemHandle(h->peer_arena[d]);
-        h->peer_arena[d] = nullptr; h->has_peer[d] = false; h->peer_ipc[d] = false;
-        if (!src[d]) continue;
+    const ptd_strip_info* in = (const ptd_strip_info*)infos;
+    int row = 0;
+    for (int r = 0; r < nranks; ++r) {
         ptd_strip_info info;
-        memcpy(&info, src[d], sizeof info);
-        if (info.ntensors != (int)h->tensors.size() || info.Hp != h->Hp || info.Wp != h->Wp) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: neighbour was built for another frame size");
-        if ((d == 0 && info.row0 + info.rows != h->row0) || (d == 1 && h->row0 + h->rows != info.row0)) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: neighbour rows [%d, %d) are not adjacent to [%d, %d)", info.row0, info.row0 + info.rows, h->row0, h->row0 + h->rows);
+        memcpy(&info, &in[r], sizeof info);
+        if (info.ntensors != (int)h->tensors.size() || info.Hp != h->Hp || info.Wp != h->Wp) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: strip %d was built for another frame size", r);
+        if (info.row0 != row) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: strip %d starts at row %d, expected %d", r, info.row0, row);
+        row += info.rows;
+        if (r == my_rank && (info.row0 != h->row0 || info.rows != h->rows)) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: blob %d is not this handle's", r);
+    }
+    if (row != h->Hp) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: the strips cover %d of %d padded rows", row, h->Hp);
+    for (int r = 0; r < DN_MAX_RANKS; ++r) {
+        if (h->peer_arena[r] && h->peer_ipc[r]) cudaIpcCloseMemHandle(h->peer_arena[r]);
+        h->peer_arena[r] = nullptr; h->peer_ipc[r] = false;
+    }
+    for (int r = 0; r < nranks; ++r) {
+        if (r == my_rank) continue;
+        ptd_strip_info info;
+        memcpy(&info, &in[r], sizeof info);
         if (info.pid_tag == (int)getpid()) {
             if (info.device != h->device) {
                 cudaError_t e = cudaDeviceEnablePeerAccess(info.device, 0);
                 if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) { ptd_set_error("ptd_dn_strip_connect: no peer access %d -> %d: %s", h->device, info.device, cudaGetErrorString(e)); return PTD_ERR_CUDA; }
                 cudaGetLastError();
             }
-            h->peer_arena[d] = (unsigned char*)(uintptr_t)info.arena;
+            h->peer_arena[r] = (unsigned char*)(uintptr_t)info.arena;
         } else {
             cudaIpcMemHandle_t ipc;
             memcpy(&ipc, info.ipc, sizeof ipc);
-            void* p = nullptr;
-            CUDA_TRY(cudaIpcOpenMemHandle(&p, ipc, cudaIpcMemLazyEnablePeerAccess));
-            h->peer_arena[d] = (unsigned char*)p; h->peer_ipc[d] = true;
+            void* q = nullptr;
+            CUDA_TRY(cudaIpcOpenMemHandle(&q, ipc, cudaIpcMemLazyEnablePeerAccess));
+            h->peer_arena[r] = (unsigned char*)q; h->peer_ipc[r] = true;
         }
-        h->peer_info[d] = info; h->has_peer[d] = true;
+        h->peer_info[r] = info;
     }
+    h->rank = my_rank; h->nranks = nranks;
+    h->has_peer[0] = my_rank > 0; h->has_peer[1] = my_rank + 1 < nranks;
     return PTD_OK;
 }
 
+// dir: 0 = the strip above (rank - 1), 1 = the strip below (rank + 1)
 static DnTensor peer_tensor(const ptd_dn* h, int dir, int id) {
+    const int r = h->rank + (dir == 0 ? -1 : 1);
     DnTensor t = h->tensors[id];
-    t.base = (float*)(h->peer_arena[dir] + h->peer_info[dir].tensor_off[id]);
-    t.rows = h->peer_info[dir].tensor_rows[id];
+    t.base = (float*)(h->peer_arena[r] + h->peer_info[r].tensor_off[id]);
+    t.rows = h->peer_info[r].tensor_rows[id];
     if (t.lo_off) t.lo_off = (t.floats() + 255) & ~(size_t)255;       // the neighbour's hi -> lo distance follows ITS row count
     return t;
 }
 static uint32_t* peer_flag(const ptd_dn* h, int dir, int id, int from) {
-    return (uint32_t*)(h->peer_arena[dir] + h->peer_info[dir].flags_off + ((size_t)id * 2 + from) * 32);
+    const int r = h->rank + (dir == 0 ? -1 : 1);
+    return (uint32_t*)(h->peer_arena[r] + h->peer_info[r].flags_off + ((size_t)id * 2 + from) * 32);
 }
 
 // Launches layers [first, last) of forward(x, j) on `st`.  ptd_dn_forward runs them all; a same-GPU strip group (tests) interleaves.
@@ -582,27 +619,47 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
             TcConvPlan& plan = L.tc[h->parity];
             TcStripLink& k = plan.p.link;
             memset(&k, 0, sizeof k);
-            if (h->has_peer[0] || h->has_peer[1]) {
-                k.done = L.d_done; k.epoch = h->epoch;
+            if (h->nranks > 1) {
+                k.epoch = h->epoch;
                 const int srcs[2] = {s0, s1};
                 for (int i = 0; i < 2; ++i) {
                     if (srcs[i] < 0) continue;
+                    if (h->tensor_full[srcs[i]]) {
+                        // replicated level: complete on this GPU - except the gathered tensor, whose rows arrive from every other strip
+                        if (srcs[i] == h->t_gather && L.spec.kind == DN_L1)
+                            for (int r = 0; r < h->nranks; ++r)
+                                if (r != h->rank) k.gather_wait[r] = (const uint32_t*)(h->arena + h->gflags_off + (size_t)r * 32);
+                        continue;
+                    }
                     // a hidden state read by layer2's first conv was produced by the PREVIOUS frame (or just zeroed)
                     const bool prev = L.spec.kind == DN_L2A && i == 1;
                     if (prev && reset_hidden) continue;
                     for (int d = 0; d < 2; ++d)
                         if (h->has_peer[d]) { k.wait[2 * i + d] = h->flag(srcs[i], d); k.wait_epoch[2 * i + d] = prev ? h->epoch - 1 : h->epoch; }
                 }
-                for (int d = 0; d < 2; ++d) {
-                    if (!h->has_peer[d]) continue;
-                    // our first row -> the UP neighbour's bottom apron, flagged there as "from down" (1); last row -> DOWN neighbour, "from up" (0)
-                    (d == 0 ? k.out_up : k.out_down) = peer_tensor(h, d, o);
-                    k.sig[d] = peer_flag(h, d, o, d == 0 ? 1 : 0);
-                    if (L.pool != -1) {
-                        (d == 0 ? k.pool_up : k.pool_down) = peer_tensor(h, d, L.pool);
-                        k.sig[2 + d] = peer_flag(h, d, L.pool, d == 0 ? 1 : 0);
+                if (!h->tensor_full[o]) {
+                    k.done = L.d_done;
+                    for (int d = 0; d < 2; ++d) {
+                        if (!h->has_peer[d]) continue;
+                        // our first row -> the UP neighbour's bottom apron, flagged there as "from down" (1); last row -> DOWN neighbour, "from up" (0)
+                        (d == 0 ? k.out_up : k.out_down) = peer_tensor(h, d, o);
+                        k.sig[d] = peer_flag(h, d, o, d == 0 ? 1 : 0);
+                        if (L.pool != -1 && !h->tensor_full[L.pool]) {
+                            (d == 0 ? k.pool_up : k.pool_down) = peer_tensor(h, d, L.pool);
+                            k.sig[2 + d] = peer_flag(h, d, L.pool, d == 0 ? 1 : 0);
+                        }
+                    }
+                    if (L.pool != -1 && h->tensor_full[L.pool]) {           // the gather: our pooled rows go into every strip's full-height tensor
+                        k.pool_yoff = h->row0 >> h->tensor_level[L.pool];
+                        for (int r = 0; r < h->nranks; ++r) {
+                            if (r == h->rank) continue;
+                            k.gather_base[r] = (float*)(h->peer_arena[r] + h->peer_info[r].tensor_off[L.pool]);
+                            k.gather_sig[r] = (uint32_t*)(h->peer_arena[r] + h->peer_info[r].gflags_off + (size_t)h->rank * 32);
+                        }
                     }
                 }
+            } else if (L.pool != -1 && h->tensor_full[L.pool] && !h->tensor_full[o]) {
+                k.pool_yoff = h->row0 >> h->tensor_level[L.pool];           // a single strip that is not the whole frame cannot exist; kept for symmetry
             }
             ptd_status rc = tc_conv_launch(plan, st, &h->launches, nullptr);
             if (rc != PTD_OK) return rc;

@@ -56,8 +56,7 @@ class StripPipeline:
         pt_blobs = exchange_blobs(self.pt.export_info(), dist, world)
         dn_blobs = exchange_blobs(self.dn.export_info(), dist, world)
         self.pt.connect(pt_blobs, rank)
-        up, down = neighbours(dn_blobs, rank)
-        self.dn.connect(up, down)
+        self.dn.connect(dn_blobs, rank)
         if dist is not None:
             dist.barrier()
 

@@ -137,15 +137,17 @@ ptd_status ptd_dn_forward_host(ptd_dn*, const float* gbuffer_host, float* rgb_ho
  * A strip handle owns padded rows [row0, row0 + rows) (multiples of 32) of the frame.  Its convs store their first / last
  * output row directly into the neighbour strips' halo rows over NVLink (peer pointers) and raise a flag there; the
  * neighbours' next conv waits for the flag on the device.  No host round trip, no NCCL call on the data path.
- * Setup (once): every rank creates its strip, exports a ptd_dn_strip_info_size()-byte POD blob, the ranks exchange the blobs
- * (torch.distributed all_gather on the host side) and connect to the strips above / below.  Needs PTD_DN_TF32.
+ * Levels at 1/8 resolution and below are not tiled: every strip computes them in full from a level-3 input that all strips
+ * gather into each other's memory (13 of the 28 convs, 3 % of the FLOPs, no exchange at all).
+ * Setup (once): every rank creates its strip, exports a ptd_dn_strip_info_size()-byte POD blob, the ranks all-gather the blobs
+ * (torch.distributed on the host side) and each passes the concatenation to ptd_dn_strip_connect.  Needs a tensor-core mode.
  * Per frame every rank calls ptd_dn_forward with the FULL-frame G-buffer [10][H][W] on its own device; it writes rows
  * [row0, min(row0 + rows, H)) of the full-frame rgb [3][H][W].  All ranks must pass the same reset_hidden. */
 ptd_status ptd_dn_strip_partition(int H, int nstrips, int index, int* row0, int* rows);   /* even split of the 32-row groups */
 ptd_status ptd_dn_create_strip(const char* weights_path, int H, int W, int row0, int rows, int device, unsigned flags, ptd_dn** out);
 int ptd_dn_strip_info_size(void);
 ptd_status ptd_dn_strip_export(ptd_dn*, void* info_out, int capacity);
-ptd_status ptd_dn_strip_connect(ptd_dn*, const void* info_up, const void* info_down);     /* NULL = frame border */
+ptd_status ptd_dn_strip_connect(ptd_dn*, const void* infos_in_strip_order, int nranks, int my_rank);   /* all strips' blobs, top strip first */
 /* Strips living in ONE process (tests; single-process multi-GPU): issues the frame layer by layer across the handles. */
 ptd_status ptd_dn_forward_group(ptd_dn** strips, int n, const float* const* gbuffers_dev, float* const* rgbs_dev, int reset_hidden,
                                 void* const* streams);

@@ -121,7 +121,7 @@ def test_row_strips_equal_the_full_frame(nstrips, mode, wfile):
     strips = [capi.Denoiser(wfile, H, W, flags=_mode(capi, mode), strip=p) for p in parts]
     infos = [s.export_info() for s in strips]
     for i, s in enumerate(strips):
-        s.connect(infos[i - 1] if i > 0 else None, infos[i + 1] if i + 1 < nstrips else None)
+        s.connect(infos, i)
     g = torch.empty(10 * H * W, dtype=torch.float32, device="cuda")
     out = torch.zeros(3 * H * W, dtype=torch.float32, device="cuda")
     for j, reset in enumerate([True, False, False, True, False]):

@@ -224,7 +224,7 @@ def test_strip_pipeline_equals_full_pipeline(tmp_path):
     pinfo, dinfo = [s.export_info() for s in pts], [s.export_info() for s in dns]
     for i in range(n):
         pts[i].connect(pinfo, i)
-        dns[i].connect(dinfo[i - 1] if i > 0 else None, dinfo[i + 1] if i + 1 < n else None)
+        dns[i].connect(dinfo, i)
     gs = [torch.zeros(10 * H * W, dtype=torch.float32, device="cuda") for _ in range(n)]     # one G-buffer per strip: only its rows are filled
     out = torch.zeros(3 * H * W, dtype=torch.float32, device="cuda")
     for k in range(3):
