@@ -80,6 +80,13 @@ class FrameLoop:
         import ctypes
         import torch
         self._C, self._torch = ctypes, torch
+        # Strip mode stays SERIAL.  With two streams a denoiser conv of frame k that spins on a neighbour's flag holds ~200 KB of
+        # every SM's shared memory, so the path-trace shade blocks of frame k + 1 (41 KB each) cannot become resident beside it; if
+        # the neighbour's SMs are in turn held by ITS frame-k+1 shade blocks spinning on OUR frame-k+1 live count, nobody moves.
+        # Seen once as a hang at N = 4 (measured before that: 562 / 798 frames/s at N = 4 / 8 instead of 468 / 597).  On one
+        # stream every wait points at a kernel that is earlier in every rank's order, so the serial loop cannot deadlock.
+        if pipe.world > 1:
+            pipelined = False
         self.pipe, self.pipelined = pipe, pipelined
         P = pipe.W * pipe.H
         self.s_pt = torch.cuda.Stream()

@@ -228,7 +228,7 @@ def main():
     Hp, Wp = dn.padded_size()
     # the frame loop: path trace of frame k + 1 overlaps the denoiser of frame k on a second stream (tiling.FrameLoop); the profiling
     # and host-API legs below use the serial single-stream form
-    loop = tiling.FrameLoop(pipe, pipelined=not args.no_pipeline)
+    loop = tiling.FrameLoop(pipe, pipelined=not args.no_pipeline)        # (FrameLoop itself stays serial in strip mode, see tiling.py)
     stream = loop.s_dn
     sptr = C.c_void_p(stream.cuda_stream)
     gbuf = loop.gbuf[0]
@@ -418,7 +418,7 @@ def main():
                      "fp32": "f32"}[args.mode],
            "data": "synthetic",
            "config": {"workload": "%s: %s" % (args.config, desc), "frames": "camera pan phi_k = phi_0 + 0.002 k, recurrent hidden state carried",
-                      "frame_loop": "serial, one stream" if args.no_pipeline else "two streams, double-buffered G-buffer: path trace of frame k+1 overlaps the denoiser of frame k",
+                      "frame_loop": "two streams, double-buffered G-buffer: path trace of frame k+1 overlaps the denoiser of frame k" if loop.pipelined else "serial, one stream",
                       "triangles": nfaces, "live_paths_per_bounce": live[:run], "denoiser_padded": [Hp, Wp], "weights": "synthetic seed 1234 (no checkpoint ships)",
                       "l2": "per-frame working set (>1.5 GB of activations) exceeds the 126 MB L2; no explicit flush",
                       "parallelism": "1 GPU" if world == 1 else "each frame tiled in %d row strips (path tracer + denoiser), one strip per GPU; halo rows / live counts "
