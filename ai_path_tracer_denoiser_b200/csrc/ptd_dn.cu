@@ -19,6 +19,7 @@
 #include <cuda_fp16.h>
 #include <unistd.h>
 #include <algorithm>
+#include <cstdlib>
 #include <cstdint>
 #include <cstring>
 #include <cmath>
@@ -253,9 +254,11 @@ static ptd_status read_ptdw(const char* path, std::map<std::string, std::vector<
 // 28 convs, 3 % of the FLOPs) are computed IN FULL by every strip: encoder 3's fused max-pool stores its rows of the level-3 input
 // into every strip's full-height tensor ("gather": peer stores to all strips + one flag per source strip), the 13 convs then run
 // without any exchange, and decoder 3 reads its rows of the replicated level-3 tensors back into the strip (src_yoff).
+// Opt-in for now: environment PTD_DN_REPL_LEVEL=3 at ptd_dn_create_strip time on every rank (default 6 = every level tiled);
+// validated bit-identical to the untiled run (tests, 8 processes at 720p), not yet re-timed under the serial frame loop.
 #define DN_MAX_TENSORS 48
 #define DN_MAX_RANKS 8
-#define DN_REPL_LEVEL 3
+#define DN_REPL_LEVEL 3                       /* the level replication starts at when enabled */
 struct ptd_strip_info {                      // POD, exchanged between the ranks as bytes (ptd_dn_strip_export / _connect)
     unsigned char ipc[64];                   // cudaIpcMemHandle_t of the activation arena
     unsigned long long arena;                // the arena's address in the owner's process (same-process connections)
@@ -299,7 +302,8 @@ struct ptd_dn {
     ptd_strip_info peer_info[DN_MAX_RANKS];
     bool has_peer[2] = {false, false};                     // a strip above / below exists
     size_t gflags_off = 0;
-    int t_gather = -1;                                     // the gathered tensor (pooled output of encoder DN_REPL_LEVEL, full height)
+    int repl_level = 6;                                    // levels >= this are replicated on every strip (6 = none)
+    int t_gather = -1;                                     // the gathered tensor (pooled output of encoder repl_level, full height)
     std::vector<int> tensor_level; std::vector<char> tensor_full;
     uint32_t epoch = 0;
     uint32_t* d_pack_done = nullptr;
@@ -340,6 +344,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     CUDA_TRY(cudaSetDevice(device));
     ptd_dn* h = new ptd_dn();
     h->device = device; h->flags = flags; h->H = H; h->W = W; h->Hp = Hp; h->Wp = Wp; h->row0 = row0; h->rows = rows; h->strip = strip;
+    if (const char* e = getenv("PTD_DN_REPL_LEVEL")) { const int v = atoi(e); if (v >= 3 && v <= 6) h->repl_level = v; }
     auto fail = [&](ptd_status code) { ptd_dn_destroy(h); return code; };
     auto dalloc = [&](size_t floats) -> float* {
         void* p = nullptr;
@@ -358,7 +363,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     const int act_esize = flags == PTD_DN_F16 ? 2 : 4;       // fp16 activations everywhere but the network's output
     auto tnew = [&](int c, int lvl, int esize = 0) -> int {
         DnTensor t;
-        const bool full = strip && lvl >= DN_REPL_LEVEL;               // replicated level: every strip holds the whole tensor
+        const bool full = strip && lvl >= h->repl_level;                // replicated level: every strip holds the whole tensor
         t.cp = cpad(c); t.rows = (full ? Hp : rows) >> lvl; t.W = Wp >> lvl; t.esize = esize ? esize : act_esize;
         h->tensor_level.push_back(lvl); h->tensor_full.push_back(full ? 1 : 0);
         const bool pair = flags == PTD_DN_3XTF32 && esize == 0;        // hi copy followed by the lo copy
@@ -386,7 +391,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     arena_bytes += h->tensors.size() * 2 * 32 + 1024;
     h->gflags_off = arena_bytes;
     arena_bytes += DN_MAX_RANKS * 32 + 1024;
-    h->t_gather = strip ? pooled[DN_REPL_LEVEL - 1] : -1;
+    h->t_gather = (strip && h->repl_level >= 1 && h->repl_level <= 5) ? pooled[h->repl_level - 1] : -1;
     if (cudaMalloc((void**)&h->arena, arena_bytes) != cudaSuccess) { ptd_set_error("ptd_dn_create: cudaMalloc(%zu B activation arena) failed: %s", arena_bytes, cudaGetErrorString(cudaGetLastError())); return fail(PTD_ERR_CUDA); }
     h->arena_bytes = arena_bytes;
     cudaMemset(h->arena, 0, arena_bytes);
@@ -407,7 +412,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
         L.spec = specs[li];
         const DnLayerSpec& s = specs[li];
         const int lvl = s.level;
-        L.H = ((strip && lvl >= DN_REPL_LEVEL) ? Hp : rows) >> lvl; L.W = Wp >> lvl;
+        L.H = ((strip && lvl >= h->repl_level) ? Hp : rows) >> lvl; L.W = Wp >> lvl;
         L.src1 = -1; L.pool = -1;
         if (s.kind == DN_L1) { L.src0 = lvl == 0 ? h->t_in16 : pooled[lvl - 1]; L.out = out1[lvl]; }
         else if (s.kind == DN_L2A) { L.src0 = out1[lvl]; L.src1 = HR(lvl); L.out = mid[lvl]; }
@@ -508,6 +513,7 @@ extern "C" ptd_status ptd_dn_strip_export(ptd_dn* h, void* info_out, int capacit
     for (size_t i = 0; i < h->tensors.size(); ++i) { info.tensor_off[i] = h->tensor_off[i]; info.tensor_rows[i] = h->tensors[i].rows; }
     info.flags_off = h->flags_off;
     info.gflags_off = h->gflags_off;
+    info.reserved = h->repl_level;
     memcpy(info_out, &info, sizeof info);
     return PTD_OK;
 }
@@ -523,6 +529,7 @@ extern "C" ptd_status ptd_dn_strip_connect(ptd_dn* h, const void* infos, int nra
         ptd_strip_info info;
         memcpy(&info, &in[r], sizeof info);
         if (info.ntensors != (int)h->tensors.size() || info.Hp != h->Hp || info.Wp != h->Wp) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: strip %d was built for another frame size", r);
+        if (info.reserved != h->repl_level) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: strip %d replicates from level %d, this one from %d (PTD_DN_REPL_LEVEL must agree on all ranks)", r, info.reserved, h->repl_level);
         if (info.row0 != row) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: strip %d starts at row %d, expected %d", r, info.row0, row);
         row += info.rows;
         if (r == my_rank && (info.row0 != h->row0 || info.rows != h->rows)) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_strip_connect: blob %d is not this handle's", r);

@@ -137,8 +137,9 @@ ptd_status ptd_dn_forward_host(ptd_dn*, const float* gbuffer_host, float* rgb_ho
  * A strip handle owns padded rows [row0, row0 + rows) (multiples of 32) of the frame.  Its convs store their first / last
  * output row directly into the neighbour strips' halo rows over NVLink (peer pointers) and raise a flag there; the
  * neighbours' next conv waits for the flag on the device.  No host round trip, no NCCL call on the data path.
- * Levels at 1/8 resolution and below are not tiled: every strip computes them in full from a level-3 input that all strips
- * gather into each other's memory (13 of the 28 convs, 3 % of the FLOPs, no exchange at all).
+ * Optionally (environment PTD_DN_REPL_LEVEL=3 on every rank when the strips are created) the levels at 1/8 resolution and below
+ * are not tiled: every strip computes them in full from a level-3 input that all strips gather into each other's memory
+ * (13 of the 28 convs, 3 % of the FLOPs, no exchange at all).
  * Setup (once): every rank creates its strip, exports a ptd_dn_strip_info_size()-byte POD blob, the ranks all-gather the blobs
  * (torch.distributed on the host side) and each passes the concatenation to ptd_dn_strip_connect.  Needs a tensor-core mode.
  * Per frame every rank calls ptd_dn_forward with the FULL-frame G-buffer [10][H][W] on its own device; it writes rows

@@ -106,9 +106,19 @@ def test_full_size_720p_properties(mode, wfile):
     assert np.abs(a - b).max() <= 2 * TOL[mode][0]
 
 
+@pytest.fixture(params=["tiled", "replicated"])
+def repl_levels(request, monkeypatch):
+    """All levels tiled (default) or levels >= 1/8 resolution replicated on every strip (PTD_DN_REPL_LEVEL=3, read at create)."""
+    if request.param == "replicated":
+        monkeypatch.setenv("PTD_DN_REPL_LEVEL", "3")
+    else:
+        monkeypatch.delenv("PTD_DN_REPL_LEVEL", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("mode", ["tf32", "f16", "3xtf32"])
 @pytest.mark.parametrize("nstrips", [2, 3])
-def test_row_strips_equal_the_full_frame(nstrips, mode, wfile):
+def test_row_strips_equal_the_full_frame(nstrips, mode, wfile, repl_levels):
     """Multi-GPU tiling on ONE device: the frame cut into row strips (32-row aligned, uneven), each strip a handle with its
     own arena, halo rows stored into the neighbour's apron by the conv epilogues + device-side flags.  Result must be
     bit-identical to the single-handle forward over 4 frames (recurrent state carried, then reset)."""

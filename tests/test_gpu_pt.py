@@ -208,11 +208,16 @@ def test_row_strips_equal_the_full_frame(scene, W, H, n):
         _same(cat, full.dump_paths(b), "bounce %d paths (strips concatenated)" % b)
 
 
-def test_strip_pipeline_equals_full_pipeline(tmp_path):
+@pytest.mark.parametrize("repl", [None, "3"], ids=["tiled", "replicated"])
+def test_strip_pipeline_equals_full_pipeline(tmp_path, repl, monkeypatch):
     """Path trace strips feeding denoiser strips (each strip only ever sees its own G-buffer rows) == the untiled frame loop."""
     capi = _capi()
     import torch
     from ai_path_tracer_denoiser_b200 import weights
+    if repl:
+        monkeypatch.setenv("PTD_DN_REPL_LEVEL", repl)          # levels >= 1/8 resolution replicated on every strip
+    else:
+        monkeypatch.delenv("PTD_DN_REPL_LEVEL", raising=False)
     wfile = weights.save_weights(weights.synthetic_state_dict(1234), str(tmp_path / "w.ptdw"))
     W, H, n = 96, 80, 3
     sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
