@@ -50,8 +50,13 @@ def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
-            raise PtdError("libptd.so is not built (%s); run `python -c 'import __graft_entry__ as g; g.build()'` "
-                           "or `make -C ai_path_tracer_denoiser_b200/csrc` - there is no CPU fallback" % LIB_PATH)
+            # a fresh checkout (built artefacts are git-ignored): build in-tree once - nvcc cross-compiles sm_100a without a GPU
+            import subprocess
+            try:
+                subprocess.check_call(["make", "-C", os.path.join(HERE, "csrc"), "-j4", "all"], stdout=subprocess.DEVNULL)
+            except Exception as e:
+                raise PtdError("libptd.so is not built (%s) and `make -C ai_path_tracer_denoiser_b200/csrc` failed: %s - "
+                               "there is no CPU fallback" % (LIB_PATH, e))
         L = C.CDLL(LIB_PATH)
         L.ptd_last_error.restype = C.c_char_p
         for f in ("ptd_scene_geoms", "ptd_scene_materials", "ptd_scene_faces", "ptd_scene_mesh_box", "ptd_scene_camera"):
