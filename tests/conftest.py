@@ -14,6 +14,15 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+def pytest_collection_modifyitems(config, items):
+    """Run the opt-in configurations (`replicated` levels: PTD_DN_REPL_LEVEL=3) after everything else: the round-end driver runs
+    `pytest -m gpu -x`, and a failure in an opt-in mode must not hide the results of the default configuration."""
+    late = [it for it in items if "replicated" in it.nodeid or "experimental" in it.nodeid]
+    if late:
+        ids = {id(it) for it in late}
+        items[:] = [it for it in items if id(it) not in ids] + late
+
+
 @pytest.fixture(scope="session")
 def root():
     return ROOT
