@@ -232,9 +232,6 @@ __device__ __forceinline__ void mma_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a
 }  // namespace tc
 
 namespace tc {
-}  // namespace tc
-
-namespace tc {
 // 16 consecutive output channels [c0, c0 + 16) of one pixel -> the tensor's channel vectors (row: address of the pixel in vector 0)
 __device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, const float* o) {
     if (t.lo_off) {                                        // 3xTF32: hi = tf32(v), lo = tf32(v - hi)
@@ -365,10 +362,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // ===== TMA producer: warp-uniform loop, one elected lane issues (same reason as the MMA role below) ==========
         // row-strip mode: the apron rows of the sources are written by the neighbour GPUs; wait for this frame's flags
         bool waited = false;
+        PtdSpinGuard guard;                                            // traps after PTD_SPIN_TIMEOUT_NS instead of hanging the GPU
         for (int i = 0; i < 4; ++i)
-            if (p.link.wait[i]) { while ((int)(tc::ld_acquire_sys(p.link.wait[i]) - p.link.wait_epoch[i]) < 0) { } waited = true; }
+            if (p.link.wait[i]) { while ((int)(tc::ld_acquire_sys(p.link.wait[i]) - p.link.wait_epoch[i]) < 0) guard.tick(); waited = true; }
         for (int i = 0; i < 8; ++i)
-            if (p.link.gather_wait[i]) { while ((int)(tc::ld_acquire_sys(p.link.gather_wait[i]) - p.link.epoch) < 0) { } waited = true; }
+            if (p.link.gather_wait[i]) { while ((int)(tc::ld_acquire_sys(p.link.gather_wait[i]) - p.link.epoch) < 0) guard.tick(); waited = true; }
         if (waited) asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (TMA) reads
         if (p.resident && tc::elect_one()) {                         // the layer's whole weight set, once per CTA
             tc::mbar_expect_tx(wfull, p.w_total_bytes);

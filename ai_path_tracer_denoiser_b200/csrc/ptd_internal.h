@@ -13,6 +13,26 @@ static_assert(sizeof(ptd_path_segment) == 44 && sizeof(ptd_intersection) == 36 &
 void ptd_set_error(const char* fmt, ...);
 #define PTD_FAIL(code, ...) do { ptd_set_error(__VA_ARGS__); return (code); } while (0)
 
+#ifdef __CUDACC__
+// Watchdog of the device-side waits on another GPU's stores (row-strip mode: halo flags of the convs, live-count mail of pt_shade).
+// A peer that died or a mis-ordered launch would otherwise spin for ever and take the GPU with it; after PTD_SPIN_TIMEOUT_NS the
+// waiting kernel traps instead, the context reports a launch failure on the next CUDA call and the C ABI returns PTD_ERR_CUDA.
+// tick() is called once per poll; the timer is read every 1024 polls (a poll is an L2 round trip, so about once per millisecond).
+#ifndef PTD_SPIN_TIMEOUT_NS
+#define PTD_SPIN_TIMEOUT_NS 20000000000ull              /* 20 s: far above any start-up skew between the ranks of one box */
+#endif
+struct PtdSpinGuard {
+    unsigned long long t0 = 0ull; unsigned polls = 0u;
+    __device__ __forceinline__ void tick() {
+        if ((++polls & 1023u) != 0u) return;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t0 == 0ull) t0 = t;
+        else if (t - t0 > PTD_SPIN_TIMEOUT_NS) __trap();
+    }
+};
+#endif
+
 struct ptd_scene {
     std::vector<ptd_geom> geoms;
     std::vector<ptd_material> materials;

@@ -354,12 +354,18 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
         // are contiguous pixel ranges and compaction is stable, so that index is (live paths of the strips above) + local index;
         // the strips above published their live counts of this bounce into our mailbox (peer stores) when they compacted.
         int goff = FIRST ? p.pix0 : 0;
-        if (!FIRST)
+        if (!FIRST) {
+            PtdSpinGuard guard;                                            // traps after PTD_SPIN_TIMEOUT_NS instead of hanging the GPU
             for (int r = 0; r < p.rank; ++r) {
                 unsigned long long m;
-                do { asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(m) : "l"(p.mail + (size_t)p.bounce * PT_MAX_RANKS + r) : "memory"); } while ((unsigned)(m >> 32) != p.epoch);
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(m) : "l"(p.mail + (size_t)p.bounce * PT_MAX_RANKS + r) : "memory");
+                    if ((unsigned)(m >> 32) == p.epoch) break;
+                    guard.tick();
+                }
                 goff += (int)(unsigned)m;
             }
+        }
         s_goff = goff;                                                    // read after the next __syncthreads
     }
     const int valid = min(PT_BLOCK, n - base);

@@ -143,7 +143,9 @@ ptd_status ptd_dn_forward_host(ptd_dn*, const float* gbuffer_host, float* rgb_ho
  * Setup (once): every rank creates its strip, exports a ptd_dn_strip_info_size()-byte POD blob, the ranks all-gather the blobs
  * (torch.distributed on the host side) and each passes the concatenation to ptd_dn_strip_connect.  Needs a tensor-core mode.
  * Per frame every rank calls ptd_dn_forward with the FULL-frame G-buffer [10][H][W] on its own device; it writes rows
- * [row0, min(row0 + rows, H)) of the full-frame rgb [3][H][W].  All ranks must pass the same reset_hidden. */
+ * [row0, min(row0 + rows, H)) of the full-frame rgb [3][H][W].  All ranks must pass the same reset_hidden.
+ * Failure detection: a kernel that waits for another strip (halo flag, live-count mail) gives up after 20 s (PTD_SPIN_TIMEOUT_NS
+ * at build time) and traps - a dead or mis-ordered peer surfaces as PTD_ERR_CUDA from the next call instead of a hung GPU. */
 ptd_status ptd_dn_strip_partition(int H, int nstrips, int index, int* row0, int* rows);   /* even split of the 32-row groups */
 ptd_status ptd_dn_create_strip(const char* weights_path, int H, int W, int row0, int rows, int device, unsigned flags, ptd_dn** out);
 int ptd_dn_strip_info_size(void);
