@@ -529,6 +529,20 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
     }
 }
 
+// PTD_PT_GATED_MAIL: one warp, no shared memory - lane r waits for strip r's live count of this bounce.  When it exits the mail
+// is in place, so the wait loop at the top of pt_shade (unchanged) passes on its first read and no 512-thread shade block with
+// 41 KB of shared memory ever sits on an SM waiting for another GPU.
+__global__ void __launch_bounds__(32) pt_mail_gate(const unsigned long long* mail, int bounce, int rank, unsigned epoch) {
+    if ((int)threadIdx.x >= rank) return;
+    PtdSpinGuard guard;
+    for (;;) {
+        unsigned long long m;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(m) : "l"(mail + (size_t)bounce * PT_MAX_RANKS + threadIdx.x) : "memory");
+        if ((unsigned)(m >> 32) == epoch) break;
+        guard.tick();
+    }
+}
+
 // ---- material sort (SORT_MATERIAL, pathtrace.cu:508-510): stable counting sort of dst[0,k) by keys[0,k) --------------
 #define SORT_TILE 256
 __global__ void sort_hist(const int* __restrict__ keys, const int* __restrict__ count, int nbins, int nblocks, int* __restrict__ hist) {
@@ -770,6 +784,10 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
         if (b == 0) pt_trace<true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
         else pt_trace<false><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
         mark();
+        if (b > 0 && h->rank > 0 && (h->flags & PTD_PT_GATED_MAIL)) {     // (timed together with the shade kernel it gates)
+            pt_mail_gate<<<1, 32, 0, st>>>(h->d_mail, b, h->rank, h->epoch);
+            h->launches += 1;
+        }
         if (b == 0) pt_shade<true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
         else pt_shade<false><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
         h->launches += 2;

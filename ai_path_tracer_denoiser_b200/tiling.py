@@ -51,7 +51,10 @@ class StripPipeline:
             self.pt = capi.PathTracer(scene, device=device)
             self.dn = capi.Denoiser(weights_path, self.H, self.W, device=device, flags=dn_flags)
             return
-        self.pt = capi.PathTracer(scene, device=device, strip=self.pt_rows)
+        # PTD_STRIP_PIPELINE=1 (same value on every rank): the two-stream frame loop in strip mode.  It needs the gated live-count
+        # mail - with it no path-trace block ever spins on another GPU, which is what made the two-stream loop deadlock (FrameLoop)
+        self.two_stream_ok = os.environ.get("PTD_STRIP_PIPELINE", "0") == "1"
+        self.pt = capi.PathTracer(scene, device=device, strip=self.pt_rows, flags=capi.PT_GATED_MAIL if self.two_stream_ok else 0)
         self.dn = capi.Denoiser(weights_path, self.H, self.W, device=device, flags=dn_flags, strip=self.dn_rows)
         pt_blobs = exchange_blobs(self.pt.export_info(), dist, world)
         dn_blobs = exchange_blobs(self.dn.export_info(), dist, world)
@@ -85,7 +88,10 @@ class FrameLoop:
         # the neighbour's SMs are in turn held by ITS frame-k+1 shade blocks spinning on OUR frame-k+1 live count, nobody moves.
         # Seen once as a hang at N = 4 (measured before that: 562 / 798 frames/s at N = 4 / 8 instead of 468 / 597).  On one
         # stream every wait points at a kernel that is earlier in every rank's order, so the serial loop cannot deadlock.
-        if pipe.world > 1:
+        # PTD_STRIP_PIPELINE=1 re-enables it on top of PTD_PT_GATED_MAIL: the mail wait moves into a one-warp gate kernel, shade blocks
+        # never spin, so a neighbour's convs can always become resident and every conv's wait points at a kernel that will run
+        # (opt-in until it has been soaked on 4 and 8 GPUs; every device-side wait now traps after 20 s instead of hanging).
+        if pipe.world > 1 and not getattr(pipe, "two_stream_ok", False):
             pipelined = False
         self.pipe, self.pipelined = pipe, pipelined
         P = pipe.W * pipe.H

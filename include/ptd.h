@@ -84,7 +84,10 @@ enum {
     PTD_PT_SORT_MATERIAL = 1u,    /* SORT_MATERIAL true  (pathtrace.cu:21, :508-510); default off as in the reference */
     PTD_PT_TRACE = 2u,            /* keep per-bounce PathSegment / ShadeableIntersection arrays for ptd_pt_dump_*     */
     PTD_PT_NO_BVH = 4u,           /* brute-force every face like the reference (pathtrace.cu:258-269); test aid        */
-    PTD_PT_KEEP_TERMINATED = 8u   /* also lay out terminated segments as thrust::partition leaves them (final dump)    */
+    PTD_PT_KEEP_TERMINATED = 8u,  /* also lay out terminated segments as thrust::partition leaves them (final dump)    */
+    PTD_PT_GATED_MAIL = 16u       /* row-strip mode: a one-warp gate kernel ahead of every pt_shade waits for the live-count mail of the
+                                     strips above, so no shade block ever spins while holding an SM (needed when the path tracer and the
+                                     denoiser of a strip run on two streams; see DESIGN.md section 4 "frame loop")            */
 };
 /* Uploads the scene once (the reference re-uploads every frame, main.cpp:143-146) and builds the BVH. */
 ptd_status ptd_pt_create(const ptd_scene*, int device, unsigned flags, ptd_pt** out);

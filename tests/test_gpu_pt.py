@@ -208,6 +208,29 @@ def test_row_strips_equal_the_full_frame(scene, W, H, n):
         _same(cat, full.dump_paths(b), "bounce %d paths (strips concatenated)" % b)
 
 
+@pytest.mark.parametrize("mode", ["experimental-gated-mail"])
+def test_row_strips_gated_mail(mode):
+    """PTD_PT_GATED_MAIL (the flag the opt-in two-stream strip loop needs, PTD_STRIP_PIPELINE=1): the live-count mail is awaited by a
+    one-warp gate kernel ahead of pt_shade.  Same bits as the untiled render, one extra launch per bounce >= 1 on the strips below
+    the first."""
+    capi = _capi()
+    import torch
+    W, H, n = 96, 80, 3
+    sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
+    sc.set_resolution(W, H)
+    ref = capi.PathTracer(sc).render_host()
+    strips = [capi.PathTracer(sc, flags=capi.PT_GATED_MAIL, strip=r) for r in pt_strip_rows(capi, H, n)]
+    infos = [s.export_info() for s in strips]
+    for i, s in enumerate(strips):
+        s.connect(infos, i)
+    g = torch.zeros(10 * H * W, dtype=torch.float32, device="cuda")
+    for rep in range(2):
+        g.zero_()
+        capi.PathTracer.render_group(strips, [g.data_ptr()] * n)
+        torch.cuda.synchronize()
+        assert g.cpu().numpy().reshape(10, H, W).tobytes() == ref.tobytes()
+
+
 @pytest.mark.parametrize("repl", [None, "3"], ids=["tiled", "replicated"])
 def test_strip_pipeline_equals_full_pipeline(tmp_path, repl, monkeypatch):
     """Path trace strips feeding denoiser strips (each strip only ever sees its own G-buffer rows) == the untiled frame loop."""
