@@ -57,6 +57,9 @@ struct PtKernelParams {
     float* gbuf; float* image;
     int* sort_keys;
     ptd_path_segment* trace_paths;
+    // PTD_PT_RAY_SORT (appended: the offsets of everything above are what the default kernels were validated with)
+    const int* order;               // order[k] = slot of the k-th ray in spatial-bin order (pt_trace<false, true> only)
+    int refill;                     // refill threshold of the binned trace kernel
 };
 
 using namespace ptm;
@@ -139,7 +142,7 @@ __device__ __forceinline__ void write_miss(const TraceOut& o, int idx) {
     }
 }
 
-template <bool FIRST>
+template <bool FIRST, bool BINNED = false>
 __global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKernelParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ptd_geom* s_geoms = reinterpret_cast<ptd_geom*>(smem_raw);
@@ -186,6 +189,7 @@ __global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKern
                 if (idx >= n) {
                     exhausted = true;
                 } else {
+                    if (BINNED) idx = __ldg(&p.order[idx]);              // consecutive tickets = rays of one spatial / direction bin
                     have = true;
                     if (FIRST) {
                         ray = camera_ray(p.cam, p.W, p.iter, p.pix0 + idx);
@@ -300,7 +304,7 @@ __global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKern
             }
             const unsigned act = __ballot_sync(FULL, node != PT_SENTINEL);
             if (act == 0u) break;
-            if (!pool_empty && __popc(act) < TR_REFILL) break;
+            if (!pool_empty && __popc(act) < (BINNED ? p.refill : TR_REFILL)) break;
         }
 
         // ---- retire the rays that finished ------------------------------------------------------------------------
@@ -529,6 +533,39 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
     }
 }
 
+// ---- PTD_PT_RAY_SORT: coherent scheduling of the secondary rays ---------------------------------------------------------
+// After a diffuse bounce neighbouring slots of the PathSegment array hold rays that start all over the scene and point anywhere:
+// the 32 lanes of a trace warp walk 32 different parts of the BVH (ncu: 16 of 32 lanes active, one L1 wavefront per lane per node
+// load).  This mode bins the live rays of a bounce by (Morton cell of the origin, direction octant) with a counting sort over
+// slot INDICES - histogram, exclusive scan, scatter - and the trace kernel takes its rays in bin order (p.order).  Only the order
+// in which rays are TRACED changes: every ShadeableIntersection is still written to its ray's own slot, so the PathSegment arrays,
+// the compaction and the RNG indices - everything the parity tests compare - are untouched.
+__device__ __forceinline__ unsigned ray_bin(const float* w, const ptd_aabb& box, int bits) {
+    const float cells = (float)(1 << bits);
+    const float fx = (w[0] - box.lb.x) / fmaxf(box.ub.x - box.lb.x, 1e-20f), fy = (w[1] - box.lb.y) / fmaxf(box.ub.y - box.lb.y, 1e-20f);
+    const float fz = (w[2] - box.lb.z) / fmaxf(box.ub.z - box.lb.z, 1e-20f);
+    const int mx = (1 << bits) - 1;
+    const unsigned cx = (unsigned)min(max((int)(fx * cells), 0), mx), cy = (unsigned)min(max((int)(fy * cells), 0), mx), cz = (unsigned)min(max((int)(fz * cells), 0), mx);
+    unsigned morton = 0;
+    for (int b = 0; b < bits; ++b) morton |= (((cx >> b) & 1u) << (3 * b)) | (((cy >> b) & 1u) << (3 * b + 1)) | (((cz >> b) & 1u) << (3 * b + 2));
+    const unsigned octant = (w[3] < 0.f ? 1u : 0u) | (w[4] < 0.f ? 2u : 0u) | (w[5] < 0.f ? 4u : 0u);
+    return (morton << 3) | octant;                                    // cell-major: concurrently running warps work in the same region
+}
+__global__ void ray_bin_hist(const ptd_path_segment* __restrict__ paths, const int* __restrict__ count, ptd_aabb box, int bits,
+                             unsigned* __restrict__ keys, int* __restrict__ hist) {
+    const int n = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        const unsigned k = ray_bin(reinterpret_cast<const float*>(paths) + (size_t)i * PT_WORDS, box, bits);
+        keys[i] = k;
+        atomicAdd(&hist[k], 1);
+    }
+}
+__global__ void ray_bin_scatter(const unsigned* __restrict__ keys, const int* __restrict__ count, int* __restrict__ offsets, int* __restrict__ order) {
+    const int n = *count;
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        order[atomicAdd(&offsets[keys[i]], 1)] = i;                     // the order inside a bin does not matter
+}
+
 // PTD_PT_GATED_MAIL: one warp, no shared memory - lane r waits for strip r's live count of this bounce.  When it exits the mail
 // is in place, so the wait loop at the top of pt_shade (unchanged) passes on its first read and no 512-thread shade block with
 // 41 KB of shared memory ever sits on an SM waiting for another GPU.
@@ -626,6 +663,10 @@ struct ptd_pt {
     std::vector<cudaEvent_t> events;
     int timed_launches = 0;
     int bvh_nodes = 0, bvh_leaves = 0, bvh_max_leaf = 0, bvh_max_depth = 0;
+    // PTD_PT_RAY_SORT
+    int bin_bits = 0, bin_refill = TR_REFILL, nbins = 0;
+    ptd_aabb bin_box;
+    unsigned* d_bin_keys = nullptr; int* d_bin_order = nullptr; int* d_bin_hist = nullptr;   // hist: [depth][nbins] inside d_ctl (zeroed with it)
 };
 
 extern "C" int ptd_device_count(void) {
@@ -640,7 +681,7 @@ extern "C" void ptd_pt_destroy(ptd_pt* h) {
     cudaFree(h->d_geoms); cudaFree(h->d_geom_bounds); cudaFree(h->d_materials); cudaFree(h->d_faces); cudaFree(h->d_nodes); cudaFree(h->d_tris);
     for (int i = 0; i < 3; ++i) cudaFree(h->d_paths[i]);
     cudaFree(h->d_dead); cudaFree(h->d_isx); cudaFree(h->d_image); cudaFree(h->d_gbuf_own); cudaFree(h->d_ctl); cudaFree(h->d_keys); cudaFree(h->d_hist);
-    cudaFree(h->d_trace_paths); cudaFree(h->d_trace_isx); cudaFree(h->d_mail);
+    cudaFree(h->d_trace_paths); cudaFree(h->d_trace_isx); cudaFree(h->d_mail); cudaFree(h->d_bin_keys); cudaFree(h->d_bin_order);
     for (int r = 0; r < PT_MAX_RANKS; ++r) if (h->peer_mail[r] && h->peer_ipc[r]) cudaIpcCloseMemHandle(h->peer_mail[r]);
     if (h->host_stream[0]) { cudaStreamDestroy(h->host_stream[0]); cudaStreamDestroy(h->host_stream[1]); cudaEventDestroy(h->host_event); }
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
@@ -671,6 +712,8 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
         if (f.materialid < 0 || f.materialid >= (int)sc->materials.size()) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_create: mesh material id %d out of range", f.materialid);
     CUDA_TRY(cudaSetDevice(device));
     ptd_pt* h = new ptd_pt();
+    if (const char* e = getenv("PTD_PT_RAY_SORT")) { if (atoi(e) > 0) flags |= PTD_PT_RAY_SORT; }   // tuning: opt in without touching the caller
+    if (!(sc->faces.size() > 0) || (flags & PTD_PT_NO_BVH)) flags &= ~(unsigned)PTD_PT_RAY_SORT;      // binning only pays for BVH traversal
     h->device = device; h->flags = flags;
     h->cam = sc->camera; h->mesh_box = sc->mesh_box;
     h->W = sc->camera.res_x; h->H = sc->camera.res_y; h->Pfull = h->W * h->H; h->depth = sc->trace_depth;
@@ -711,10 +754,30 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
     // control block: counts[depth+1] | tickets[2*depth] | status[depth][ntiles]
     size_t off_counts = 0, off_ticket = ((size_t)(h->depth + 1) * 4 + 15) / 16 * 16, off_status = off_ticket + ((size_t)h->depth * 8 + 15) / 16 * 16;
     h->ctl_bytes = off_status + (size_t)h->depth * h->ntiles * 8;
+    const size_t off_bins = h->ctl_bytes;
+    if (flags & PTD_PT_RAY_SORT) {
+        h->bin_bits = 4;                                                // 4096 cells x 8 octants = 32768 bins, ~28 rays per bin at 720p
+        if (const char* e = getenv("PTD_PT_RAY_SORT_BITS")) { const int v = atoi(e); if (v >= 1 && v <= 5) h->bin_bits = v; }
+        if (const char* e = getenv("PTD_PT_RAY_SORT_REFILL")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->bin_refill = v; }
+        h->nbins = 8 << (3 * h->bin_bits);
+        h->ctl_bytes += (size_t)h->depth * h->nbins * 4;
+        // cells over the box of everything a ray can start from: the mesh and the geoms
+        h->bin_box = sc->mesh_box;
+        std::vector<ptd_aabb> gb;
+        ptd_geom_bounds(sc->geoms, gb);
+        for (const ptd_aabb& b : gb) {
+            if (!(b.lb.x > -1e30f && b.ub.x < 1e30f)) continue;       // a degenerate transform's "never cull" box
+            h->bin_box.lb.x = std::min(h->bin_box.lb.x, b.lb.x); h->bin_box.lb.y = std::min(h->bin_box.lb.y, b.lb.y); h->bin_box.lb.z = std::min(h->bin_box.lb.z, b.lb.z);
+            h->bin_box.ub.x = std::max(h->bin_box.ub.x, b.ub.x); h->bin_box.ub.y = std::max(h->bin_box.ub.y, b.ub.y); h->bin_box.ub.z = std::max(h->bin_box.ub.z, b.ub.z);
+        }
+        ALLOC(h->d_bin_keys, sizeof(unsigned) * P);
+        ALLOC(h->d_bin_order, sizeof(int) * P);
+    }
     ALLOC(h->d_ctl, h->ctl_bytes);
     ALLOC(h->d_mail, sizeof(unsigned long long) * (size_t)(h->depth + 1) * PT_MAX_RANKS);
     cudaMemset(h->d_mail, 0, sizeof(unsigned long long) * (size_t)(h->depth + 1) * PT_MAX_RANKS);
     h->d_counts = (int*)(h->d_ctl + off_counts); h->d_ticket = (int*)(h->d_ctl + off_ticket); h->d_status = (unsigned long long*)(h->d_ctl + off_status);
+    if (flags & PTD_PT_RAY_SORT) h->d_bin_hist = (int*)(h->d_ctl + off_bins);
     if (sort) {
         h->sort_blocks = (h->P + SORT_TILE - 1) / SORT_TILE;
         ALLOC(h->d_keys, sizeof(int) * P);
@@ -782,6 +845,17 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
         p.ticket = h->d_ticket + 2 * b; p.ticket2 = h->d_ticket + 2 * b + 1;
         p.isx = h->d_trace_isx ? h->d_trace_isx + (size_t)b * h->P : h->d_isx;
         if (b == 0) pt_trace<true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+        else if (h->flags & PTD_PT_RAY_SORT) {
+            // bin the live rays of this bounce, then trace them in bin order (timed together with the trace kernel they serve)
+            int* hist = h->d_bin_hist + (size_t)b * h->nbins;
+            const int blocks = std::min((h->P + 255) / 256, 148 * 8);
+            ray_bin_hist<<<blocks, 256, 0, st>>>(p.src, h->d_counts + b, h->bin_box, h->bin_bits, h->d_bin_keys, hist);
+            sort_scan<<<1, 1024, 0, st>>>(hist, h->nbins);
+            ray_bin_scatter<<<blocks, 256, 0, st>>>(h->d_bin_keys, h->d_counts + b, hist, h->d_bin_order);
+            p.order = h->d_bin_order; p.refill = h->bin_refill;
+            pt_trace<false, true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+            h->launches += 3;
+        }
         else pt_trace<false><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
         mark();
         if (b > 0 && h->rank > 0 && (h->flags & PTD_PT_GATED_MAIL)) {     // (timed together with the shade kernel it gates)

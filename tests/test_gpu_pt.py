@@ -208,6 +208,32 @@ def test_row_strips_equal_the_full_frame(scene, W, H, n):
         _same(cat, full.dump_paths(b), "bounce %d paths (strips concatenated)" % b)
 
 
+@pytest.mark.parametrize("bits", [4, 2], ids=["experimental-ray-sort-4bit", "experimental-ray-sort-2bit"])
+def test_ray_sort_changes_nothing(bits, monkeypatch):
+    """PTD_PT_RAY_SORT (opt-in): rays are TRACED in (origin cell, direction octant) bin order, every record stays in its slot -
+    PathSegments, ShadeableIntersections, live counts, the final partition layout and the G-buffer must all be bit-identical to
+    the default scheduling, on a mesh scene (BVH) with the geoms in play too."""
+    capi = _capi()
+    monkeypatch.setenv("PTD_PT_RAY_SORT_BITS", str(bits))
+    monkeypatch.delenv("PTD_PT_RAY_SORT", raising=False)
+    sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
+    sc.set_resolution(160, 96)
+    out = []
+    for flags in (0, capi.PT_RAY_SORT):
+        pt = capi.PathTracer(sc, flags=flags | capi.PT_TRACE | capi.PT_KEEP_TERMINATED)
+        for rep in range(2):                                       # the second frame reuses the (re-zeroed) bin histograms
+            g = pt.render_host()
+        counts, run = pt.live_counts()
+        out.append((g, counts[:run], [(pt.dump_paths(b), pt.dump_intersections(b)) for b in range(run)], pt.dump_final_paths(), pt.launches()))
+    a, b = out
+    assert a[0].tobytes() == b[0].tobytes() and a[1] == b[1]
+    for k, ((pa, ia), (pb, ib)) in enumerate(zip(a[2], b[2])):
+        _same(pa, pb, "bounce %d paths" % k)
+        _same(ia, ib, "bounce %d intersections" % k)
+    _same(a[3], b[3], "final partition layout")
+    assert b[4] == a[4] + 3 * (sc.counts()[3] - 1)                # three binning kernels per bounce >= 1
+
+
 @pytest.mark.parametrize("mode", ["experimental-gated-mail"])
 def test_row_strips_gated_mail(mode):
     """PTD_PT_GATED_MAIL (the flag the opt-in two-stream strip loop needs, PTD_STRIP_PIPELINE=1): the live-count mail is awaited by a
