@@ -36,7 +36,7 @@ ptd_dn_forward_host ptd_dn_create_strip ptd_dn_padded_size ptd_dn_dump_hidden pt
 ptd_pt_launches_last_render ptd_dn_profile ptd_dn_launch_times ptd_dn_launch_name ptd_pt_profile
 ptd_pt_launch_times ptd_dn_strip_partition ptd_dn_strip_info_size ptd_dn_strip_export ptd_dn_strip_connect
 ptd_dn_forward_group ptd_pt_create_strip ptd_pt_strip_info_size ptd_pt_strip_export ptd_pt_strip_connect
-ptd_pt_render_group""".split()
+ptd_pt_render_group ptd_frame_host""".split()
 
 
 class PtdError(RuntimeError):
@@ -77,6 +77,7 @@ def lib():
         L.ptd_pt_destroy.restype = None
         L.ptd_pt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_pt_render_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ptd_frame_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_pt_export_rgba8.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_pt_live_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
         L.ptd_pt_dump_paths.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.POINTER(C.c_int)]
@@ -261,6 +262,17 @@ class PathTracer:
             camp = cam.ctypes.data
         check(lib().ptd_pt_render_host(self.h, camp, iter, out.ctypes.data), "ptd_pt_render_host")
         return out
+
+    def frame_host(self, dn, cam=None, iter=1, reset=False, want_gbuffer=True):
+        """One frame of runCuda()'s body through ptd_frame_host: (G-buffer [10,H,W] or None, denoised frame [3,H,W])."""
+        g = np.zeros((10, self.H, self.W), np.float32) if want_gbuffer else None
+        rgb = np.zeros((3, self.H, self.W), np.float32)
+        camp = None
+        if cam is not None:
+            cam = np.ascontiguousarray(cam, CAM_DT).reshape(1)
+            camp = cam.ctypes.data
+        check(lib().ptd_frame_host(self.h, dn.h, camp, iter, 1 if reset else 0, g.ctypes.data if want_gbuffer else None, rgb.ctypes.data), "ptd_frame_host")
+        return g, rgb
 
     def render(self, gbuf_dev_ptr, cam=None, iter=1, stream=None):
         camp = None

@@ -651,7 +651,7 @@ struct ptd_pt {
     ptd_path_segment* d_dead = nullptr;
     ptd_intersection* d_isx = nullptr;
     int trace_blocks = 0;
-    float* d_image = nullptr; float* d_gbuf_own = nullptr;
+    float* d_image = nullptr; float* d_gbuf_own = nullptr; float* d_frame_rgb = nullptr;
     unsigned char* d_ctl = nullptr; size_t ctl_bytes = 0;     // counts | tickets | status (memset once per frame)
     int* d_counts = nullptr; int* d_ticket = nullptr; unsigned long long* d_status = nullptr;
     int* d_keys = nullptr; int* d_hist = nullptr; int sort_blocks = 0;
@@ -681,7 +681,7 @@ extern "C" void ptd_pt_destroy(ptd_pt* h) {
     cudaFree(h->d_geoms); cudaFree(h->d_geom_bounds); cudaFree(h->d_materials); cudaFree(h->d_faces); cudaFree(h->d_nodes); cudaFree(h->d_tris);
     for (int i = 0; i < 3; ++i) cudaFree(h->d_paths[i]);
     cudaFree(h->d_dead); cudaFree(h->d_isx); cudaFree(h->d_image); cudaFree(h->d_gbuf_own); cudaFree(h->d_ctl); cudaFree(h->d_keys); cudaFree(h->d_hist);
-    cudaFree(h->d_trace_paths); cudaFree(h->d_trace_isx); cudaFree(h->d_mail); cudaFree(h->d_bin_keys); cudaFree(h->d_bin_order);
+    cudaFree(h->d_trace_paths); cudaFree(h->d_trace_isx); cudaFree(h->d_mail); cudaFree(h->d_bin_keys); cudaFree(h->d_bin_order); cudaFree(h->d_frame_rgb);
     for (int r = 0; r < PT_MAX_RANKS; ++r) if (h->peer_mail[r] && h->peer_ipc[r]) cudaIpcCloseMemHandle(h->peer_mail[r]);
     if (h->host_stream[0]) { cudaStreamDestroy(h->host_stream[0]); cudaStreamDestroy(h->host_stream[1]); cudaEventDestroy(h->host_event); }
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
@@ -977,6 +977,43 @@ extern "C" ptd_status ptd_pt_render_host(ptd_pt* h, const ptd_camera* cam, int i
     rc = pt_run(h, cam, iter, nullptr, h->host_stream[0], 1, h->depth);
     if (rc != PTD_OK) return rc;
     CUDA_TRY(cudaMemcpyAsync(host_tensor, h->d_gbuf_own, 3 * plane, cudaMemcpyDeviceToHost, h->host_stream[0]));
+    CUDA_TRY(cudaStreamSynchronize(h->host_stream[1]));
+    CUDA_TRY(cudaStreamSynchronize(h->host_stream[0]));
+    return PTD_OK;
+}
+
+// One frame of the reference's runCuda() body (main.cpp:143-158: pathtraceInit / pathtrace / network_prediction) as ONE blocking
+// call: path trace -> denoise on the device, host copies only where the caller wants them.  Compared with ptd_pt_render_host +
+// ptd_dn_forward_host (the two reference call sites taken one by one) the 40*P-byte G-buffer is never uploaded again, and its
+// download (host_tensor, optional) overlaps the remaining bounces and the denoiser.
+extern "C" ptd_status ptd_frame_host(ptd_pt* h, ptd_dn* dn, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host) {
+    if (!h || !dn || !rgb_host || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_host: bad argument");
+    if (h->nranks > 1 || h->rows != h->H) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_frame_host: row-strip handles take device pointers (ptd_pt_render + ptd_dn_forward)");
+    CUDA_TRY(cudaSetDevice(h->device));
+    if (!h->host_stream[0]) {
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream[0], cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream[1], cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->host_event, cudaEventDisableTiming));
+    }
+    const size_t plane = sizeof(float) * (size_t)h->Pfull;
+    if (!h->d_frame_rgb) CUDA_TRY(cudaMalloc((void**)&h->d_frame_rgb, 3 * plane));
+    ptd_status rc = pt_run(h, cam, iter, nullptr, h->host_stream[0], 0, 1);
+    if (rc != PTD_OK) return rc;
+    if (host_tensor) {                                                  // normal / depth / albedo planes are final after bounce 0
+        CUDA_TRY(cudaEventRecord(h->host_event, h->host_stream[0]));
+        CUDA_TRY(cudaStreamWaitEvent(h->host_stream[1], h->host_event, 0));
+        CUDA_TRY(cudaMemcpyAsync(host_tensor + 3 * (size_t)h->Pfull, h->d_gbuf_own + 3 * (size_t)h->Pfull, 7 * plane, cudaMemcpyDeviceToHost, h->host_stream[1]));
+    }
+    rc = pt_run(h, cam, iter, nullptr, h->host_stream[0], 1, h->depth);
+    if (rc != PTD_OK) return rc;
+    if (host_tensor) {                                                  // the radiance planes travel while the denoiser runs
+        CUDA_TRY(cudaEventRecord(h->host_event, h->host_stream[0]));
+        CUDA_TRY(cudaStreamWaitEvent(h->host_stream[1], h->host_event, 0));
+        CUDA_TRY(cudaMemcpyAsync(host_tensor, h->d_gbuf_own, 3 * plane, cudaMemcpyDeviceToHost, h->host_stream[1]));
+    }
+    rc = ptd_dn_forward(dn, h->d_gbuf_own, h->d_frame_rgb, reset_hidden, h->host_stream[0]);
+    if (rc != PTD_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(rgb_host, h->d_frame_rgb, 3 * plane, cudaMemcpyDeviceToHost, h->host_stream[0]));
     CUDA_TRY(cudaStreamSynchronize(h->host_stream[1]));
     CUDA_TRY(cudaStreamSynchronize(h->host_stream[0]));
     return PTD_OK;

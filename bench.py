@@ -179,6 +179,8 @@ def main():
     ap.add_argument("--mode", default="f16", choices=["tf32", "f16", "3xtf32", "fp32"])
     ap.add_argument("--config", default="C3", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e", default="calls", choices=["calls", "fused"], help="host-pointer API of the e2e leg at N = 1: the reference's two call sites "
+                    "(ptd_pt_render_host + ptd_dn_forward_host) or the one-call frame (ptd_frame_host: the G-buffer is downloaded but never uploaded again)")
     ap.add_argument("--no-pipeline", action="store_true", help="serial frame loop (path trace, then denoise, on one stream) instead of the two-stream loop")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -353,10 +355,15 @@ def main():
     if world == 1:
         host_g = torch.empty(10 * P, dtype=torch.float32).pin_memory()
         host_rgb = torch.empty(3 * P, dtype=torch.float32).pin_memory()
-        def e2e_step(k, reset):
-            capi.check(L.ptd_pt_render_host(pt.h, cams[k].ctypes.data, 1, C.c_void_p(host_g.data_ptr())), "ptd_pt_render_host")
-            capi.check(L.ptd_dn_forward_host(dn.h, C.c_void_p(host_g.data_ptr()), C.c_void_p(host_rgb.data_ptr()), 1 if reset else 0), "ptd_dn_forward_host")
-        h2d, d2h = 40 * P, 52 * P
+        if args.e2e == "fused":
+            def e2e_step(k, reset):
+                capi.check(L.ptd_frame_host(pt.h, dn.h, cams[k].ctypes.data, 1, 1 if reset else 0, C.c_void_p(host_g.data_ptr()), C.c_void_p(host_rgb.data_ptr())), "ptd_frame_host")
+            h2d, d2h = 84, 52 * P                        # the camera record in, G-buffer + frame out
+        else:
+            def e2e_step(k, reset):
+                capi.check(L.ptd_pt_render_host(pt.h, cams[k].ctypes.data, 1, C.c_void_p(host_g.data_ptr())), "ptd_pt_render_host")
+                capi.check(L.ptd_dn_forward_host(dn.h, C.c_void_p(host_g.data_ptr()), C.c_void_p(host_rgb.data_ptr()), 1 if reset else 0), "ptd_dn_forward_host")
+            h2d, d2h = 40 * P, 52 * P
     else:
         r0, nr = pipe.pt_rows
         host_rgb = [torch.empty(3, nr * W, dtype=torch.float32).pin_memory() for _ in range(2)]
@@ -425,7 +432,8 @@ def main():
                                       "stored into the neighbours' memory by the kernels over NVLink (CUDA IPC peer pointers), no host or NCCL call per frame" % world,
                       "strip_rows_rank0": list(pipe.dn_rows)},
            "gpu_launches": launches_per_step * args.steps,
-           "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3},
+           "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
+                   "api": ("ptd_frame_host" if args.e2e == "fused" else "ptd_pt_render_host + ptd_dn_forward_host") if world == 1 else "ptd_pt_render + ptd_dn_forward per strip, frame rows read back to pinned host memory"},
            "roofline": roof, "clocks": clocks}
     if replicas:
         out["replicas"] = replicas

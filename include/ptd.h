@@ -140,6 +140,11 @@ void ptd_dn_destroy(ptd_dn*);
 ptd_status ptd_dn_forward(ptd_dn*, const float* gbuffer_dev, float* rgb_dev, int reset_hidden, void* stream);
 /* Host-pointer form == the reference call site (main.cpp:101-118: H2D of 40*P bytes, forward, D2H of 12*P). Blocking. */
 ptd_status ptd_dn_forward_host(ptd_dn*, const float* gbuffer_host, float* rgb_host, int reset_hidden);
+/* One frame of runCuda()'s body (main.cpp:143-158) as a single blocking call: path trace with `cam`, denoise on the device (the
+ * G-buffer never leaves it), denoised frame [3][H][W] -> rgb_host.  host_tensor (optional, may be NULL) receives the 10-plane
+ * G-buffer exactly as pathtrace.cu:525 leaves it in scene->state.host_tensor; its copy overlaps the later bounces and the denoiser.
+ * Both handles must live on the same device and cover the whole frame.  Pinned host memory makes the copies asynchronous. */
+ptd_status ptd_frame_host(ptd_pt*, ptd_dn*, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host);
 /* ---- row-strip mode: the denoiser of ONE frame tiled over several GPUs ----------------------------
  * A strip handle owns padded rows [row0, row0 + rows) (multiples of 32) of the frame.  Its convs store their first / last
  * output row directly into the neighbour strips' halo rows over NVLink (peer pointers) and raise a flag there; the

@@ -38,3 +38,25 @@ def test_pipelined_loop_equals_serial_loop(tmp_path):
     for k in range(len(cams)):
         assert frames[True][k].tobytes() == frames[False][k].tobytes(), k
     assert np.isfinite(frames[True][-1]).all() and np.abs(frames[True][-1]).max() > 0
+
+
+@pytest.mark.parametrize("mode", ["experimental-frame-host"])
+def test_frame_host_equals_the_two_host_calls(tmp_path, mode):
+    """ptd_frame_host (runCuda()'s body as one call: the G-buffer stays on the device) == ptd_pt_render_host followed by
+    ptd_dn_forward_host, bit for bit, with and without the optional host copy of the G-buffer, recurrent state carried."""
+    from ai_path_tracer_denoiser_b200 import capi, weights
+    if capi.device_count() < 1:
+        pytest.fail("no CUDA device")
+    wfile = weights.save_weights(weights.synthetic_state_dict(1234), str(tmp_path / "w.ptdw"))
+    sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
+    sc.set_resolution(160, 96)
+    cams = [capi.frame_camera(sc.camera[0], k) for k in range(4)]
+    pt_a, dn_a = capi.PathTracer(sc), capi.Denoiser(wfile, 96, 160, flags=capi.DN_TF32)
+    pt_b, dn_b = capi.PathTracer(sc), capi.Denoiser(wfile, 96, 160, flags=capi.DN_TF32)
+    for k, cam in enumerate(cams):
+        g_ref = pt_a.render_host(cam)
+        rgb_ref = dn_a.forward_host(g_ref, reset=(k == 0))
+        g, rgb = pt_b.frame_host(dn_b, cam=cam, reset=(k == 0), want_gbuffer=(k % 2 == 0))
+        if g is not None:
+            assert g.tobytes() == g_ref.tobytes(), k
+        assert rgb.tobytes() == rgb_ref.tobytes(), k
