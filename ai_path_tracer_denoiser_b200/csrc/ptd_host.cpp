@@ -62,6 +62,7 @@ inline ptd_vec3 cross3(ptd_vec3 x, ptd_vec3 y) {
 inline ptd_vec3 sub3(ptd_vec3 a, ptd_vec3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
 inline ptd_vec3 add3(ptd_vec3 a, ptd_vec3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
 inline float len3(ptd_vec3 a) { return sqrtf(dot3(a, a)); }
+inline ptd_vec3 muls3(ptd_vec3 a, float k) { return v3(a.x * k, a.y * k, a.z * k); }
 
 M4 matmul(const M4& a, const M4& b) {                       // type_mat4x4.inl:686-704
     M4 r;
@@ -647,7 +648,14 @@ void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out) {
     out.nodes.reserve((size_t)n);
     out.nodes.push_back(PtdBvhNode());
     stack.push_back(Task{0, 0, n, 1});
-    const int NB = 16, MAX_LEAF = 4;
+    // Build knobs (environment, read per build; the defaults are the configuration every committed measurement used):
+    //   PTD_BVH_MAX_LEAF  1..16  ranges of at most this many triangles become leaves                          (4)
+    //   PTD_BVH_SWEEP     n      ranges of at most n triangles get an exact sweep-SAH split instead of bins   (0 = never)
+    //   PTD_BVH_LEAF_COST x      > 0: SAH termination - a range of <= 16 triangles becomes a leaf when no split beats
+    //                            area * count * x (x = cost of a triangle test relative to a node visit)       (0 = off)
+    auto env_int = [](const char* k, int def, int lo, int hi) { const char* e = getenv(k); if (!e) return def; const int v = atoi(e); return v < lo || v > hi ? def : v; };
+    const int NB = 16, MAX_LEAF = env_int("PTD_BVH_MAX_LEAF", 4, 1, 16), SWEEP = env_int("PTD_BVH_SWEEP", 0, 0, 1 << 20);
+    const float LEAF_COST = getenv("PTD_BVH_LEAF_COST") ? (float)atof(getenv("PTD_BVH_LEAF_COST")) : 0.f;
     std::vector<int> order;
     order.reserve(n);
     while (!stack.empty()) {
@@ -661,7 +669,7 @@ void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out) {
         const int cnt = t.hi - t.lo;
         out.max_depth = std::max(out.max_depth, t.depth);
         int split = -1;
-        if (cnt > MAX_LEAF) {
+        if (cnt > MAX_LEAF || (LEAF_COST > 0.f && cnt > 1)) {
             float best = FLT_MAX;
             int best_axis = -1, best_bin = -1;
             for (int a = 0; a < 3; ++a) {
@@ -685,7 +693,32 @@ void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out) {
                     if (cost < best) { best = cost; best_axis = a; best_bin = b; }
                 }
             }
-            if (best_axis >= 0) {
+            // exact sweep for small ranges: every split position along every axis, centroids sorted
+            int sweep_axis = -1, sweep_pos = -1;
+            if (cnt <= SWEEP) {
+                std::vector<int> tmp(idx.begin() + t.lo, idx.begin() + t.hi);
+                std::vector<float> ra(cnt);
+                for (int a = 0; a < 3; ++a) {
+                    std::sort(tmp.begin(), tmp.end(), [&](int x, int y) { const float cx = cen[(size_t)x * 3 + a], cy = cen[(size_t)y * 3 + a]; return cx < cy || (cx == cy && x < y); });
+                    Box acc; box_reset(acc);
+                    for (int i = cnt - 1; i > 0; --i) { box_merge(acc, tb[tmp[i]]); ra[i] = box_area(acc); }
+                    box_reset(acc);
+                    for (int i = 1; i < cnt; ++i) {
+                        box_merge(acc, tb[tmp[i - 1]]);
+                        const float cost = box_area(acc) * i + ra[i] * (cnt - i);
+                        if (cost < best) { best = cost; sweep_axis = a; sweep_pos = i; best_axis = -1; }
+                    }
+                }
+            }
+            if (LEAF_COST > 0.f && cnt <= 16 && best < FLT_MAX) {
+                // SAH termination: splitting costs one more node visit (area of this node) plus the children's triangle tests
+                const float here = box_area(nb);
+                if (here * cnt * LEAF_COST <= here + best * LEAF_COST) { best_axis = -1; sweep_axis = -1; }
+            }
+            if (sweep_axis >= 0) {
+                std::sort(idx.begin() + t.lo, idx.begin() + t.hi, [&](int x, int y) { const float cx = cen[(size_t)x * 3 + sweep_axis], cy = cen[(size_t)y * 3 + sweep_axis]; return cx < cy || (cx == cy && x < y); });
+                split = t.lo + sweep_pos;
+            } else if (best_axis >= 0) {
                 float ext = cb.hi[best_axis] - cb.lo[best_axis];
                 float k = NB * (1.f - 1e-6f) / ext;
                 int* first = idx.data() + t.lo;
@@ -807,6 +840,107 @@ void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out) {
         t.v1[0] = f.v[1].x; t.v1[1] = f.v[1].y; t.v1[2] = f.v[1].z; t.material = f.materialid;
         t.v2[0] = f.v[2].x; t.v2[1] = f.v[2].y; t.v2[2] = f.v[2].z; t.pad = 0;
     }
+}
+
+// ---- host-side probe of the BVH (no GPU): the traversal of pt_trace restated on the CPU, checked against the brute-force loop ----
+namespace {
+struct ProbeRng { uint32_t s; float next() { s = s * 1664525u + 1013904223u; return (float)(s >> 8) * (1.0f / 16777216.0f); } };
+// Moeller-Trumbore with back-face culling (the semantics of glm::intersectRayTriangle, intersect.inl:37-74): t = ray parameter or -1
+inline float probe_tri(const float* v0, const float* v1, const float* v2, const float* o, const float* d) {
+    const float e1[3] = {v1[0] - v0[0], v1[1] - v0[1], v1[2] - v0[2]}, e2[3] = {v2[0] - v0[0], v2[1] - v0[1], v2[2] - v0[2]};
+    const float p[3] = {d[1] * e2[2] - d[2] * e2[1], d[2] * e2[0] - d[0] * e2[2], d[0] * e2[1] - d[1] * e2[0]};
+    const float a = e1[0] * p[0] + e1[1] * p[1] + e1[2] * p[2];
+    if (a < 1.1920929e-7f) return -1.f;
+    const float f = 1.0f / a;
+    const float sv[3] = {o[0] - v0[0], o[1] - v0[1], o[2] - v0[2]};
+    const float bx = f * (sv[0] * p[0] + sv[1] * p[1] + sv[2] * p[2]);
+    if (bx < 0.f || bx > 1.f) return -1.f;
+    const float q[3] = {sv[1] * e1[2] - sv[2] * e1[1], sv[2] * e1[0] - sv[0] * e1[2], sv[0] * e1[1] - sv[1] * e1[0]};
+    const float by = f * (d[0] * q[0] + d[1] * q[1] + d[2] * q[2]);
+    if (by < 0.f || by + bx > 1.f) return -1.f;
+    return f * (e2[0] * q[0] + e2[1] * q[1] + e2[2] * q[2]);
+}
+inline void probe_consider(float t, int face, float& t_min, int& best) {     // min t, then lowest face index (pathtrace.cu:259-268)
+    if (t > 0.f && (t_min > t || (t_min == t && best >= 0 && face < best))) { t_min = t; best = face; }
+}
+}  // namespace
+
+// out[0] rays whose BVH hit (face, t) differs from brute force (must be 0)   out[1] interior-node visits per ray
+// out[2] triangle tests per ray   out[3] deepest traversal stack   out[4] 4-wide nodes   out[5] leaves
+// out[6] mean used children per 4-wide node   out[7] rays that hit something (fraction)
+extern "C" ptd_status ptd_bvh_probe(const ptd_scene* sc, int nrays, unsigned seed, int brute_rays, double out[8]) {
+    if (!sc || !out || nrays < 1 || brute_rays < 0) PTD_FAIL(PTD_ERR_ARG, "ptd_bvh_probe: bad argument");
+    const std::vector<ptd_face>& faces = sc->faces;
+    const int nf = (int)faces.size();
+    if (nf == 0) PTD_FAIL(PTD_ERR_STATE, "ptd_bvh_probe: the scene has no mesh");
+    PtdBvh bvh;
+    ptd_build_bvh(faces, bvh);
+    ProbeRng rng{seed * 2654435761u + 12345u};
+    long long visits = 0, tests = 0, hits = 0; int max_sp = 0, mismatches = 0;
+    std::vector<int> stack(3 * bvh.max_depth4 + 8);
+    for (int r = 0; r < nrays; ++r) {
+        // a diffuse-bounce-like ray: starts just off a random face, uniform direction in the hemisphere of its geometric normal
+        const ptd_face& f = faces[std::min(nf - 1, (int)(rng.next() * nf))];
+        float u = rng.next(), v = rng.next();
+        if (u + v > 1.f) { u = 1.f - u; v = 1.f - v; }
+        ptd_vec3 pnt = add3(f.v[0], add3(muls3(sub3(f.v[1], f.v[0]), u), muls3(sub3(f.v[2], f.v[0]), v)));
+        ptd_vec3 n = cross3(sub3(f.v[1], f.v[0]), sub3(f.v[2], f.v[0]));
+        if (!(len3(n) > 0.f)) { --r; if (rng.next() < 1e-6f) break; continue; }
+        n = norm3(n);
+        ptd_vec3 d;
+        do { d = v3(2.f * rng.next() - 1.f, 2.f * rng.next() - 1.f, 2.f * rng.next() - 1.f); } while (dot3(d, d) > 1.f || dot3(d, d) < 1e-4f);
+        d = norm3(d);
+        if (dot3(d, n) < 0.f) d = v3(-d.x, -d.y, -d.z);
+        const float o[3] = {pnt.x + 0.01f * d.x, pnt.y + 0.01f * d.y, pnt.z + 0.01f * d.z}, dd[3] = {d.x, d.y, d.z};
+        // ---- BVH4 traversal, same order and culling rules as pt_trace ----
+        float t_min = FLT_MAX; int best = -1;
+        const float ooeps = 1e-30f;
+        float id[3], ood[3]; int nearp[3];
+        for (int a = 0; a < 3; ++a) { id[a] = 1.0f / (fabsf(dd[a]) > ooeps ? dd[a] : copysignf(ooeps, dd[a])); ood[a] = o[a] * id[a]; nearp[a] = id[a] < 0.f; }
+        int sp = 0, node = 0;
+        const int SENT = 0x76543210;
+        stack[0] = SENT;
+        while (node != SENT) {
+            if (node >= 0) {
+                ++visits;
+                const float* w = bvh.wide4[node].f;
+                float dist[4]; int code[4];
+                const float tlim = t_min * 1.00001f;
+                for (int k = 0; k < 4; ++k) {
+                    const float nx = w[(nearp[0] ? 4 : 0) + k], fx = w[(nearp[0] ? 0 : 4) + k], ny = w[8 + (nearp[1] ? 4 : 0) + k], fy = w[8 + (nearp[1] ? 0 : 4) + k];
+                    const float nz = w[16 + (nearp[2] ? 4 : 0) + k], fz = w[16 + (nearp[2] ? 0 : 4) + k];
+                    const float tn = std::max(std::max(nx * id[0] - ood[0], ny * id[1] - ood[1]), std::max(nz * id[2] - ood[2], 0.0f));
+                    const float tf = std::min(std::min(fx * id[0] - ood[0], fy * id[1] - ood[1]), fz * id[2] - ood[2]);
+                    dist[k] = (tn <= tf && tn <= tlim) ? tn : FLT_MAX;
+                    memcpy(&code[k], &w[24 + k], 4);
+                }
+                for (int i = 1; i < 4; ++i)                       // insertion sort, ascending entry distance
+                    for (int j = i; j > 0 && dist[j] < dist[j - 1]; --j) { std::swap(dist[j], dist[j - 1]); std::swap(code[j], code[j - 1]); }
+                for (int k = 3; k >= 1; --k) if (dist[k] < FLT_MAX) stack[++sp] = code[k];
+                max_sp = std::max(max_sp, sp);
+                node = dist[0] < FLT_MAX ? code[0] : stack[sp--];
+            } else {
+                const int c = ~node, first = c >> 4, cnt = (c & 15) + 1;
+                for (int k = first; k < first + cnt; ++k) {
+                    ++tests;
+                    const PtdBvhTri& t = bvh.tris[k];
+                    probe_consider(probe_tri(t.v0, t.v1, t.v2, o, dd), t.face, t_min, best);
+                }
+                node = stack[sp--];
+            }
+        }
+        if (best >= 0) ++hits;
+        if (r < brute_rays) {
+            float bt = FLT_MAX; int bb = -1;
+            for (int k = 0; k < nf; ++k) probe_consider(probe_tri(&faces[k].v[0].x, &faces[k].v[1].x, &faces[k].v[2].x, o, dd), k, bt, bb);
+            if (bb != best || (bb >= 0 && bt != t_min)) ++mismatches;
+        }
+    }
+    long long used = 0;
+    for (const PtdBvh4& w : bvh.wide4) for (int k = 0; k < 4; ++k) if (w.f[k] <= w.f[4 + k]) ++used;
+    out[0] = mismatches; out[1] = (double)visits / nrays; out[2] = (double)tests / nrays; out[3] = max_sp; out[4] = (double)bvh.wide4.size();
+    out[5] = bvh.leaves; out[6] = bvh.wide4.empty() ? 0.0 : (double)used / bvh.wide4.size(); out[7] = (double)hits / nrays;
+    return PTD_OK;
 }
 
 void ptd_geom_bounds(const std::vector<ptd_geom>& geoms, std::vector<ptd_aabb>& out) {

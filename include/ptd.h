@@ -122,6 +122,12 @@ ptd_status ptd_pt_dump_intersections(ptd_pt*, int bounce, ptd_intersection* host
 ptd_status ptd_pt_dump_final_paths(ptd_pt*, ptd_path_segment* host, int capacity);    /* needs PTD_PT_KEEP_TERMINATED */
 ptd_status ptd_pt_dump_image(ptd_pt*, float* host_rgb /* [P][3] */);
 ptd_status ptd_pt_bvh_stats(const ptd_pt*, int* nodes, int* leaves, int* max_leaf, int* max_depth);
+/* Host-side probe of the BVH ptd_pt_create would build for the scene's mesh (no GPU needed): `nrays` seeded diffuse-bounce-like rays
+ * walk the 4-wide layout with pt_trace's traversal rules; the first `brute_rays` of them are checked against the loop over every
+ * face (pathtrace.cu:258-269).  out[0] = rays whose (face, t) differ (must be 0), out[1] = interior-node visits per ray,
+ * out[2] = triangle tests per ray, out[3] = deepest stack, out[4] = 4-wide nodes, out[5] = leaves, out[6] = mean used children per
+ * node, out[7] = fraction of rays that hit. */
+ptd_status ptd_bvh_probe(const ptd_scene*, int nrays, unsigned seed, int brute_rays, double out[8]);
 
 /* ---- HP-2 recurrent denoising autoencoder (replaces network_prediction_faster_version) ----------- */
 enum {

@@ -179,3 +179,39 @@ def test_cli_usage_and_no_device_message():
     if capi.device_count() == 0:
         r = subprocess.run([exe, os.path.join(SCENES, "cornell_64x48.txt")], capture_output=True, text=True)
         assert r.returncode == 2 and "no CPU fallback" in r.stderr
+
+
+def _bvh_probe(scene, nrays, brute):
+    out = (C.c_double * 8)()
+    capi.check(capi.lib().ptd_bvh_probe(scene.h, nrays, 11, brute, out), "ptd_bvh_probe")
+    return list(out)
+
+
+@pytest.mark.parametrize("knobs", [{}, {"PTD_BVH_MAX_LEAF": "2"}, {"PTD_BVH_MAX_LEAF": "8", "PTD_BVH_SWEEP": "64"}, {"PTD_BVH_LEAF_COST": "0.6"}],
+                         ids=["default", "maxleaf2", "maxleaf8-sweep", "sah-leaves"])
+def test_bvh_traversal_equals_brute_force_on_the_host(knobs, monkeypatch, tmp_path):
+    """The BVH pt_trace walks is new work (the reference loops over every face, pathtrace.cu:258-269): on the host, the same 4-wide
+    layout and traversal rules must return exactly the brute-force (face, t) for every probe ray - on the shipped hall mesh and on a
+    generated sponza-like mesh (thin columns, arches, large floor quads), for the default build and for the tuning knobs."""
+    from ai_path_tracer_denoiser_b200 import scenegen
+    for k in ("PTD_BVH_MAX_LEAF", "PTD_BVH_SWEEP", "PTD_BVH_LEAF_COST"):
+        monkeypatch.delenv(k, raising=False)
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    small = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
+    r = _bvh_probe(small, 4000, 4000)
+    assert r[0] == 0 and r[7] > 0.5, r
+    obj = str(tmp_path / "sponza_like.obj")
+    scenegen.write_obj(obj, "sponza", 12000)
+    big = capi.Scene(path=scenegen.write_mesh_scene(str(tmp_path / "s.txt"), obj, 64, 48, kind="sponza", material="diffuse"))
+    r = _bvh_probe(big, 6000, 6000)
+    assert r[0] == 0 and r[7] > 0.5, r
+    assert r[3] + 2 <= 96                                              # traversal stack of pt_trace (PT_STACK)
+    assert 1.0 < r[1] < 60 and r[2] < 60, r                              # a sane tree: tens of node visits / triangle tests per ray, not thousands
+
+
+def test_bvh_probe_argument_errors():
+    out = (C.c_double * 8)()
+    cornell = capi.Scene(path=os.path.join(SCENES, "cornell_64x48.txt"))     # no mesh
+    assert capi.lib().ptd_bvh_probe(cornell.h, 10, 1, 0, out) == capi.ERR_STATE if hasattr(capi, "ERR_STATE") else capi.lib().ptd_bvh_probe(cornell.h, 10, 1, 0, out) < 0
+    assert capi.lib().ptd_bvh_probe(None, 10, 1, 0, out) < 0
