@@ -36,7 +36,7 @@ ptd_dn_forward_host ptd_dn_create_strip ptd_dn_padded_size ptd_dn_dump_hidden pt
 ptd_pt_launches_last_render ptd_dn_profile ptd_dn_launch_times ptd_dn_launch_name ptd_pt_profile
 ptd_pt_launch_times ptd_dn_strip_partition ptd_dn_strip_info_size ptd_dn_strip_export ptd_dn_strip_connect
 ptd_dn_forward_group ptd_pt_create_strip ptd_pt_strip_info_size ptd_pt_strip_export ptd_pt_strip_connect
-ptd_pt_render_group ptd_frame_host ptd_bvh_probe""".split()
+ptd_pt_render_group ptd_frame_host ptd_bvh_probe ptd_bvh_probe_order""".split()
 
 
 class PtdError(RuntimeError):
@@ -78,6 +78,7 @@ def lib():
         L.ptd_pt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_pt_render_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ptd_frame_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ptd_bvh_probe_order.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_double)]
         L.ptd_bvh_probe.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_double)]
         L.ptd_pt_export_rgba8.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_pt_live_counts.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]

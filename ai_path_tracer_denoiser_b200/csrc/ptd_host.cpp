@@ -868,6 +868,8 @@ inline void probe_consider(float t, int face, float& t_min, int& best) {     // 
 // out[0] rays whose BVH hit (face, t) differs from brute force (must be 0)   out[1] interior-node visits per ray
 // out[2] triangle tests per ray   out[3] deepest traversal stack   out[4] 4-wide nodes   out[5] leaves
 // out[6] mean used children per 4-wide node   out[7] rays that hit something (fraction)
+namespace { struct ProbeTrace { std::vector<std::vector<int>> nodes, lines; std::vector<unsigned> bin; int bits = 0; ptd_aabb box; }; static thread_local ProbeTrace* g_probe_trace = nullptr; }
+
 extern "C" ptd_status ptd_bvh_probe(const ptd_scene* sc, int nrays, unsigned seed, int brute_rays, double out[8]) {
     if (!sc || !out || nrays < 1 || brute_rays < 0) PTD_FAIL(PTD_ERR_ARG, "ptd_bvh_probe: bad argument");
     const std::vector<ptd_face>& faces = sc->faces;
@@ -900,9 +902,20 @@ extern "C" ptd_status ptd_bvh_probe(const ptd_scene* sc, int nrays, unsigned see
         int sp = 0, node = 0;
         const int SENT = 0x76543210;
         stack[0] = SENT;
+        if (g_probe_trace) {                                          // ptd_bvh_probe_order: this ray's bin (same key as ray_bin in ptd_pt.cu)
+            ProbeTrace& T = *g_probe_trace;
+            T.nodes.emplace_back(); T.lines.emplace_back();
+            const int mx = (1 << T.bits) - 1; unsigned c[3];
+            const float lo[3] = {T.box.lb.x, T.box.lb.y, T.box.lb.z}, hi[3] = {T.box.ub.x, T.box.ub.y, T.box.ub.z};
+            for (int a = 0; a < 3; ++a) c[a] = (unsigned)std::min(std::max((int)((o[a] - lo[a]) / std::max(hi[a] - lo[a], 1e-20f) * (float)(1 << T.bits)), 0), mx);
+            unsigned morton = 0;
+            for (int b = 0; b < T.bits; ++b) morton |= (((c[0] >> b) & 1u) << (3 * b)) | (((c[1] >> b) & 1u) << (3 * b + 1)) | (((c[2] >> b) & 1u) << (3 * b + 2));
+            T.bin.push_back((morton << 3) | (dd[0] < 0.f ? 1u : 0u) | (dd[1] < 0.f ? 2u : 0u) | (dd[2] < 0.f ? 4u : 0u));
+        }
         while (node != SENT) {
             if (node >= 0) {
                 ++visits;
+                if (g_probe_trace) g_probe_trace->nodes.back().push_back(node);
                 const float* w = bvh.wide4[node].f;
                 float dist[4]; int code[4];
                 const float tlim = t_min * 1.00001f;
@@ -923,6 +936,7 @@ extern "C" ptd_status ptd_bvh_probe(const ptd_scene* sc, int nrays, unsigned see
                 const int c = ~node, first = c >> 4, cnt = (c & 15) + 1;
                 for (int k = first; k < first + cnt; ++k) {
                     ++tests;
+                    if (g_probe_trace) g_probe_trace->lines.back().push_back(k * 48 / 128);
                     const PtdBvhTri& t = bvh.tris[k];
                     probe_consider(probe_tri(t.v0, t.v1, t.v2, o, dd), t.face, t_min, best);
                 }
@@ -940,6 +954,52 @@ extern "C" ptd_status ptd_bvh_probe(const ptd_scene* sc, int nrays, unsigned see
     for (const PtdBvh4& w : bvh.wide4) for (int k = 0; k < 4; ++k) if (w.f[k] <= w.f[4 + k]) ++used;
     out[0] = mismatches; out[1] = (double)visits / nrays; out[2] = (double)tests / nrays; out[3] = max_sp; out[4] = (double)bvh.wide4.size();
     out[5] = bvh.leaves; out[6] = bvh.wide4.empty() ? 0.0 : (double)used / bvh.wide4.size(); out[7] = (double)hits / nrays;
+    return PTD_OK;
+}
+
+// What PTD_PT_RAY_SORT can buy, estimated on the host: the probe's rays (fully incoherent, like the later bounces) are grouped into
+// warps of 32 in arrival order and in (origin cell, direction octant) bin order; lanes step through their node / triangle sequences
+// together, and every step costs one L1 wavefront per DISTINCT 128-byte line the active lanes touch (7 loads per node, 3 per
+// triangle - the model the ncu capture of pt_trace fits: 115 wavefronts per ray measured).
+// out[0], out[1] = wavefronts per ray in arrival / bin order; out[2], out[3] = warp steps per ray (node + triangle trips, i.e.
+// issue slots) in arrival / bin order; out[4] = bins in use; out[5] = rays.
+extern "C" ptd_status ptd_bvh_probe_order(const ptd_scene* sc, int nrays, unsigned seed, int cell_bits, double out[8]) {
+    if (!sc || !out || nrays < 32 || cell_bits < 1 || cell_bits > 5) PTD_FAIL(PTD_ERR_ARG, "ptd_bvh_probe_order: bad argument");
+    ProbeTrace T;
+    T.bits = cell_bits; T.box = sc->mesh_box;
+    g_probe_trace = &T;
+    double tmp[8];
+    ptd_status rc = ptd_bvh_probe(sc, nrays, seed, 0, tmp);
+    g_probe_trace = nullptr;
+    if (rc != PTD_OK) return rc;
+    const int n = (int)T.nodes.size();
+    std::vector<int> order(n);
+    for (int i = 0; i < n; ++i) order[i] = i;
+    auto evaluate = [&](double& wavefronts, double& steps) {
+        wavefronts = steps = 0;
+        std::vector<int> seen;
+        for (int w0 = 0; w0 + 32 <= n; w0 += 32) {
+            for (int pass = 0; pass < 2; ++pass) {                     // node sequences, then triangle-line sequences
+                size_t longest = 0;
+                for (int l = 0; l < 32; ++l) longest = std::max(longest, (pass ? T.lines : T.nodes)[order[w0 + l]].size());
+                steps += (double)longest;
+                for (size_t k = 0; k < longest; ++k) {
+                    seen.clear();
+                    for (int l = 0; l < 32; ++l) { const std::vector<int>& q = (pass ? T.lines : T.nodes)[order[w0 + l]]; if (k < q.size()) seen.push_back(q[k]); }
+                    std::sort(seen.begin(), seen.end());
+                    wavefronts += (double)(std::unique(seen.begin(), seen.end()) - seen.begin()) * (pass ? 3 : 7);
+                }
+            }
+        }
+        const double rays = (double)(n / 32 * 32);
+        wavefronts /= rays; steps /= rays;
+    };
+    evaluate(out[0], out[2]);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return T.bin[a] < T.bin[b]; });
+    evaluate(out[1], out[3]);
+    std::vector<unsigned> bins(T.bin);
+    std::sort(bins.begin(), bins.end());
+    out[4] = (double)(std::unique(bins.begin(), bins.end()) - bins.begin()); out[5] = n; out[6] = out[7] = 0;
     return PTD_OK;
 }
 

@@ -128,6 +128,10 @@ ptd_status ptd_pt_bvh_stats(const ptd_pt*, int* nodes, int* leaves, int* max_lea
  * out[2] = triangle tests per ray, out[3] = deepest stack, out[4] = 4-wide nodes, out[5] = leaves, out[6] = mean used children per
  * node, out[7] = fraction of rays that hit. */
 ptd_status ptd_bvh_probe(const ptd_scene*, int nrays, unsigned seed, int brute_rays, double out[8]);
+/* Host-side estimate of what PTD_PT_RAY_SORT buys: the probe's rays grouped into warps of 32 in arrival order and in bin order
+ * (cell_bits per axis + direction octant); out[0], out[1] = L1 wavefronts per ray (one per distinct 128-byte line per load) in
+ * arrival / bin order, out[2], out[3] = warp steps per ray, out[4] = bins in use, out[5] = rays. */
+ptd_status ptd_bvh_probe_order(const ptd_scene*, int nrays, unsigned seed, int cell_bits, double out[8]);
 
 /* ---- HP-2 recurrent denoising autoencoder (replaces network_prediction_faster_version) ----------- */
 enum {

@@ -215,3 +215,18 @@ def test_bvh_probe_argument_errors():
     cornell = capi.Scene(path=os.path.join(SCENES, "cornell_64x48.txt"))     # no mesh
     assert capi.lib().ptd_bvh_probe(cornell.h, 10, 1, 0, out) == capi.ERR_STATE if hasattr(capi, "ERR_STATE") else capi.lib().ptd_bvh_probe(cornell.h, 10, 1, 0, out) < 0
     assert capi.lib().ptd_bvh_probe(None, 10, 1, 0, out) < 0
+
+
+def test_ray_binning_estimate_on_the_host(tmp_path):
+    """ptd_bvh_probe_order: grouping incoherent rays by (origin cell, direction octant) - what PTD_PT_RAY_SORT does on the device -
+    must not cost more L1 wavefronts or warp steps per ray than arrival order, and on a mesh of some size it must save some."""
+    from ai_path_tracer_denoiser_b200 import scenegen
+    obj = str(tmp_path / "sponza_like.obj")
+    scenegen.write_obj(obj, "sponza", 20000)
+    sc = capi.Scene(path=scenegen.write_mesh_scene(str(tmp_path / "s.txt"), obj, 64, 48, kind="sponza", material="diffuse"))
+    out = (C.c_double * 8)()
+    capi.check(capi.lib().ptd_bvh_probe_order(sc.h, 64000, 3, 3, out), "ptd_bvh_probe_order")
+    arrival_wf, binned_wf, arrival_steps, binned_steps, bins, rays = list(out)[:6]
+    assert rays >= 63000 and 8 < bins <= 8 * 8 ** 3
+    assert binned_wf < 0.9 * arrival_wf and binned_steps <= arrival_steps * 1.02, list(out)
+    assert capi.lib().ptd_bvh_probe_order(sc.h, 64000, 3, 9, out) < 0          # cell bits out of range
