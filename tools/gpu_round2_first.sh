@@ -1,0 +1,42 @@
+#!/usr/bin/env bash
+# First GPU-box visit of round 2: validates, then times, the opt-ins written after round 1's GPU budget was spent.
+# Every step runs under its own `timeout`; every device-side wait traps after 20 s, so nothing here can hang the box.
+#   usage: gpurun --timeout 1500 -- 'bash tools/gpu_round2_first.sh r03a'           (1 GPU)
+#          gpurun --gpus 4 --timeout 900 -- 'bash tools/gpu_round2_first.sh r03b strips 4'
+set -uo pipefail
+TAG=${1:-r03a}; WHAT=${2:-single}; N=${3:-4}
+OUT=gpurun_out/$TAG
+mkdir -p "$OUT"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$OUT/gpu.csv" 2>&1
+B="--steps 100 --warmup 5 --no-cpu-baseline"
+if [ "$WHAT" = single ]; then
+  timeout 1200 python -m pytest tests -m gpu -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -4 "$OUT/pytest_gpu.log"
+  timeout 400 python bench.py $B > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"; echo "default rc=$?"
+  for cfg in "4 22" "4 8" "5 22" "3 22"; do
+    set -- $cfg
+    PTD_PT_RAY_SORT=1 PTD_PT_RAY_SORT_BITS=$1 PTD_PT_RAY_SORT_REFILL=$2 timeout 400 python bench.py $B > "$OUT/bench_raysort_b$1_r$2.json" 2> "$OUT/bench_raysort_b$1_r$2.err"; echo "raysort bits=$1 refill=$2 rc=$?"
+  done
+  PTD_PT_RAY_SORT=1 timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_raysort_serial.json" 2> "$OUT/bench_raysort_serial.err"
+  timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_default_serial.json" 2> "$OUT/bench_default_serial.err"
+  timeout 400 python bench.py $B --e2e fused > "$OUT/bench_e2e_fused.json" 2> "$OUT/bench_e2e_fused.err"; echo "fused rc=$?"
+  python - "$OUT" <<'PY'
+import glob, json, os, sys
+for p in sorted(glob.glob(os.path.join(sys.argv[1], "bench_*.json"))):
+    try:
+        d = json.loads(open(p).read().strip().splitlines()[-1])
+        print("%-34s %7.1f fps  e2e %7.1f  trace/bounce %s" % (os.path.basename(p), d["value"], d["e2e"]["value"], d["roofline"]["per_bounce_ms"]["pt_trace"]))
+    except Exception as e:
+        print(os.path.basename(p), "unreadable:", e)
+PY
+else
+  TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
+  timeout 300 $TR tools/check_strips_multi.py > "$OUT/check_n$N.log" 2>&1; echo "strip parity rc=$?"; tail -$N "$OUT/check_n$N.log"
+  timeout 300 $TR bench.py --gpus $N $B > "$OUT/bench_n${N}_serial.json" 2> "$OUT/bench_n${N}_serial.err"; echo "serial rc=$?"
+  for rep in 1 2 3; do
+    PTD_STRIP_PIPELINE=1 timeout 300 $TR bench.py --gpus $N $B > "$OUT/bench_n${N}_pipelined_$rep.json" 2> "$OUT/bench_n${N}_pipelined_$rep.err"; echo "pipelined run $rep rc=$?"
+  done
+  PTD_DN_REPL_LEVEL=3 timeout 300 $TR bench.py --gpus $N $B > "$OUT/bench_n${N}_serial_repl.json" 2> "$OUT/bench_n${N}_serial_repl.err"; echo "replicated rc=$?"
+  PTD_DN_REPL_LEVEL=3 PTD_STRIP_PIPELINE=1 timeout 300 $TR bench.py --gpus $N $B > "$OUT/bench_n${N}_pipelined_repl.json" 2> "$OUT/bench_n${N}_pipelined_repl.err"; echo "pipelined+replicated rc=$?"
+  grep -ho '"value": [0-9.]*' "$OUT"/bench_n${N}_*.json | head -20
+fi
+ls -la "$OUT"
