@@ -66,3 +66,24 @@ def test_checkpoint_export_round_trip(tmp_path):
     r = subprocess.run([sys.executable, os.path.join(root, "tools", "export_weights.py"), str(tmp_path / "bad.pt"), str(tmp_path / "x.ptdw")],
                        capture_output=True, text=True)
     assert r.returncode == 2 and "lacks" in r.stdout
+
+
+def test_algorithmic_work_figures_of_the_bench():
+    """bench.py's roofline uses SURVEY.md section 8d's algorithmic work: 2*9*Cin*Cout FLOP and 4*(Cin+Cout) bytes per output pixel with
+    UNPADDED channel counts - 148 474 FLOP and 1 808 B per padded full-resolution pixel, 139.87 GFLOP / 1 703 MB at 736x1280."""
+    import importlib.util
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    spec = importlib.util.spec_from_file_location("ptd_bench", os.path.join(root, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    t = bench.layer_table(736, 1280)
+    assert len(t) == 28
+    flops, nbytes = sum(f for f, _ in t.values()), sum(b for _, b in t.values())
+    # bytes: the formula the survey states gives 1 697.05 MB; its per-layer table sums to 1 703.1 MB because the rows below 1/4
+    # resolution carry a little more than (Cin + Cout) * 4 B per pixel - 0.35 % apart, the bench uses the formula
+    assert abs(flops / 1e9 - 139.87) < 0.01 and abs(nbytes / 1e6 - 1697.05) < 0.01 and abs(nbytes / 1e6 / 1703.1 - 1) < 0.005
+    px = 736 * 1280
+    assert round(flops / px) == 148474 and abs(nbytes / px - 1808) < 8
+    assert abs(t["enc1.l2a"][0] / 1e9 - 34.73) < 0.01 and abs(t["dec1.c1"][1] / 1e6 - 252.5) < 0.1      # rows of the section 8a table
+    peaks = bench.measured_peaks()
+    assert peaks["hbm"] > 1000 and peaks["bf16"] > 100
