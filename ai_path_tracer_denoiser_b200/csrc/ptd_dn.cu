@@ -53,6 +53,9 @@ struct FpConvArgs {
     DnTensor out;
 };
 
+// RAW = 1 (PTD_DN_FP32_BATCH_STATS): store the value BatchNorm will see - acc + bias (order 2) or lrelu(acc + bias) (order 3) - and leave
+// the normalisation to bn_batch_stats / bn_batch_apply, which need the whole layer's output first.
+template <int RAW>
 __global__ void __launch_bounds__(128) conv3x3_fp32(const FpConvArgs a) {
     __shared__ float s_in[FC_CK * FC_PS];
     __shared__ __align__(16) float s_w[9 * FC_CK * FC_BN];
@@ -128,7 +131,8 @@ __global__ void __launch_bounds__(128) conv3x3_fp32(const FpConvArgs a) {
         float o[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            if (a.order == 0) { float v = fmaf(acc[i][j], sc[j], sh[j]); o[j] = v > 0.f ? v : 0.1f * v; }
+            if (RAW) { float v = acc[i][j] + bi[j]; o[j] = (a.order == 3 && !(v > 0.f)) ? 0.1f * v : v; }
+            else if (a.order == 0) { float v = fmaf(acc[i][j], sc[j], sh[j]); o[j] = v > 0.f ? v : 0.1f * v; }
             else { float v = acc[i][j] + bi[j]; v = v > 0.f ? v : 0.1f * v; o[j] = fmaf(v, sc[j], sh[j]); }
         }
         float* dst = a.out.base + (size_t)(co / 4) * a.out.quad_stride() + ((size_t)(gy + 1) * a.out.W + gx) * 4;
@@ -149,6 +153,59 @@ __global__ void maxpool2_chw4(const DnTensor in, const DnTensor out) {
     *o = make_float4(fmaxf(fmaxf(a.x, b.x), fmaxf(d.x, e.x)), fmaxf(fmaxf(a.y, b.y), fmaxf(d.y, e.y)),
                      fmaxf(fmaxf(a.z, b.z), fmaxf(d.z, e.z)), fmaxf(fmaxf(a.w, b.w), fmaxf(d.w, e.w)));
 }
+// ---- PTD_DN_FP32_BATCH_STATS: BatchNorm with the statistics of the CURRENT activations (what the reference's TorchScript export
+// actually runs: convert_to_torchscript.py:26-30 traces the model without .eval(), so nn.BatchNorm2d normalises with the batch
+// mean and the biased batch variance of its input, N = 1 -> over the H x W pixels of the padded frame) ----
+// stats[2 * c] = sum, stats[2 * c + 1] = sum of squares of channel c over the image rows (aprons excluded), in double
+__global__ void __launch_bounds__(256) bn_batch_stats(const DnTensor t, double* __restrict__ stats) {
+    __shared__ double s_red[8][8];
+    const int q = blockIdx.y;
+    const float4* plane = reinterpret_cast<const float4*>(t.base + (size_t)q * t.quad_stride()) + t.W;      // first image row
+    const size_t n = (size_t)t.rows * t.W;
+    double s[4] = {0, 0, 0, 0}, ss[4] = {0, 0, 0, 0};
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const float4 v = plane[i];
+        s[0] += v.x; s[1] += v.y; s[2] += v.z; s[3] += v.w;
+        ss[0] += (double)v.x * v.x; ss[1] += (double)v.y * v.y; ss[2] += (double)v.z * v.z; ss[3] += (double)v.w * v.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { s[k] += __shfl_xor_sync(0xffffffffu, s[k], o); ss[k] += __shfl_xor_sync(0xffffffffu, ss[k], o); }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { for (int k = 0; k < 4; ++k) { s_red[warp][k] = s[k]; s_red[warp][4 + k] = ss[k]; } }
+    __syncthreads();
+    if (threadIdx.x < 8) {
+        double v = 0;
+        for (int w = 0; w < 8; ++w) v += s_red[w][threadIdx.x];
+        const int c = q * 4 + (threadIdx.x & 3);
+        atomicAdd(&stats[2 * c + (threadIdx.x >> 2)], v);
+    }
+}
+// in place: y = (x - mean) / sqrt(var + eps) * gamma + beta, then LeakyReLU when the layer is conv -> BN -> LReLU (model.py:24-26);
+// the conv -> LReLU -> BN layer (model.py:30-32) got its LeakyReLU in the conv epilogue.  Pad channels have gamma = beta = 0.
+__global__ void __launch_bounds__(256) bn_batch_apply(const DnTensor t, const double* __restrict__ stats, const float* __restrict__ gamma,
+                                                      const float* __restrict__ beta, int lrelu_after) {
+    const int q = blockIdx.y;
+    float4* plane = reinterpret_cast<float4*>(t.base + (size_t)q * t.quad_stride()) + t.W;
+    const size_t n = (size_t)t.rows * t.W;
+    float mul[4], add[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const int c = q * 4 + k;
+        const double mean = stats[2 * c] / (double)n, var = fmax(stats[2 * c + 1] / (double)n - mean * mean, 0.0);
+        const float invstd = (float)(1.0 / sqrt(var + 1e-5));
+        mul[k] = invstd * gamma[c];
+        add[k] = beta[c] - (float)mean * mul[k];
+    }
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        float4 v = plane[i];
+        v.x = fmaf(v.x, mul[0], add[0]); v.y = fmaf(v.y, mul[1], add[1]); v.z = fmaf(v.z, mul[2], add[2]); v.w = fmaf(v.w, mul[3], add[3]);
+        if (lrelu_after) { v.x = v.x > 0.f ? v.x : 0.1f * v.x; v.y = v.y > 0.f ? v.y : 0.1f * v.y; v.z = v.z > 0.f ? v.z : 0.1f * v.z; v.w = v.w > 0.f ? v.w : 0.1f * v.w; }
+        plane[i] = v;
+    }
+}
+
 // planar G-buffer [10][H][W] -> CHW4 with 16 channels (4 quads): the strip's rows (frame rows row0 .. row0 + rows - 1), zero in the
 // bottom / right padding (decision D3); thread = pixel.  Apron rows: zero at the frame border; where a neighbour strip exists
 // it pushes its boundary row into OUR apron (and we push ours into its), then the last block raises the neighbours' flags -
@@ -275,6 +332,7 @@ struct DnLayer {
     int src0, src1, out, pool;      // tensor ids (-1 = none); hidden-state ids are resolved per parity
     float* d_w9 = nullptr;          // [9][cin_p][coutp]  (CUDA-core engine)
     float* d_scale = nullptr; float* d_shift = nullptr; float* d_bias = nullptr;
+    float* d_gamma = nullptr; float* d_beta = nullptr;       // PTD_DN_FP32_BATCH_STATS: the BatchNorm affine parameters, unfolded
     TcConvPlan tc[2];               // tensor-core engine plans, one per hidden-state parity
     uint32_t* d_done = nullptr;
 };
@@ -293,6 +351,7 @@ struct ptd_dn {
     int t_in16 = -1, t_hidden[6][2], t_final = -1;
     int hidden_c[6] = {0};
     float* d_gbuf = nullptr; float* d_rgb = nullptr;   // staging for the host-pointer entry point
+    double* d_bn_stats = nullptr;                      // PTD_DN_FP32_BATCH_STATS: [2 * 128] per-channel sum / sum of squares of the layer in flight
     struct Pool { int in[2], out; };
     std::vector<Pool> pools;        // pools[k] follows layer 3k+2 (CUDA-core engine only; the TC engine pools in its epilogue)
     // the other strips of the frame, by rank (top strip = 0); up = rank - 1, down = rank + 1
@@ -328,16 +387,17 @@ extern "C" void ptd_dn_destroy(ptd_dn* h) {
 }
 
 static inline int cpad(int c) { return (c + 15) & ~15; }
+static inline bool dn_cuda_core_engine(unsigned flags) { return flags == PTD_DN_FP32 || flags == PTD_DN_FP32_BATCH_STATS; }
 
 static ptd_status dn_create(const char* weights_path, int H, int W, int row0, int rows, bool strip, int device, unsigned flags, ptd_dn** out) {
     if (!weights_path || !out || H <= 0 || W <= 0) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: bad argument");
     *out = nullptr;
     if (ptd_device_count() <= device || device < 0) PTD_FAIL(PTD_ERR_CUDA, "ptd_dn_create: CUDA device %d not available (no CPU fallback exists)", device);
-    if (flags != PTD_DN_FP32 && flags != PTD_DN_TF32 && flags != PTD_DN_F16 && flags != PTD_DN_3XTF32) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: unknown flags %u", flags);
+    if (flags != PTD_DN_FP32 && flags != PTD_DN_TF32 && flags != PTD_DN_F16 && flags != PTD_DN_3XTF32 && flags != PTD_DN_FP32_BATCH_STATS) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: unknown flags %u", flags);
     const int Hp = (H + 31) / 32 * 32, Wp = (W + 31) / 32 * 32;
     if (!strip) { row0 = 0; rows = Hp; }
     if (row0 < 0 || rows <= 0 || row0 % 32 || rows % 32 || row0 + rows > Hp) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create_strip: rows [%d, %d) must be multiples of 32 inside the padded frame of %d rows", row0, row0 + rows, Hp);
-    if (strip && flags == PTD_DN_FP32) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_dn_create_strip: row strips need a tensor-core engine (PTD_DN_TF32 / PTD_DN_F16)");
+    if (strip && dn_cuda_core_engine(flags)) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_dn_create_strip: row strips need a tensor-core engine (PTD_DN_TF32 / PTD_DN_F16)");
     std::map<std::string, std::vector<float>> sd;
     ptd_status rc = read_ptdw(weights_path, sd);
     if (rc != PTD_OK) return rc;
@@ -357,6 +417,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     DALLOC(h->d_gbuf, (size_t)10 * H * W);
     DALLOC(h->d_rgb, (size_t)3 * H * W);
     { float* dd = nullptr; DALLOC(dd, 64); h->d_pack_done = (uint32_t*)dd; }
+    if (flags == PTD_DN_FP32_BATCH_STATS) { float* dd = nullptr; DALLOC(dd, 2 * 128 * 2); h->d_bn_stats = (double*)dd; }
 
     // ---- activation arena: every tensor the convs read or write, one allocation (one IPC handle per strip) ----
     size_t arena_bytes = 0;
@@ -451,7 +512,14 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
         cudaMemcpy(L.d_scale, scale.data(), coutp * 4, cudaMemcpyHostToDevice);
         cudaMemcpy(L.d_shift, shift.data(), coutp * 4, cudaMemcpyHostToDevice);
         cudaMemcpy(L.d_bias, bias.data(), coutp * 4, cudaMemcpyHostToDevice);
-        if (flags != PTD_DN_FP32) {
+        if (flags == PTD_DN_FP32_BATCH_STATS) {
+            std::vector<float> gam(coutp, 0.f), bet(coutp, 0.f);
+            for (int co = 0; co < s.cout; ++co) { gam[co] = (*g)[co]; bet[co] = (*be)[co]; }
+            DALLOC(L.d_gamma, coutp); DALLOC(L.d_beta, coutp);
+            cudaMemcpy(L.d_gamma, gam.data(), coutp * 4, cudaMemcpyHostToDevice);
+            cudaMemcpy(L.d_beta, bet.data(), coutp * 4, cudaMemcpyHostToDevice);
+        }
+        if (!dn_cuda_core_engine(flags)) {
             float* dd = nullptr;
             DALLOC(dd, 64);
             L.d_done = (uint32_t*)dd;
@@ -590,7 +658,8 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
         if (name) h->launch_names.push_back(name);
     };
     const bool tf32 = h->flags == PTD_DN_TF32;               // fp32 storage, operands rounded to tf32 at the producer
-    const bool tensor = h->flags != PTD_DN_FP32;
+    const bool tensor = !dn_cuda_core_engine(h->flags);
+    const bool batch_stats = h->flags == PTD_DN_FP32_BATCH_STATS;
     if (first <= -1) {                                                  // stage -1: start of the frame
         h->epoch += 1;
         h->launches = 0;
@@ -677,8 +746,19 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
             a.H = L.H; a.W = L.W; a.w = L.d_w9; a.scale = L.d_scale; a.shift = L.d_shift; a.bias = L.d_bias;
             a.order = L.spec.lrelu_first ? 1 : 0; a.out = h->tensors[o];
             dim3 grid((L.W + FC_TW - 1) / FC_TW, (L.H + FC_TH - 1) / FC_TH, (a.out.cp + FC_BN - 1) / FC_BN);
-            conv3x3_fp32<<<grid, 128, 0, st>>>(a);
-            ++h->launches;
+            if (batch_stats) {
+                a.order = L.spec.lrelu_first ? 3 : 2;
+                conv3x3_fp32<1><<<grid, 128, 0, st>>>(a);
+                CUDA_TRY(cudaMemsetAsync(h->d_bn_stats, 0, sizeof(double) * 2 * 128, st));
+                const size_t npx = (size_t)a.out.rows * a.out.W;
+                dim3 sgrid((unsigned)std::min<size_t>((npx + 255) / 256, 592), a.out.cp / 4);
+                bn_batch_stats<<<sgrid, 256, 0, st>>>(a.out, h->d_bn_stats);
+                bn_batch_apply<<<sgrid, 256, 0, st>>>(a.out, h->d_bn_stats, L.d_gamma, L.d_beta, L.spec.lrelu_first ? 0 : 1);
+                h->launches += 3;
+            } else {
+                conv3x3_fp32<0><<<grid, 128, 0, st>>>(a);
+                ++h->launches;
+            }
             mark(L.spec.name.c_str());
             if (L.pool != -1) {
                 const DnTensor& po = h->tensors[L.pool];

@@ -138,8 +138,11 @@ enum {
     PTD_DN_FP32 = 0u,             /* fp32 FFMA convolutions (strict-parity path)                                   */
     PTD_DN_TF32 = 1u,             /* tcgen05 kind::tf32 tensor-core convolutions, fp32 accumulate in TMEM (default of the CLI) */
     PTD_DN_3XTF32 = 2u,           /* tcgen05 kind::tf32 with hi/lo operand splitting (hi*hi + hi*lo + lo*hi): fp32-class accuracy on the tensor cores */
-    PTD_DN_F16 = 3u               /* fp16 activation storage (same 10-bit mantissa as tf32, half the HBM / shared-memory bytes) + tcgen05 kind::f16,
+    PTD_DN_F16 = 3u,              /* fp16 activation storage (same 10-bit mantissa as tf32, half the HBM / shared-memory bytes) + tcgen05 kind::f16,
                                      fp32 accumulate; the denoised frame itself is written in fp32.  Same stated tolerance as PTD_DN_TF32. */
+    PTD_DN_FP32_BATCH_STATS = 4u  /* TorchScript-export compatibility: the fp32 engine with every BatchNorm normalising by the
+                                     statistics of its current input, as the module traced by convert_to_torchscript.py:26-30 (never put in
+                                     eval mode) does; call with reset_hidden = 1 every frame to mimic its j == 0.  Slow path (4 launches per layer). */
 };
 /* weights_path: "PTDW" flat dump of the model's state_dict (ai_path_tracer_denoiser_b200/weights.py).
  * H, W: frame size (any; zero-padded bottom/right to a multiple of 32 internally, output cropped). */

@@ -29,7 +29,10 @@ def synthetic_gbuffer(H, W, seed=0, frame=0):
 
 
 class DenoiserOracle:
-    def __init__(self, state_dict, dtype=torch.float32, threads=None):
+    def __init__(self, state_dict, dtype=torch.float32, threads=None, batch_stats=False):
+        """batch_stats=True: BatchNorm in TRAINING mode (batch mean / biased batch variance of the current input) - what the module
+        traced by training/convert_to_torchscript.py:26-30 computes, since the script never calls .eval()."""
+        self.batch_stats = batch_stats
         if threads:
             torch.set_num_threads(threads)
         self.dtype = dtype
@@ -40,8 +43,11 @@ class DenoiserOracle:
     def _cbl(self, x, name):
         ck, bk, order = self.layers[name]
         y = F.conv2d(x, self.sd[ck + ".weight"], self.sd[ck + ".bias"], padding=1)
-        bn = lambda t: F.batch_norm(t, self.sd[bk + ".running_mean"], self.sd[bk + ".running_var"], self.sd[bk + ".weight"],
-                                    self.sd[bk + ".bias"], training=False, eps=BN_EPS)
+        if self.batch_stats:
+            bn = lambda t: F.batch_norm(t, None, None, self.sd[bk + ".weight"], self.sd[bk + ".bias"], training=True, eps=BN_EPS)
+        else:
+            bn = lambda t: F.batch_norm(t, self.sd[bk + ".running_mean"], self.sd[bk + ".running_var"], self.sd[bk + ".weight"],
+                                        self.sd[bk + ".bias"], training=False, eps=BN_EPS)
         if order == "bn_lrelu":
             return F.leaky_relu(bn(y), LRELU_SLOPE)
         return bn(F.leaky_relu(y, LRELU_SLOPE))          # encoder layer2 first conv: LeakyReLU then BN (model.py:30-32)

@@ -212,3 +212,19 @@ def test_long_sequence_300_frames_is_stable(wfile):
             errs.append(_err(y, ref))
     assert all(ma <= TOL["tf32"][0] and rl <= TOL["tf32"][1] for ma, rl in errs), errs
     assert errs[-1][1] <= 3 * errs[0][1] + 1e-4, errs                # no growth through the recurrence
+
+
+@pytest.mark.parametrize("mode", ["experimental-traced-export"])
+def test_batch_stats_mode_matches_traced_export_semantics(mode, wfile):
+    """PTD_DN_FP32_BATCH_STATS: BatchNorm with the statistics of the current activations + hidden state zeroed every
+    frame == the reference AutoEncoder in train() mode (golden made from the reference itself).  Stated tolerance: max-abs 2e-3 on
+    O(1) outputs (the statistics of the 3 x 5-pixel bottleneck amplify fp32 reduction-order differences), rel-L2 2e-4."""
+    capi = _capi()
+    g = np.load(os.path.join(GOLDEN, "dn_traced_96x160.npz"))
+    dn = capi.Denoiser(wfile, 96, 160, flags=capi.DN_FP32_BATCH_STATS)
+    for j in range(len(g["x"])):
+        y = dn.forward_host(g["x"][j], reset=True)
+        err = np.abs(y - g["y"][j])
+        assert err.max() <= 2e-3 and np.sqrt((err ** 2).sum() / (g["y"][j] ** 2).sum()) <= 2e-4, (j, err.max())
+    with pytest.raises(capi.PtdError):
+        capi.Denoiser(wfile, 96, 160, flags=capi.DN_FP32_BATCH_STATS, strip=(0, 32))      # cuda-core engines are not tiled

@@ -24,6 +24,20 @@ def test_oracle_matches_reference_model_golden(name):
     assert np.abs(O.hidden[2][0].numpy() - g["hidden3"]).max() <= ATOL * 4
 
 
+def test_oracle_batch_stats_mode_matches_reference_in_training_mode():
+    """the module traced by convert_to_torchscript.py:26-30 is never put in eval mode - BatchNorm normalises with the
+    statistics of its current input and j == 0 zeroes the hidden state on every call.  Golden = the reference AutoEncoder in
+    train() mode (tools/make_golden_dn.py); it must differ from the eval-mode forward, or the mode would be untested."""
+    g = np.load(os.path.join(GOLDEN, "dn_traced_96x160.npz"))
+    sd = weights.synthetic_state_dict(1234)
+    O = DenoiserOracle(sd, batch_stats=True)
+    for j in range(len(g["x"])):
+        y = O.forward(g["x"][j], reset=True)
+        assert np.abs(y - g["y"][j]).max() <= 5 * ATOL                 # batch statistics: one more reduction whose order may differ
+    y_eval = DenoiserOracle(sd).forward(g["x"][0], reset=True)
+    assert np.abs(y_eval - g["y"][0]).max() > 1e-2
+
+
 def test_state_dict_layout_and_roundtrip(tmp_path):
     sd = weights.synthetic_state_dict(1234)
     assert len(sd) == 196                                                          # SURVEY.md section 8a

@@ -37,6 +37,15 @@ def main():
         hid = model.encoder3[0].hidden[0].numpy().copy()
         np.savez_compressed(os.path.join(out_dir, "dn_%dx%d.npz" % (H, W)), x=xs.astype(np.float16) if False else xs, y=ys, hidden3=hid)
         print(H, W, "out abs-max", np.abs(ys).max(axis=(1, 2, 3)))
+    # what the TorchScript export of the reference actually computes - convert_to_torchscript.py:26-30 traces
+    # model.forward (j defaults to 0: hidden state zeroed every call) without ever calling .eval(): BatchNorm in training mode
+    model.train()
+    H, W, frames = 96, 160, 2
+    xs = np.stack([synthetic_gbuffer(H, W, seed=9, frame=j) for j in range(frames)])
+    with torch.no_grad():
+        ys = np.stack([model(torch.from_numpy(xs[j:j + 1]))[0].numpy().copy() for j in range(frames)])
+    np.savez_compressed(os.path.join(out_dir, "dn_traced_%dx%d.npz" % (H, W)), x=xs, y=ys)
+    print("traced-export semantics", H, W, "out abs-max", np.abs(ys).max(axis=(1, 2, 3)))
 
 
 if __name__ == "__main__":
