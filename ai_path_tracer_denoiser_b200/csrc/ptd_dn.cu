@@ -189,18 +189,17 @@ __global__ void __launch_bounds__(256) bn_batch_apply(const DnTensor t, const do
     const int q = blockIdx.y;
     float4* plane = reinterpret_cast<float4*>(t.base + (size_t)q * t.quad_stride()) + t.W;
     const size_t n = (size_t)t.rows * t.W;
-    float mul[4], add[4];
+    float mul[4], add[4], mu[4];
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
         const int c = q * 4 + k;
         const double mean = stats[2 * c] / (double)n, var = fmax(stats[2 * c + 1] / (double)n - mean * mean, 0.0);
         const float invstd = (float)(1.0 / sqrt(var + 1e-5));
-        mul[k] = invstd * gamma[c];
-        add[k] = beta[c] - (float)mean * mul[k];
+        mu[k] = (float)mean; mul[k] = invstd * gamma[c]; add[k] = beta[c];
     }
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
         float4 v = plane[i];
-        v.x = fmaf(v.x, mul[0], add[0]); v.y = fmaf(v.y, mul[1], add[1]); v.z = fmaf(v.z, mul[2], add[2]); v.w = fmaf(v.w, mul[3], add[3]);
+        v.x = fmaf(v.x - mu[0], mul[0], add[0]); v.y = fmaf(v.y - mu[1], mul[1], add[1]); v.z = fmaf(v.z - mu[2], mul[2], add[2]); v.w = fmaf(v.w - mu[3], mul[3], add[3]);
         if (lrelu_after) { v.x = v.x > 0.f ? v.x : 0.1f * v.x; v.y = v.y > 0.f ? v.y : 0.1f * v.y; v.z = v.z > 0.f ? v.z : 0.1f * v.z; v.w = v.w > 0.f ? v.w : 0.1f * v.w; }
         plane[i] = v;
     }
@@ -812,6 +811,10 @@ extern "C" ptd_status ptd_dn_forward_host(ptd_dn* h, const float* gbuf_host, flo
     if (rc != PTD_OK) return rc;
     CUDA_TRY(cudaMemcpy(rgb_host, h->d_rgb, P * 12, cudaMemcpyDeviceToHost));            // main.cpp:91 (.to(kCPU))
     return PTD_OK;
+}
+
+void ptd_dn_describe(const ptd_dn* h, int* device, int* H, int* W, int* strip) {
+    *device = h->device; *H = h->H; *W = h->W; *strip = h->strip ? 1 : 0;
 }
 
 extern "C" ptd_status ptd_dn_padded_size(const ptd_dn* h, int* Hp, int* Wp) {

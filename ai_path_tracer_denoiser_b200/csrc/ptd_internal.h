@@ -81,5 +81,8 @@ void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out);
 // Conservative (padded) world-space boxes of the cube / sphere geoms: a ray that misses one cannot hit the geom.
 void ptd_geom_bounds(const std::vector<ptd_geom>& geoms, std::vector<ptd_aabb>& out);
 
+// what ptd_frame_host (ptd_pt.cu) needs to know about a denoiser handle (ptd_dn.cu)
+void ptd_dn_describe(const ptd_dn* h, int* device, int* H, int* W, int* strip);
+
 // camera helpers shared with the CLI
 void ptd_camera_derive(ptd_camera& cam, float fovy_deg);

@@ -807,7 +807,11 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
     CUDA_TRY(cudaSetDevice(h->device));
     if (cam && (cam->res_x != h->W || cam->res_y != h->H)) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_render: camera resolution %dx%d differs from the handle's %dx%d", cam->res_x, cam->res_y, h->W, h->H);
     if (!gbuf) {
-        if (!h->d_gbuf_own) { CUDA_TRY(cudaMalloc((void**)&h->d_gbuf_own, sizeof(float) * 10 * (size_t)h->Pfull)); CUDA_TRY(cudaMemset(h->d_gbuf_own, 0, sizeof(float) * 10 * (size_t)h->Pfull)); }
+        if (!h->d_gbuf_own) {
+            CUDA_TRY(cudaMalloc((void**)&h->d_gbuf_own, sizeof(float) * 10 * (size_t)h->Pfull));
+            CUDA_TRY(cudaMemset(h->d_gbuf_own, 0, sizeof(float) * 10 * (size_t)h->Pfull));
+            CUDA_TRY(cudaDeviceSynchronize());        // the memset runs on the legacy stream; `st` may be a non-blocking stream that does not wait for it
+        }
         gbuf = h->d_gbuf_own;
     }
     PtKernelParams p;
@@ -988,7 +992,10 @@ extern "C" ptd_status ptd_pt_render_host(ptd_pt* h, const ptd_camera* cam, int i
 // download (host_tensor, optional) overlaps the remaining bounces and the denoiser.
 extern "C" ptd_status ptd_frame_host(ptd_pt* h, ptd_dn* dn, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host) {
     if (!h || !dn || !rgb_host || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_host: bad argument");
-    if (h->nranks > 1 || h->rows != h->H) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_frame_host: row-strip handles take device pointers (ptd_pt_render + ptd_dn_forward)");
+    int dn_device = 0, dn_H = 0, dn_W = 0, dn_strip = 0;
+    ptd_dn_describe(dn, &dn_device, &dn_H, &dn_W, &dn_strip);
+    if (h->nranks > 1 || h->rows != h->H || dn_strip) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_frame_host: row-strip handles take device pointers (ptd_pt_render + ptd_dn_forward)");
+    if (dn_device != h->device || dn_H != h->H || dn_W != h->W) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_host: the denoiser handle is for %dx%d on device %d, the path tracer for %dx%d on device %d", dn_W, dn_H, dn_device, h->W, h->H, h->device);
     CUDA_TRY(cudaSetDevice(h->device));
     if (!h->host_stream[0]) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream[0], cudaStreamNonBlocking));
