@@ -109,6 +109,7 @@ struct __align__(64) TcParams {
     int lrelu_first, round_out;
     DnTensor out, pool_out;
     TcStripLink link;
+    int pdl;                             // launched with programmatic stream serialization (appended: the offsets above are the validated ones)
 };
 
 struct TcConvPlan {
@@ -330,6 +331,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nchunks = p.n0 + p.n1;
 
+    // PTD_DN_PDL (opt-in): programmatic dependent launch.  The NEXT layer's CTAs may start as soon as every CTA of this launch is
+    // running; they set up barriers, TMEM and their resident weights - none of which depend on this layer - and only then wait
+    // (griddepcontrol.wait, TMA producer below) for this launch to finish and flush before reading its output.  The layers at
+    // <= 1/8 resolution have fewer tiles than SMs and sit at a 12-17 us launch + prologue floor each; this hides the prologue.
+    if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+
     if (warp == 0 && lane == 0) {
         tc::prefetch_tmap(&p.mapA0);
         if (p.n1) tc::prefetch_tmap(&p.mapA1);
@@ -376,6 +383,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             }
         }
         __syncwarp();
+        if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous launch has completed and its stores are visible
         int stage = 0; uint32_t phase = 0;
         const uint32_t stage_tx = TC_A_BYTES + (p.resident ? 0u : p.b_stage_bytes);
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
@@ -645,7 +653,18 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
 
 inline ptd_status tc_conv_launch(TcConvPlan& plan, cudaStream_t st, int* launches, bool* pooled) {
     if (!plan.valid) PTD_FAIL(PTD_ERR_STATE, "tc conv: plan not built");
-    if (plan.p.half) conv_tc_kernel<true><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.p);
+    if (plan.p.pdl) {
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = plan.smem; cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        const cudaError_t e = plan.p.half ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, plan.p) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, plan.p);
+        if (e != cudaSuccess) PTD_FAIL(PTD_ERR_CUDA, "tc conv: cudaLaunchKernelEx failed: %s", cudaGetErrorString(e));
+    }
+    else if (plan.p.half) conv_tc_kernel<true><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.p);
     else conv_tc_kernel<false><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.p);
     if (launches) ++*launches;
     if (pooled) *pooled = plan.p.pool_out.base != nullptr;

@@ -360,6 +360,7 @@ struct ptd_dn {
     ptd_strip_info peer_info[DN_MAX_RANKS];
     bool has_peer[2] = {false, false};                     // a strip above / below exists
     size_t gflags_off = 0;
+    bool pdl = false;                                      // PTD_DN_PDL=1: convs launched with programmatic stream serialization
     int repl_level = 6;                                    // levels >= this are replicated on every strip (6 = none)
     int t_gather = -1;                                     // the gathered tensor (pooled output of encoder repl_level, full height)
     std::vector<int> tensor_level; std::vector<char> tensor_full;
@@ -403,6 +404,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     CUDA_TRY(cudaSetDevice(device));
     ptd_dn* h = new ptd_dn();
     h->device = device; h->flags = flags; h->H = H; h->W = W; h->Hp = Hp; h->Wp = Wp; h->row0 = row0; h->rows = rows; h->strip = strip;
+    if (const char* e = getenv("PTD_DN_PDL")) h->pdl = atoi(e) > 0;
     if (const char* e = getenv("PTD_DN_REPL_LEVEL")) { const int v = atoi(e); if (v >= 3 && v <= 6) h->repl_level = v; }
     auto fail = [&](ptd_status code) { ptd_dn_destroy(h); return code; };
     auto dalloc = [&](size_t floats) -> float* {
@@ -736,6 +738,7 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
             } else if (L.pool != -1 && h->tensor_full[L.pool] && !h->tensor_full[o]) {
                 k.pool_yoff = h->row0 >> h->tensor_level[L.pool];           // a single strip that is not the whole frame cannot exist; kept for symmetry
             }
+            plan.p.pdl = (h->pdl && li > 0 && !h->profiling) ? 1 : 0;       // the first conv follows pack_gbuffer, which does not trigger early
             ptd_status rc = tc_conv_launch(plan, st, &h->launches, nullptr);
             if (rc != PTD_OK) return rc;
             mark(L.spec.name.c_str());

@@ -228,3 +228,21 @@ def test_batch_stats_mode_matches_traced_export_semantics(mode, wfile):
         assert err.max() <= 2e-3 and np.sqrt((err ** 2).sum() / (g["y"][j] ** 2).sum()) <= 2e-4, (j, err.max())
     with pytest.raises(capi.PtdError):
         capi.Denoiser(wfile, 96, 160, flags=capi.DN_FP32_BATCH_STATS, strip=(0, 32))      # cuda-core engines are not tiled
+
+
+@pytest.mark.parametrize("mode", ["experimental-pdl-tf32", "experimental-pdl-f16"])
+def test_programmatic_dependent_launch_changes_nothing(mode, wfile, monkeypatch):
+    """PTD_DN_PDL=1 (opt-in): the convs are launched with programmatic stream serialization - the next layer's prologue overlaps the
+    tail of the current one and griddepcontrol.wait orders the data.  Must be bit-identical to the plain launches over a recurrent
+    sequence, at a size with both many-tile and few-tile layers."""
+    capi = _capi()
+    flags = capi.DN_TF32 if mode.endswith("tf32") else capi.DN_F16
+    H, W = 200, 328
+    xs = [synthetic_gbuffer(H, W, seed=21, frame=j) for j in range(4)]
+    outs = {}
+    for pdl in ("0", "1"):
+        monkeypatch.setenv("PTD_DN_PDL", pdl)
+        dn = capi.Denoiser(wfile, H, W, flags=flags)
+        outs[pdl] = [dn.forward_host(x, reset=(j == 0)) for j, x in enumerate(xs)]
+    for a, b in zip(outs["0"], outs["1"]):
+        assert a.tobytes() == b.tobytes()

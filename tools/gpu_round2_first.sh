@@ -18,6 +18,8 @@ if [ "$WHAT" = single ]; then
   done
   PTD_PT_RAY_SORT=1 timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_raysort_serial.json" 2> "$OUT/bench_raysort_serial.err"
   timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_default_serial.json" 2> "$OUT/bench_default_serial.err"
+  PTD_DN_PDL=1 timeout 400 python bench.py $B > "$OUT/bench_pdl.json" 2> "$OUT/bench_pdl.err"; echo "pdl rc=$?"
+  PTD_DN_PDL=1 timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_pdl_serial.json" 2> "$OUT/bench_pdl_serial.err"
   timeout 400 python bench.py $B --e2e fused > "$OUT/bench_e2e_fused.json" 2> "$OUT/bench_e2e_fused.err"; echo "fused rc=$?"
   python - "$OUT" <<'PY'
 import glob, json, os, sys
