@@ -236,6 +236,7 @@ def test_programmatic_dependent_launch_changes_nothing(mode, wfile, monkeypatch)
     tail of the current one and griddepcontrol.wait orders the data.  Must be bit-identical to the plain launches over a recurrent
     sequence, at a size with both many-tile and few-tile layers."""
     capi = _capi()
+    from oracle.dn_oracle import synthetic_gbuffer
     flags = capi.DN_TF32 if mode.endswith("tf32") else capi.DN_F16
     H, W = 200, 328
     xs = [synthetic_gbuffer(H, W, seed=21, frame=j) for j in range(4)]
