@@ -230,3 +230,21 @@ def test_ray_binning_estimate_on_the_host(tmp_path):
     assert rays >= 63000 and 8 < bins <= 8 * 8 ** 3
     assert binned_wf < 0.9 * arrival_wf and binned_steps <= arrival_steps * 1.02, list(out)
     assert capi.lib().ptd_bvh_probe_order(sc.h, 64000, 3, 9, out) < 0          # cell bits out of range
+
+
+def test_cli_surface_and_error_behaviour_without_a_gpu(tmp_path):
+    """ptd_cli keeps the reference's command line (`exe SCENEFILE.txt`, main.cpp:50-56): usage without arguments, loud failures for a
+    missing scene / unknown mode, and - on a box without a CUDA device - a refusal to render instead of a CPU fallback."""
+    import subprocess
+    cli = os.path.join(ROOT, "ai_path_tracer_denoiser_b200", "ptd_cli")
+    if not os.path.exists(cli):
+        capi.lib()                                                    # builds libptd.so + ptd_cli in-tree
+    r = subprocess.run([cli], capture_output=True, text=True)
+    assert r.returncode == 1 and "SCENEFILE.txt" in r.stdout + r.stderr
+    r = subprocess.run([cli, str(tmp_path / "nope.txt")], capture_output=True, text=True)
+    assert r.returncode == 2 and "cannot open scene file" in r.stdout + r.stderr
+    r = subprocess.run([cli, os.path.join(SCENES, "cornell_64x48.txt"), "--mode", "bogus"], capture_output=True, text=True)
+    assert r.returncode == 1 and "unknown --mode" in r.stdout + r.stderr
+    if capi.device_count() == 0:
+        r = subprocess.run([cli, os.path.join(SCENES, "cornell_64x48.txt"), "--frames", "1"], capture_output=True, text=True)
+        assert r.returncode == 2 and "no CPU fallback" in r.stdout + r.stderr
