@@ -4,12 +4,14 @@
 #   usage: gpurun --timeout 1500 -- 'bash tools/gpu_round2_first.sh r03a'           (1 GPU)
 #          gpurun --gpus 4 --timeout 900 -- 'bash tools/gpu_round2_first.sh r03b strips 4'
 set -uo pipefail
+[ -x tools/microbench/umma_rate ] || nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tools/microbench/umma_rate tools/microbench/umma_rate.cu
 TAG=${1:-r03a}; WHAT=${2:-single}; N=${3:-4}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$OUT/gpu.csv" 2>&1
 B="--steps 100 --warmup 5 --no-cpu-baseline"
 if [ "$WHAT" = single ]; then
+  timeout 120 tools/microbench/umma_rate 2048 > "$OUT/umma_rate.txt" 2>&1; echo "umma_rate rc=$?"; head -40 "$OUT/umma_rate.txt"
   timeout 1200 python -m pytest tests -m gpu -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -4 "$OUT/pytest_gpu.log"
   timeout 400 python bench.py $B > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"; echo "default rc=$?"
   for cfg in "4 22" "4 8" "5 22" "3 22"; do
