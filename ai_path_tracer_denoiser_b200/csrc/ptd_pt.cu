@@ -333,7 +333,10 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
 }
 
 // ---- kernel 2 of a bounce: shadeMaterial (:333-390) + thrust::partition (:505) + finalGather / copy_data for the paths that end here
-template <bool FIRST>
+// WIDE (PTD_PT_WIDE_LOOKBACK=1, opt-in): the decoupled look-back reads PT_BLOCK predecessor states per trip with the whole block
+// instead of 32 with one warp.  With ~300 tiles in flight the one-warp walk is ~10 dependent L2 round trips per tile while the other
+// 15 warps sit at the barrier (ncu: stall_barrier dominates pt_shade); one block-wide trip covers every tile in flight.
+template <bool FIRST, bool WIDE = false>
 __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
     __shared__ __align__(16) uint32_t s_words[PT_BLOCK * PT_WORDS];                  // 5632 B staging (loads, then compacted stores)
     __shared__ __align__(16) uint32_t s_isx[PT_BLOCK * 9];                           // 4608 B: the tile's ShadeableIntersections
@@ -473,7 +476,51 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
     int warp_off = 0, block_kept = 0;
 #pragma unroll
     for (int w = 0; w < PT_BLOCK / 32; ++w) { if (w < warp) warp_off += s_warp_kept[w]; block_kept += s_warp_kept[w]; }
-    if (warp == 0) {
+    if (WIDE) {
+        __shared__ int s_first[PT_BLOCK / 32], s_pending[PT_BLOCK / 32], s_sum[PT_BLOCK / 32];
+        int excl = 0;
+        if (tile == 0) {
+            if (tid == 0) st_status(&p.status[0], (2ull << 32) | (unsigned)block_kept);
+        } else {
+            if (tid == 0) st_status(&p.status[tile], (1ull << 32) | (unsigned)block_kept);
+            int j = tile - 1;                                              // thread `tid` looks at predecessor j - tid
+            for (;;) {
+                const int t = j - tid;
+                const unsigned long long sv = t >= 0 ? ld_status(&p.status[t]) : (2ull << 32);   // before tile 0: prefix 0
+                const unsigned st = (unsigned)(sv >> 32);
+                const unsigned has_prefix = __ballot_sync(0xffffffffu, st == 2u);
+                const unsigned not_ready = __ballot_sync(0xffffffffu, st == 0u);
+                const int first = has_prefix ? __ffs(has_prefix) - 1 : 32;                    // nearest prefix inside this warp's 32 predecessors
+                const unsigned needed = first >= 31 ? 0xffffffffu : ((2u << first) - 1u);    // lanes 0 .. first (all of them when there is none)
+                int v = ((needed >> lane) & 1u) ? (int)(unsigned)sv : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                if (lane == 0) { s_first[warp] = first; s_pending[warp] = (not_ready & needed) != 0u; s_sum[warp] = v; }
+                __syncthreads();
+                int total = 0; bool pending = false, found = false;
+#pragma unroll 1
+                for (int w = 0; w < PT_BLOCK / 32; ++w) {                  // warps in look-back order, up to the first one that saw a prefix
+                    pending |= s_pending[w] != 0; total += s_sum[w];
+                    if (s_first[w] < 32) { found = true; break; }
+                }
+                __syncthreads();                                           // the three arrays are rewritten by the next trip
+                if (pending) continue;                                     // block-uniform: a needed predecessor has not published yet
+                excl += total;
+                if (found) break;
+                j -= PT_BLOCK;
+            }
+            if (tid == 0) st_status(&p.status[tile], (2ull << 32) | (unsigned)(excl + block_kept));
+        }
+        if (tid == 0) {
+            s_excl = excl;
+            if (base + PT_BLOCK >= n) {                                                       // last tile publishes the live count and mails it
+                p.counts[p.bounce + 1] = excl + block_kept;
+                const unsigned long long m = ((unsigned long long)p.epoch << 32) | (unsigned)(excl + block_kept);
+                for (int r = p.rank + 1; r < p.nranks; ++r)
+                    if (p.peer_mail[r]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_mail[r] + (size_t)(p.bounce + 1) * PT_MAX_RANKS + p.rank), "l"(m) : "memory");
+            }
+        }
+    } else if (warp == 0) {
         // decoupled look-back, one WARP wide: state 1 = tile aggregate, 2 = inclusive prefix (value in the low 32 bits).  Each trip
         // reads the 32 predecessors' states at once; with ~1000 tiles in flight a one-thread walk was a chain of hundreds of
         // dependent L2 reads and left the rest of the block at the barrier (ncu: stall_barrier 19.6 of 33 warps per issue).
@@ -663,6 +710,7 @@ struct ptd_pt {
     std::vector<cudaEvent_t> events;
     int timed_launches = 0;
     int bvh_nodes = 0, bvh_leaves = 0, bvh_max_leaf = 0, bvh_max_depth = 0;
+    bool wide_lookback = false;                              // PTD_PT_WIDE_LOOKBACK=1
     // PTD_PT_RAY_SORT
     int bin_bits = 0, bin_refill = TR_REFILL, nbins = 0;
     ptd_aabb bin_box;
@@ -715,6 +763,7 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
     if (const char* e = getenv("PTD_PT_RAY_SORT")) { if (atoi(e) > 0) flags |= PTD_PT_RAY_SORT; }   // tuning: opt in without touching the caller
     if (!(sc->faces.size() > 0) || (flags & PTD_PT_NO_BVH)) flags &= ~(unsigned)PTD_PT_RAY_SORT;      // binning only pays for BVH traversal
     h->device = device; h->flags = flags;
+    if (const char* e = getenv("PTD_PT_WIDE_LOOKBACK")) h->wide_lookback = atoi(e) > 0;
     h->cam = sc->camera; h->mesh_box = sc->mesh_box;
     h->W = sc->camera.res_x; h->H = sc->camera.res_y; h->Pfull = h->W * h->H; h->depth = sc->trace_depth;
     h->row0 = row0; h->rows = rows; h->P = h->W * rows;
@@ -866,7 +915,11 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
             pt_mail_gate<<<1, 32, 0, st>>>(h->d_mail, b, h->rank, h->epoch);
             h->launches += 1;
         }
-        if (b == 0) pt_shade<true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+        if (h->wide_lookback) {
+            if (b == 0) pt_shade<true, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+            else pt_shade<false, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+        }
+        else if (b == 0) pt_shade<true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
         else pt_shade<false><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
         h->launches += 2;
         mark();

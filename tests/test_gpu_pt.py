@@ -234,6 +234,27 @@ def test_ray_sort_changes_nothing(bits, monkeypatch):
     assert b[4] == a[4] + 3 * (sc.counts()[3] - 1)                # three binning kernels per bounce >= 1
 
 
+@pytest.mark.parametrize("res", [(160, 96), (800, 600)], ids=["experimental-wide-lookback-30tiles", "experimental-wide-lookback-938tiles"])
+def test_wide_lookback_changes_nothing(res, monkeypatch):
+    """PTD_PT_WIDE_LOOKBACK=1 (opt-in): pt_shade's decoupled look-back reads 512 predecessor tiles per trip with the whole block.
+    The compaction must stay the same stable compaction: identical live counts, PathSegment order and G-buffer - with fewer tiles
+    than one trip covers and with more (second trip)."""
+    capi = _capi()
+    sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
+    sc.set_resolution(*res)
+    out = []
+    for wide in ("0", "1"):
+        monkeypatch.setenv("PTD_PT_WIDE_LOOKBACK", wide)
+        pt = capi.PathTracer(sc, flags=capi.PT_TRACE)
+        g = pt.render_host()
+        counts, run = pt.live_counts()
+        out.append((g, counts[:run], [pt.dump_paths(b) for b in range(run)]))
+    a, b = out
+    assert a[1] == b[1] and a[0].tobytes() == b[0].tobytes()
+    for k, (pa, pb) in enumerate(zip(a[2], b[2])):
+        _same(pa, pb, "bounce %d paths" % k)
+
+
 @pytest.mark.parametrize("mode", ["experimental-gated-mail"])
 def test_row_strips_gated_mail(mode):
     """PTD_PT_GATED_MAIL (the flag the opt-in two-stream strip loop needs, PTD_STRIP_PIPELINE=1): the live-count mail is awaited by a

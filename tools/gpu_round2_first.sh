@@ -20,6 +20,7 @@ if [ "$WHAT" = single ]; then
   done
   PTD_PT_RAY_SORT=1 timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_raysort_serial.json" 2> "$OUT/bench_raysort_serial.err"
   timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_default_serial.json" 2> "$OUT/bench_default_serial.err"
+  PTD_PT_WIDE_LOOKBACK=1 timeout 400 python bench.py $B > "$OUT/bench_wide_lookback.json" 2> "$OUT/bench_wide_lookback.err"; echo "wide look-back rc=$?"
   PTD_DN_PDL=1 timeout 400 python bench.py $B > "$OUT/bench_pdl.json" 2> "$OUT/bench_pdl.err"; echo "pdl rc=$?"
   PTD_DN_PDL=1 timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_pdl_serial.json" 2> "$OUT/bench_pdl_serial.err"
   timeout 400 python bench.py $B --e2e fused > "$OUT/bench_e2e_fused.json" 2> "$OUT/bench_e2e_fused.err"; echo "fused rc=$?"
@@ -28,7 +29,8 @@ import glob, json, os, sys
 for p in sorted(glob.glob(os.path.join(sys.argv[1], "bench_*.json"))):
     try:
         d = json.loads(open(p).read().strip().splitlines()[-1])
-        print("%-34s %7.1f fps  e2e %7.1f  trace/bounce %s" % (os.path.basename(p), d["value"], d["e2e"]["value"], d["roofline"]["per_bounce_ms"]["pt_trace"]))
+        print("%-34s %7.1f fps  e2e %7.1f  convs %.3f ms  trace/bounce %s  shade/bounce %s" % (os.path.basename(p), d["value"], d["e2e"]["value"], d["roofline"]["conv"]["ms"],
+              d["roofline"]["per_bounce_ms"]["pt_trace"], d["roofline"]["per_bounce_ms"]["pt_shade"]))
     except Exception as e:
         print(os.path.basename(p), "unreadable:", e)
 PY
