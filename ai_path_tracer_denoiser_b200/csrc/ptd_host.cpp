@@ -877,6 +877,10 @@ extern "C" ptd_status ptd_bvh_probe(const ptd_scene* sc, int nrays, unsigned see
     if (nf == 0) PTD_FAIL(PTD_ERR_STATE, "ptd_bvh_probe: the scene has no mesh");
     PtdBvh bvh;
     ptd_build_bvh(faces, bvh);
+    PtdBvh8 bvh8;                                                       // PTD_BVH8=1: probe the 8-wide quantised layout instead
+    const bool wide8 = getenv("PTD_BVH8") && atoi(getenv("PTD_BVH8")) > 0;
+    if (wide8) { ptd_build_bvh8(faces, bvh, bvh8); if (!bvh8.ok) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_bvh_probe: this mesh does not fit the BVH8q encoding"); }
+    std::vector<unsigned long long> gstack(4 * (size_t)std::max(bvh8.max_depth, 1) + 8);
     ProbeRng rng{seed * 2654435761u + 12345u};
     long long visits = 0, tests = 0, hits = 0; int max_sp = 0, mismatches = 0;
     std::vector<int> stack(3 * bvh.max_depth4 + 8);
@@ -911,6 +915,47 @@ extern "C" ptd_status ptd_bvh_probe(const ptd_scene* sc, int nrays, unsigned see
             unsigned morton = 0;
             for (int b = 0; b < T.bits; ++b) morton |= (((c[0] >> b) & 1u) << (3 * b)) | (((c[1] >> b) & 1u) << (3 * b + 1)) | (((c[2] >> b) & 1u) << (3 * b + 2));
             T.bin.push_back((morton << 3) | (dd[0] < 0.f ? 1u : 0u) | (dd[1] < 0.f ? 2u : 0u) | (dd[2] < 0.f ? 4u : 0u));
+        }
+        if (wide8) {
+            // node group = (first interior child, hit bits << 24 | imask), nearest child = highest hit bit; triangle group = (first triangle, mask)
+            const int oct = nearp[0] | (nearp[1] << 1) | (nearp[2] << 2);
+            unsigned g_base = 0, g_bits = 0x80000000u | 1u;               // the root: pretend slot 7 ^ oct ... of a parent whose only interior child is node 0
+            int gsp = 0; bool root = true;
+            for (;;) {
+                unsigned t_base = 0, t_bits = 0;
+                if (g_bits > 0x00ffffffu) {
+                    int child;
+                    if (root) { child = 0; g_bits = 0; root = false; }
+                    else {
+                        const int bit = 31 - __builtin_clz(g_bits);
+                        g_bits &= ~(1u << bit);
+                        if (g_bits > 0x00ffffffu) { gstack[gsp++] = ((unsigned long long)g_base << 32) | g_bits; max_sp = std::max(max_sp, gsp); }
+                        const int slot = (7 - (bit - 24)) ^ oct;
+                        child = (int)g_base + __builtin_popcount(g_bits & 0xffu & ((1u << slot) - 1u));
+                    }
+                    ++visits;
+                    if (g_probe_trace) g_probe_trace->nodes.back().push_back(child * 80 / 128);      // the 128-byte line a lane's loads start in
+                    const PtdBvh8Node& nd = bvh8.nodes[child];
+                    unsigned ih = 0, th = 0;
+                    ptd_bvh8_node_hits(nd, o, id, oct, t_min * 1.00001f, &ih, &th);
+                    g_base = (unsigned)nd.child_base; g_bits = (ih << 24) | nd.imask;
+                    t_base = (unsigned)nd.tri_base & 0x00ffffffu; t_bits = th;
+                }
+                while (t_bits) {
+                    const int k = __builtin_ctz(t_bits);
+                    t_bits &= t_bits - 1;
+                    ++tests;
+                    const PtdBvhTri& t = bvh8.tris[t_base + k];
+                    if (g_probe_trace) g_probe_trace->lines.back().push_back((int)((t_base + k) * 48 / 128));
+                    probe_consider(probe_tri(t.v0, t.v1, t.v2, o, dd), t.face, t_min, best);
+                }
+                if (g_bits <= 0x00ffffffu) {
+                    if (gsp == 0) break;
+                    const unsigned long long e = gstack[--gsp];
+                    g_base = (unsigned)(e >> 32); g_bits = (unsigned)e;
+                }
+            }
+            node = SENT;
         }
         while (node != SENT) {
             if (node >= 0) {
@@ -954,6 +999,11 @@ extern "C" ptd_status ptd_bvh_probe(const ptd_scene* sc, int nrays, unsigned see
     for (const PtdBvh4& w : bvh.wide4) for (int k = 0; k < 4; ++k) if (w.f[k] <= w.f[4 + k]) ++used;
     out[0] = mismatches; out[1] = (double)visits / nrays; out[2] = (double)tests / nrays; out[3] = max_sp; out[4] = (double)bvh.wide4.size();
     out[5] = bvh.leaves; out[6] = bvh.wide4.empty() ? 0.0 : (double)used / bvh.wide4.size(); out[7] = (double)hits / nrays;
+    if (wide8) {
+        used = 0;
+        for (const PtdBvh8Node& n8 : bvh8.nodes) used += __builtin_popcount((unsigned)n8.tri_base >> 24);
+        out[4] = (double)bvh8.nodes.size(); out[6] = (double)used / bvh8.nodes.size();
+    }
     return PTD_OK;
 }
 

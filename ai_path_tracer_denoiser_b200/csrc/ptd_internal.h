@@ -3,6 +3,7 @@
 #include <string>
 #include <vector>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include "ptd.h"
 
@@ -78,6 +79,17 @@ struct PtdBvh {
     int leaves = 0, max_leaf = 0, max_depth = 0;
 };
 void ptd_build_bvh(const std::vector<ptd_face>& faces, PtdBvh& out);
+// 8-wide BVH with 8-bit quantised child boxes (ptd_bvh8.cpp): 80-byte nodes, five 16-byte loads per visit
+struct PtdBvh8Node {
+    float origin[3]; uint8_t e[3]; uint8_t imask;
+    int child_base; int tri_base;            // tri_base: low 24 bits = first triangle, high 8 bits = valid-slot mask
+    uint8_t meta[8];
+    uint8_t qlo[3][8], qhi[3][8];
+};
+static_assert(sizeof(PtdBvh8Node) == 80, "BVH8q node is 80 bytes");
+struct PtdBvh8 { std::vector<PtdBvh8Node> nodes; std::vector<PtdBvhTri> tris; int max_depth = 0, max_node_tris = 0; bool ok = false; };
+void ptd_build_bvh8(const std::vector<ptd_face>& faces, const PtdBvh& binary, PtdBvh8& out);
+void ptd_bvh8_node_hits(const PtdBvh8Node& n, const float o[3], const float idir[3], int oct, float tlim, unsigned* interior_hits, unsigned* tri_hits);
 // Conservative (padded) world-space boxes of the cube / sphere geoms: a ray that misses one cannot hit the geom.
 void ptd_geom_bounds(const std::vector<ptd_geom>& geoms, std::vector<ptd_aabb>& out);
 

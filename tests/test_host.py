@@ -210,6 +210,30 @@ def test_bvh_traversal_equals_brute_force_on_the_host(knobs, monkeypatch, tmp_pa
     assert 1.0 < r[1] < 60 and r[2] < 60, r                              # a sane tree: tens of node visits / triangle tests per ray, not thousands
 
 
+@pytest.mark.parametrize("knobs", [{}, {"PTD_BVH_MAX_LEAF": "1"}, {"PTD_BVH8_GREEDY": "1"}], ids=["dp-collapse", "dp-collapse-leaf1", "greedy-collapse"])
+def test_bvh8q_traversal_equals_brute_force_on_the_host(knobs, monkeypatch, tmp_path):
+    """BVH8q (csrc/ptd_bvh8.cpp: 8-wide, 8-bit quantised child boxes, 80-byte nodes, SAH-optimal collapse) - the data structure the next
+    trace kernel is designed around - must be conservative: its host traversal (node groups / triangle masks, octant slot order)
+    returns exactly the brute-force (face, t) for every probe ray, with fewer node visits than the 4-wide layout."""
+    from ai_path_tracer_denoiser_b200 import scenegen
+    for k in ("PTD_BVH_MAX_LEAF", "PTD_BVH_SWEEP", "PTD_BVH_LEAF_COST", "PTD_BVH8", "PTD_BVH8_GREEDY", "PTD_BVH8_CPRIM"):
+        monkeypatch.delenv(k, raising=False)
+    obj = str(tmp_path / "sponza_like.obj")
+    scenegen.write_obj(obj, "sponza", 12000)
+    big = capi.Scene(path=scenegen.write_mesh_scene(str(tmp_path / "s.txt"), obj, 64, 48, kind="sponza", material="diffuse"))
+    small = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
+    ref = _bvh_probe(big, 6000, 0)
+    for k, v in knobs.items():
+        monkeypatch.setenv(k, v)
+    monkeypatch.setenv("PTD_BVH8", "1")
+    r = _bvh_probe(small, 4000, 4000)
+    assert r[0] == 0 and r[7] > 0.5, r
+    r = _bvh_probe(big, 6000, 6000)
+    assert r[0] == 0 and r[7] == ref[7], (r, ref)                       # same rays, same hit fraction
+    assert r[1] < ref[1] and r[3] <= 16, (r, ref)                       # fewer node visits per ray; a shallow stack of node groups
+    assert r[6] > (3.0 if "PTD_BVH8_GREEDY" in knobs else 5.5)          # children per 8-wide node: the DP collapse fills them
+
+
 def test_bvh_probe_argument_errors():
     out = (C.c_double * 8)()
     cornell = capi.Scene(path=os.path.join(SCENES, "cornell_64x48.txt"))     # no mesh
