@@ -179,8 +179,9 @@ def main():
     ap.add_argument("--mode", default="f16", choices=["tf32", "f16", "3xtf32", "fp32"])
     ap.add_argument("--config", default="C3", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e", default="calls", choices=["calls", "fused"], help="host-pointer API of the e2e leg at N = 1: the reference's two call sites "
-                    "(ptd_pt_render_host + ptd_dn_forward_host) or the one-call frame (ptd_frame_host: the G-buffer is downloaded but never uploaded again)")
+    ap.add_argument("--e2e", default="auto", choices=["auto", "calls", "fused"], help="host-pointer API of the e2e leg at N = 1: the reference's two call sites "
+                    "(ptd_pt_render_host + ptd_dn_forward_host), the one-call frame (ptd_frame_host: the G-buffer is downloaded but never uploaded again), "
+                    "or auto = the one-call frame if - and only if - it reproduces the two-call path bit for bit on this box, else the two calls")
     ap.add_argument("--no-pipeline", action="store_true", help="serial frame loop (path trace, then denoise, on one stream) instead of the two-stream loop")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -355,7 +356,22 @@ def main():
     if world == 1:
         host_g = torch.empty(10 * P, dtype=torch.float32).pin_memory()
         host_rgb = torch.empty(3 * P, dtype=torch.float32).pin_memory()
-        if args.e2e == "fused":
+        e2e_api, e2e_check = args.e2e, None
+        if e2e_api == "auto":
+            # ptd_frame_host was written after round 1's GPU budget was spent: it is used only if, here and now, it returns exactly what
+            # the two reference call sites return for the same camera (G-buffer and denoised frame, hidden state reset on both sides)
+            try:
+                capi.check(L.ptd_pt_render_host(pt.h, cams[0].ctypes.data, 1, C.c_void_p(host_g.data_ptr())), "ptd_pt_render_host")
+                capi.check(L.ptd_dn_forward_host(dn.h, C.c_void_p(host_g.data_ptr()), C.c_void_p(host_rgb.data_ptr()), 1), "ptd_dn_forward_host")
+                ref_g, ref_rgb = host_g.clone(), host_rgb.clone()
+                host_g.zero_(); host_rgb.zero_()
+                capi.check(L.ptd_frame_host(pt.h, dn.h, cams[0].ctypes.data, 1, 1, C.c_void_p(host_g.data_ptr()), C.c_void_p(host_rgb.data_ptr())), "ptd_frame_host")
+                same = bool(torch.equal(ref_g, host_g)) and bool(torch.equal(ref_rgb, host_rgb))
+                e2e_api = "fused" if same else "calls"
+                e2e_check = "ptd_frame_host == ptd_pt_render_host + ptd_dn_forward_host bit for bit on frame 0" if same else "ptd_frame_host differed from the two-call path on frame 0: not used"
+            except Exception as exc:                      # noqa: BLE001 - any failure of the new entry point falls back to the measured path
+                e2e_api, e2e_check = "calls", "ptd_frame_host failed its self-check (%s): not used" % str(exc)[:200]
+        if e2e_api == "fused":
             def e2e_step(k, reset):
                 capi.check(L.ptd_frame_host(pt.h, dn.h, cams[k].ctypes.data, 1, 1 if reset else 0, C.c_void_p(host_g.data_ptr()), C.c_void_p(host_rgb.data_ptr())), "ptd_frame_host")
             h2d, d2h = 84, 52 * P                        # the camera record in, G-buffer + frame out
@@ -433,8 +449,11 @@ def main():
                       "strip_rows_rank0": list(pipe.dn_rows)},
            "gpu_launches": launches_per_step * args.steps,
            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
-                   "api": ("ptd_frame_host" if args.e2e == "fused" else "ptd_pt_render_host + ptd_dn_forward_host") if world == 1 else "ptd_pt_render + ptd_dn_forward per strip, frame rows read back to pinned host memory"},
+                   "api": ("ptd_frame_host (one blocking call per frame: camera in, G-buffer + denoised frame out to host memory)" if e2e_api == "fused" else "ptd_pt_render_host + ptd_dn_forward_host") if world == 1
+                          else "ptd_pt_render + ptd_dn_forward per strip, frame rows read back to pinned host memory"},
            "roofline": roof, "clocks": clocks}
+    if world == 1 and e2e_check:
+        out["e2e"]["self_check"] = e2e_check
     if replicas:
         out["replicas"] = replicas
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
