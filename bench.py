@@ -168,6 +168,33 @@ def run_reference(args, W, H, config):
                       "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
 
 
+def run_autotune(args):
+    """Opt-in code paths that were written after round 1's GPU budget was spent are switched on for this run only if,
+    on THIS box and on the bench workload, tools/selfcheck.py finds them bit-identical to the default path and at least 3 % faster.
+    Each check runs in its own process under a timeout, before this process touches the GPU: a fault or a hang in an opt-in costs its
+    gain, never the benchmark.  Returns {feature: outcome} for the JSON line."""
+    out = {}
+    for feature, var in (("ray_sort", "PTD_PT_RAY_SORT"), ("wide_lookback", "PTD_PT_WIDE_LOOKBACK"), ("pdl", "PTD_DN_PDL")):
+        if var in os.environ:                                            # the caller decided
+            out[feature] = {"used": os.environ[var] not in ("", "0"), "why": "%s set by the caller" % var}
+            continue
+        try:
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "selfcheck.py"), feature, "--config", args.config, "--mode", args.mode],
+                               capture_output=True, text=True, timeout=150)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode != 0 or not line:
+                out[feature] = {"used": False, "why": "self-check failed (rc %d): %s" % (r.returncode, (r.stderr or r.stdout).strip()[-200:])}
+                continue
+            d = json.loads(line[-1])
+            use = bool(d["ok"]) and d["feat_ms"] < 0.97 * d["base_ms"]
+            out[feature] = {"used": use, "bit_identical": bool(d["ok"]), "base_ms": d["base_ms"], "feat_ms": d["feat_ms"]}
+            if use:
+                os.environ[var] = "1"
+        except Exception as exc:                                         # noqa: BLE001 - timeout, missing file, bad JSON: the opt-in stays off
+            out[feature] = {"used": False, "why": "self-check did not finish: %s" % str(exc)[:200]}
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -182,6 +209,7 @@ def main():
     ap.add_argument("--e2e", default="auto", choices=["auto", "calls", "fused"], help="host-pointer API of the e2e leg at N = 1: the reference's two call sites "
                     "(ptd_pt_render_host + ptd_dn_forward_host), the one-call frame (ptd_frame_host: the G-buffer is downloaded but never uploaded again), "
                     "or auto = the one-call frame if - and only if - it reproduces the two-call path bit for bit on this box, else the two calls")
+    ap.add_argument("--no-autotune", action="store_true", help="do not try the opt-in code paths (tools/selfcheck.py); N = 1 only")
     ap.add_argument("--no-pipeline", action="store_true", help="serial frame loop (path trace, then denoise, on one stream) instead of the two-stream loop")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -191,11 +219,15 @@ def main():
         args.warmup = min(args.warmup, 1)
         return run_reference(args, W, H, args.config)
 
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    autotune = None
+    if world == 1 and not args.no_autotune and args.mode != "fp32":
+        autotune = run_autotune(args)
+
     import torch
     import torch.distributed as dist
     from ai_path_tracer_denoiser_b200 import capi, weights
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if capi.device_count() < 1:
@@ -454,6 +486,8 @@ def main():
            "roofline": roof, "clocks": clocks}
     if world == 1 and e2e_check:
         out["e2e"]["self_check"] = e2e_check
+    if autotune is not None:
+        out["config"]["autotune"] = autotune
     if replicas:
         out["replicas"] = replicas
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -9,7 +9,7 @@ TAG=${1:-r03a}; WHAT=${2:-single}; N=${3:-4}
 OUT=gpurun_out/$TAG
 mkdir -p "$OUT"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$OUT/gpu.csv" 2>&1
-B="--steps 100 --warmup 5 --no-cpu-baseline"
+B="--steps 100 --warmup 5 --no-cpu-baseline --no-autotune"      # explicit A/B runs below; the last single-GPU run is the plain default (autotune on)
 if [ "$WHAT" = single ]; then
   timeout 120 tools/microbench/umma_rate 2048 > "$OUT/umma_rate.txt" 2>&1; echo "umma_rate rc=$?"; head -40 "$OUT/umma_rate.txt"
   timeout 1200 python -m pytest tests -m gpu -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -4 "$OUT/pytest_gpu.log"
@@ -23,6 +23,8 @@ if [ "$WHAT" = single ]; then
   PTD_PT_WIDE_LOOKBACK=1 timeout 400 python bench.py $B > "$OUT/bench_wide_lookback.json" 2> "$OUT/bench_wide_lookback.err"; echo "wide look-back rc=$?"
   PTD_DN_PDL=1 timeout 400 python bench.py $B > "$OUT/bench_pdl.json" 2> "$OUT/bench_pdl.err"; echo "pdl rc=$?"
   PTD_DN_PDL=1 timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_pdl_serial.json" 2> "$OUT/bench_pdl_serial.err"
+  for f in ray_sort wide_lookback pdl; do timeout 200 python tools/selfcheck.py $f > "$OUT/selfcheck_$f.json" 2> "$OUT/selfcheck_$f.err"; echo "selfcheck $f rc=$?"; cat "$OUT/selfcheck_$f.json"; done
+  timeout 900 python bench.py > "$OUT/bench_plain_default.json" 2> "$OUT/bench_plain_default.err"; echo "plain default (autotune + e2e auto) rc=$?"
   timeout 400 python bench.py $B --e2e fused > "$OUT/bench_e2e_fused.json" 2> "$OUT/bench_e2e_fused.err"; echo "fused rc=$?"
   python - "$OUT" <<'PY'
 import glob, json, os, sys
