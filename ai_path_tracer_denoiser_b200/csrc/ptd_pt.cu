@@ -712,7 +712,7 @@ struct ptd_pt {
     int bvh_nodes = 0, bvh_leaves = 0, bvh_max_leaf = 0, bvh_max_depth = 0;
     bool wide_lookback = false;                              // PTD_PT_WIDE_LOOKBACK=1
     // PTD_PT_RAY_SORT
-    int bin_bits = 0, bin_refill = TR_REFILL, nbins = 0;
+    int bin_bits = 0, bin_refill = TR_REFILL, nbins = 0, bin_from = 2;   // bounce 1 is still origin-coherent by pixel order: binning starts at bounce 2
     ptd_aabb bin_box;
     unsigned* d_bin_keys = nullptr; int* d_bin_order = nullptr; int* d_bin_hist = nullptr;   // hist: [depth][nbins] inside d_ctl (zeroed with it)
 };
@@ -808,6 +808,7 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
         h->bin_bits = 4;                                                // 4096 cells x 8 octants = 32768 bins, ~28 rays per bin at 720p
         if (const char* e = getenv("PTD_PT_RAY_SORT_BITS")) { const int v = atoi(e); if (v >= 1 && v <= 5) h->bin_bits = v; }
         if (const char* e = getenv("PTD_PT_RAY_SORT_REFILL")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->bin_refill = v; }
+        if (const char* e = getenv("PTD_PT_RAY_SORT_FROM")) { const int v = atoi(e); if (v >= 1 && v <= 1023) h->bin_from = v; }
         h->nbins = 8 << (3 * h->bin_bits);
         h->ctl_bytes += (size_t)h->depth * h->nbins * 4;
         // cells over the box of everything a ray can start from: the mesh and the geoms
@@ -898,7 +899,7 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
         p.ticket = h->d_ticket + 2 * b; p.ticket2 = h->d_ticket + 2 * b + 1;
         p.isx = h->d_trace_isx ? h->d_trace_isx + (size_t)b * h->P : h->d_isx;
         if (b == 0) pt_trace<true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
-        else if (h->flags & PTD_PT_RAY_SORT) {
+        else if ((h->flags & PTD_PT_RAY_SORT) && b >= h->bin_from) {
             // bin the live rays of this bounce, then trace them in bin order (timed together with the trace kernel they serve)
             int* hist = h->d_bin_hist + (size_t)b * h->nbins;
             const int blocks = std::min((h->P + 255) / 256, 148 * 8);

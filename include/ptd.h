@@ -88,7 +88,8 @@ enum {
     PTD_PT_RAY_SORT = 32u,        /* per bounce >= 1, bin the live rays by (Morton cell of the origin, direction octant) and trace them in bin
                                      order: coherent warps for the BVH traversal.  Only the ORDER of tracing changes - every record stays in
                                      its slot, results are bit-identical.  Also switched on by the environment variable PTD_PT_RAY_SORT=1
-                                     (PTD_PT_RAY_SORT_BITS = cell bits per axis, 1..5; PTD_PT_RAY_SORT_REFILL = refill threshold)    */
+                                     (PTD_PT_RAY_SORT_BITS = cell bits per axis, 1..5; PTD_PT_RAY_SORT_REFILL = refill threshold; PTD_PT_RAY_SORT_FROM =
+                                     first binned bounce, default 2: bounce 1 is still origin-coherent by pixel order)    */
     PTD_PT_GATED_MAIL = 16u       /* row-strip mode: a one-warp gate kernel ahead of every pt_shade waits for the live-count mail of the
                                      strips above, so no shade block ever spins while holding an SM (needed when the path tracer and the
                                      denoiser of a strip run on two streams; see DESIGN.md section 4 "frame loop")            */

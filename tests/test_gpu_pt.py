@@ -215,6 +215,7 @@ def test_ray_sort_changes_nothing(bits, monkeypatch):
     the default scheduling, on a mesh scene (BVH) with the geoms in play too."""
     capi = _capi()
     monkeypatch.setenv("PTD_PT_RAY_SORT_BITS", str(bits))
+    monkeypatch.setenv("PTD_PT_RAY_SORT_FROM", "1")                    # bin every bounce after the camera rays (default: from bounce 2)
     monkeypatch.delenv("PTD_PT_RAY_SORT", raising=False)
     sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
     sc.set_resolution(160, 96)

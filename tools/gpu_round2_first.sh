@@ -18,6 +18,7 @@ if [ "$WHAT" = single ]; then
     set -- $cfg
     PTD_PT_RAY_SORT=1 PTD_PT_RAY_SORT_BITS=$1 PTD_PT_RAY_SORT_REFILL=$2 timeout 400 python bench.py $B > "$OUT/bench_raysort_b$1_r$2.json" 2> "$OUT/bench_raysort_b$1_r$2.err"; echo "raysort bits=$1 refill=$2 rc=$?"
   done
+  PTD_PT_RAY_SORT=1 PTD_PT_RAY_SORT_FROM=1 timeout 400 python bench.py $B > "$OUT/bench_raysort_from1.json" 2> "$OUT/bench_raysort_from1.err"
   PTD_PT_RAY_SORT=1 timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_raysort_serial.json" 2> "$OUT/bench_raysort_serial.err"
   timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_default_serial.json" 2> "$OUT/bench_default_serial.err"
   PTD_PT_WIDE_LOOKBACK=1 timeout 400 python bench.py $B > "$OUT/bench_wide_lookback.json" 2> "$OUT/bench_wide_lookback.err"; echo "wide look-back rc=$?"
