@@ -174,24 +174,38 @@ def run_autotune(args):
     Each check runs in its own process under a timeout, before this process touches the GPU: a fault or a hang in an opt-in costs its
     gain, never the benchmark.  Returns {feature: outcome} for the JSON line."""
     out = {}
-    for feature, var in (("ray_sort", "PTD_PT_RAY_SORT"), ("wide_lookback", "PTD_PT_WIDE_LOOKBACK"), ("pdl", "PTD_DN_PDL")):
+    features = (("ray_sort", "PTD_PT_RAY_SORT", [{}, {"PTD_PT_RAY_SORT_REFILL": "8"}, {"PTD_PT_RAY_SORT_FROM": "1"}]),     # knob variants tried once the plain one passed
+                ("wide_lookback", "PTD_PT_WIDE_LOOKBACK", [{}]), ("pdl", "PTD_DN_PDL", [{}]))
+    for feature, var, variants in features:
         if var in os.environ:                                            # the caller decided
             out[feature] = {"used": os.environ[var] not in ("", "0"), "why": "%s set by the caller" % var}
             continue
-        try:
-            r = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "selfcheck.py"), feature, "--config", args.config, "--mode", args.mode],
-                               capture_output=True, text=True, timeout=150)
-            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
-            if r.returncode != 0 or not line:
-                out[feature] = {"used": False, "why": "self-check failed (rc %d): %s" % (r.returncode, (r.stderr or r.stdout).strip()[-200:])}
-                continue
-            d = json.loads(line[-1])
-            use = bool(d["ok"]) and d["feat_ms"] < 0.97 * d["base_ms"]
-            out[feature] = {"used": use, "bit_identical": bool(d["ok"]), "base_ms": d["base_ms"], "feat_ms": d["feat_ms"]}
-            if use:
-                os.environ[var] = "1"
-        except Exception as exc:                                         # noqa: BLE001 - timeout, missing file, bad JSON: the opt-in stays off
-            out[feature] = {"used": False, "why": "self-check did not finish: %s" % str(exc)[:200]}
+        best, tried = None, []
+        for knobs in variants:
+            try:
+                cmd = [sys.executable, os.path.join(ROOT, "tools", "selfcheck.py"), feature, "--config", args.config, "--mode", args.mode]
+                for k, v in knobs.items():
+                    cmd += ["--env", "%s=%s" % (k, v)]
+                r = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
+                line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+                if r.returncode != 0 or not line:
+                    tried.append({"knobs": knobs, "why": "self-check failed (rc %d): %s" % (r.returncode, (r.stderr or r.stdout).strip()[-200:])})
+                    break                                                # a failing opt-in is not tried again with other knobs
+                d = json.loads(line[-1])
+                tried.append({"knobs": knobs, "bit_identical": bool(d["ok"]), "base_ms": d["base_ms"], "feat_ms": d["feat_ms"]})
+                if not d["ok"]:
+                    break
+                if d["feat_ms"] < 0.97 * d["base_ms"] and (best is None or d["feat_ms"] / d["base_ms"] < best[0]):
+                    best = (d["feat_ms"] / d["base_ms"], knobs)
+            except Exception as exc:                                     # noqa: BLE001 - timeout, missing file, bad JSON: the opt-in stays off
+                tried.append({"knobs": knobs, "why": "self-check did not finish: %s" % str(exc)[:200]})
+                break
+        ok_all = all(t.get("bit_identical") for t in tried)
+        out[feature] = {"used": bool(best) and ok_all, "tried": tried}
+        if best and ok_all:
+            os.environ[var] = "1"
+            os.environ.update(best[1])
+            out[feature]["knobs"] = best[1]
     return out
 
 

@@ -29,7 +29,9 @@ def main():
     ap.add_argument("--config", default="C3")
     ap.add_argument("--mode", default="f16", choices=["tf32", "f16", "3xtf32"])
     ap.add_argument("--frames", type=int, default=12)
+    ap.add_argument("--env", action="append", default=[], help="K=V set while the opt-in handle is created (tuning knobs of the feature)")
     args = ap.parse_args()
+    knobs = dict(kv.split("=", 1) for kv in args.env)
     import torch
     from ai_path_tracer_denoiser_b200 import capi, scenegen, weights
     if capi.device_count() < 1:
@@ -64,8 +66,11 @@ def main():
     if args.feature in ("ray_sort", "wide_lookback"):
         base = capi.PathTracer(sc)
         os.environ[var] = "1"
+        os.environ.update(knobs)
         feat = capi.PathTracer(sc)
         os.environ.pop(var, None)
+        for k in knobs:
+            os.environ.pop(k, None)
         ga = torch.zeros(10 * P, dtype=torch.float32, device="cuda")
         gb = torch.zeros(10 * P, dtype=torch.float32, device="cuda")
         ok = True
@@ -94,8 +99,11 @@ def main():
         torch.cuda.synchronize()
         base = capi.Denoiser(wfile, H, W, flags=flags)
         os.environ[var] = "1"
+        os.environ.update(knobs)
         feat = capi.Denoiser(wfile, H, W, flags=flags)
         os.environ.pop(var, None)
+        for k in knobs:
+            os.environ.pop(k, None)
         oa = torch.zeros(3 * P, dtype=torch.float32, device="cuda")
         ob = torch.zeros(3 * P, dtype=torch.float32, device="cuda")
         ok = True
@@ -109,7 +117,7 @@ def main():
         base_ms2 = timed(lambda k: base.forward(C.c_void_p(gs[k % 4].data_ptr()), C.c_void_p(oa.data_ptr()), False, stream=sptr), 3 * args.frames)
         detail["base_ms_again"] = base_ms2
         base_ms = min(base_ms, base_ms2)
-    print(json.dumps({"feature": args.feature, "switch": var, "ok": bool(ok), "base_ms": round(base_ms, 4), "feat_ms": round(feat_ms, 4), "detail": detail}))
+    print(json.dumps({"feature": args.feature, "switch": var, "ok": bool(ok), "base_ms": round(base_ms, 4), "feat_ms": round(feat_ms, 4), "knobs": knobs, "detail": detail}))
 
 
 if __name__ == "__main__":
