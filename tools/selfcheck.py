@@ -81,6 +81,8 @@ def main():
             same = bool(torch.equal(ga, gb)) and base.live_counts() == feat.live_counts()
             ok = ok and same
         detail["launches"] = [base.launches(), feat.launches()]
+        for k in (4, 5):                                               # the host-pointer entry point bench.py's e2e leg uses (its own streams)
+            ok = ok and base.render_host(cams[k]).tobytes() == feat.render_host(cams[k]).tobytes()
         base_ms = timed(lambda k: base.render(C.c_void_p(ga.data_ptr()), cam=cams[k], stream=sptr), args.frames)
         feat_ms = timed(lambda k: feat.render(C.c_void_p(gb.data_ptr()), cam=cams[k], stream=sptr), args.frames)
         base_ms2 = timed(lambda k: base.render(C.c_void_p(ga.data_ptr()), cam=cams[k], stream=sptr), args.frames)      # A-B-A: drift shows up here
@@ -112,6 +114,9 @@ def main():
             feat.forward(C.c_void_p(gs[k].data_ptr()), C.c_void_p(ob.data_ptr()), k == 0, stream=sptr)
             torch.cuda.synchronize()
             ok = ok and bool(torch.equal(oa, ob)) and bool(torch.isfinite(ob).all())
+        g_host = gs[0].cpu().numpy().reshape(10, H, W)                 # the host-pointer entry point bench.py's e2e leg uses (legacy default stream)
+        for k in range(2):
+            ok = ok and base.forward_host(g_host, reset=(k == 0)).tobytes() == feat.forward_host(g_host, reset=(k == 0)).tobytes()
         base_ms = timed(lambda k: base.forward(C.c_void_p(gs[k % 4].data_ptr()), C.c_void_p(oa.data_ptr()), False, stream=sptr), 3 * args.frames)
         feat_ms = timed(lambda k: feat.forward(C.c_void_p(gs[k % 4].data_ptr()), C.c_void_p(ob.data_ptr()), False, stream=sptr), 3 * args.frames)
         base_ms2 = timed(lambda k: base.forward(C.c_void_p(gs[k % 4].data_ptr()), C.c_void_p(oa.data_ptr()), False, stream=sptr), 3 * args.frames)
