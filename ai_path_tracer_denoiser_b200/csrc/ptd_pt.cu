@@ -60,6 +60,8 @@ struct PtKernelParams {
     // PTD_PT_RAY_SORT (appended: the offsets of everything above are what the default kernels were validated with)
     const int* order;               // order[k] = slot of the k-th ray in spatial-bin order (pt_trace<false, true> only)
     int refill;                     // refill threshold of the binned trace kernel
+    // pt_shade<.., .., true>: the survivors' bin keys and the next bounce's histogram are produced while the rays are still in registers
+    ptd_aabb bin_box; int bin_bits; unsigned* bin_keys; int* bin_hist_next;
 };
 
 using namespace ptm;
@@ -322,6 +324,19 @@ __global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKern
     }
 }
 
+// bin key of a ray for PTD_PT_RAY_SORT (see "coherent scheduling of the secondary rays" below): Morton cell of the origin | direction octant
+__device__ __forceinline__ unsigned ray_bin(const float* w, const ptd_aabb& box, int bits) {
+    const float cells = (float)(1 << bits);
+    const float fx = (w[0] - box.lb.x) / fmaxf(box.ub.x - box.lb.x, 1e-20f), fy = (w[1] - box.lb.y) / fmaxf(box.ub.y - box.lb.y, 1e-20f);
+    const float fz = (w[2] - box.lb.z) / fmaxf(box.ub.z - box.lb.z, 1e-20f);
+    const int mx = (1 << bits) - 1;
+    const unsigned cx = (unsigned)min(max((int)(fx * cells), 0), mx), cy = (unsigned)min(max((int)(fy * cells), 0), mx), cz = (unsigned)min(max((int)(fz * cells), 0), mx);
+    unsigned morton = 0;
+    for (int b = 0; b < bits; ++b) morton |= (((cx >> b) & 1u) << (3 * b)) | (((cy >> b) & 1u) << (3 * b + 1)) | (((cz >> b) & 1u) << (3 * b + 2));
+    const unsigned octant = (w[3] < 0.f ? 1u : 0u) | (w[4] < 0.f ? 2u : 0u) | (w[5] < 0.f ? 4u : 0u);
+    return (morton << 3) | octant;                                    // cell-major: concurrently running warps work in the same region
+}
+
 // ---- block-wide helpers -------------------------------------------------------------------------------------------
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long* p) {
     unsigned long long v;
@@ -336,7 +351,9 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
 // WIDE (PTD_PT_WIDE_LOOKBACK=1, opt-in): the decoupled look-back reads PT_BLOCK predecessor states per trip with the whole block
 // instead of 32 with one warp.  With ~300 tiles in flight the one-warp walk is ~10 dependent L2 round trips per tile while the other
 // 15 warps sit at the barrier (ncu: stall_barrier dominates pt_shade); one block-wide trip covers every tile in flight.
-template <bool FIRST, bool WIDE = false>
+// KEYS (PTD_PT_RAY_SORT, next bounce binned): every survivor's bin key is written at its compacted index and counted into the next
+// bounce's histogram here, where the new ray is still in registers - the separate ray_bin_hist pass (a 40 MB re-read) is not needed.
+template <bool FIRST, bool WIDE = false, bool KEYS = false>
 __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
     __shared__ __align__(16) uint32_t s_words[PT_BLOCK * PT_WORDS];                  // 5632 B staging (loads, then compacted stores)
     __shared__ __align__(16) uint32_t s_isx[PT_BLOCK * 9];                           // 4608 B: the tile's ShadeableIntersections
@@ -571,6 +588,12 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
         const int nwords = block_kept * PT_WORDS;
         for (int i = tid; i < nwords; i += PT_BLOCK) dst[i] = s_words[i];               // contiguous, 128 B per warp store
     }
+    if (KEYS && keep) {
+        const float w6[6] = {ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z};
+        const unsigned k = ray_bin(w6, p.bin_box, p.bin_bits);
+        p.bin_keys[excl + local_rank] = k;
+        atomicAdd(&p.bin_hist_next[k], 1);
+    }
     if (p.dead && active && !keep) {
         // rejected items end up behind the survivors in REVERSE order (thrust CUDA back end) and are never moved again
         const int rej_before = base - excl + (tid - local_rank);
@@ -587,17 +610,6 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
 // slot INDICES - histogram, exclusive scan, scatter - and the trace kernel takes its rays in bin order (p.order).  Only the order
 // in which rays are TRACED changes: every ShadeableIntersection is still written to its ray's own slot, so the PathSegment arrays,
 // the compaction and the RNG indices - everything the parity tests compare - are untouched.
-__device__ __forceinline__ unsigned ray_bin(const float* w, const ptd_aabb& box, int bits) {
-    const float cells = (float)(1 << bits);
-    const float fx = (w[0] - box.lb.x) / fmaxf(box.ub.x - box.lb.x, 1e-20f), fy = (w[1] - box.lb.y) / fmaxf(box.ub.y - box.lb.y, 1e-20f);
-    const float fz = (w[2] - box.lb.z) / fmaxf(box.ub.z - box.lb.z, 1e-20f);
-    const int mx = (1 << bits) - 1;
-    const unsigned cx = (unsigned)min(max((int)(fx * cells), 0), mx), cy = (unsigned)min(max((int)(fy * cells), 0), mx), cz = (unsigned)min(max((int)(fz * cells), 0), mx);
-    unsigned morton = 0;
-    for (int b = 0; b < bits; ++b) morton |= (((cx >> b) & 1u) << (3 * b)) | (((cy >> b) & 1u) << (3 * b + 1)) | (((cz >> b) & 1u) << (3 * b + 2));
-    const unsigned octant = (w[3] < 0.f ? 1u : 0u) | (w[4] < 0.f ? 2u : 0u) | (w[5] < 0.f ? 4u : 0u);
-    return (morton << 3) | octant;                                    // cell-major: concurrently running warps work in the same region
-}
 __global__ void ray_bin_hist(const ptd_path_segment* __restrict__ paths, const int* __restrict__ count, ptd_aabb box, int bits,
                              unsigned* __restrict__ keys, int* __restrict__ hist) {
     const int n = *count;
@@ -712,6 +724,7 @@ struct ptd_pt {
     int bvh_nodes = 0, bvh_leaves = 0, bvh_max_leaf = 0, bvh_max_depth = 0;
     bool wide_lookback = false;                              // PTD_PT_WIDE_LOOKBACK=1
     // PTD_PT_RAY_SORT
+    bool bin_fused = true;
     int bin_bits = 0, bin_refill = TR_REFILL, nbins = 0, bin_from = 2;   // bounce 1 is still origin-coherent by pixel order: binning starts at bounce 2
     ptd_aabb bin_box;
     unsigned* d_bin_keys = nullptr; int* d_bin_order = nullptr; int* d_bin_hist = nullptr;   // hist: [depth][nbins] inside d_ctl (zeroed with it)
@@ -808,6 +821,7 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
         h->bin_bits = 4;                                                // 4096 cells x 8 octants = 32768 bins, ~28 rays per bin at 720p
         if (const char* e = getenv("PTD_PT_RAY_SORT_BITS")) { const int v = atoi(e); if (v >= 1 && v <= 5) h->bin_bits = v; }
         if (const char* e = getenv("PTD_PT_RAY_SORT_REFILL")) { const int v = atoi(e); if (v >= 1 && v <= 32) h->bin_refill = v; }
+        if (const char* e = getenv("PTD_PT_RAY_SORT_UNFUSED")) h->bin_fused = !(atoi(e) > 0);
         if (const char* e = getenv("PTD_PT_RAY_SORT_FROM")) { const int v = atoi(e); if (v >= 1 && v <= 1023) h->bin_from = v; }
         h->nbins = 8 << (3 * h->bin_bits);
         h->ctl_bytes += (size_t)h->depth * h->nbins * 4;
@@ -879,6 +893,8 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
     p.sort_keys = h->d_keys; p.trace_paths = h->d_trace_paths;
     const size_t smem = p.geoms_in_smem ? (sizeof(ptd_geom) + sizeof(ptd_aabb)) * h->ngeoms : 0;
     const bool sort = (h->flags & PTD_PT_SORT_MATERIAL) != 0;
+    // keys are written at compacted indices by pt_shade unless a material sort permutes the paths afterwards (or PTD_PT_RAY_SORT_UNFUSED=1)
+    const bool bin_fused = !sort && h->bin_fused;
     auto mark = [&]() {
         if (!h->profiling) return;
         if ((int)h->events.size() <= h->nmark) { cudaEvent_t e; cudaEventCreate(&e); h->events.push_back(e); }
@@ -903,12 +919,15 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
             // bin the live rays of this bounce, then trace them in bin order (timed together with the trace kernel they serve)
             int* hist = h->d_bin_hist + (size_t)b * h->nbins;
             const int blocks = std::min((h->P + 255) / 256, 148 * 8);
-            ray_bin_hist<<<blocks, 256, 0, st>>>(p.src, h->d_counts + b, h->bin_box, h->bin_bits, h->d_bin_keys, hist);
+            if (!bin_fused) {                                           // else bounce b - 1's pt_shade wrote the keys and this histogram (b >= bin_from >= 1)
+                ray_bin_hist<<<blocks, 256, 0, st>>>(p.src, h->d_counts + b, h->bin_box, h->bin_bits, h->d_bin_keys, hist);
+                h->launches += 1;
+            }
             sort_scan<<<1, 1024, 0, st>>>(hist, h->nbins);
             ray_bin_scatter<<<blocks, 256, 0, st>>>(h->d_bin_keys, h->d_counts + b, hist, h->d_bin_order);
             p.order = h->d_bin_order; p.refill = h->bin_refill;
             pt_trace<false, true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
-            h->launches += 3;
+            h->launches += 2;
         }
         else pt_trace<false><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
         mark();
@@ -916,7 +935,16 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
             pt_mail_gate<<<1, 32, 0, st>>>(h->d_mail, b, h->rank, h->epoch);
             h->launches += 1;
         }
-        if (h->wide_lookback) {
+        // the next bounce is binned: this pt_shade also writes its survivors' keys and the next histogram
+        const bool keys = bin_fused && (h->flags & PTD_PT_RAY_SORT) && b + 1 >= h->bin_from && b + 1 < h->depth;
+        if (keys) { p.bin_box = h->bin_box; p.bin_bits = h->bin_bits; p.bin_keys = h->d_bin_keys; p.bin_hist_next = h->d_bin_hist + (size_t)(b + 1) * h->nbins; }
+        if (keys && h->wide_lookback) {
+            if (b == 0) pt_shade<true, true, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+            else pt_shade<false, true, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+        } else if (keys) {
+            if (b == 0) pt_shade<true, false, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+            else pt_shade<false, false, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+        } else if (h->wide_lookback) {
             if (b == 0) pt_shade<true, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
             else pt_shade<false, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
         }

@@ -208,14 +208,15 @@ def test_row_strips_equal_the_full_frame(scene, W, H, n):
         _same(cat, full.dump_paths(b), "bounce %d paths (strips concatenated)" % b)
 
 
-@pytest.mark.parametrize("bits", [4, 2], ids=["experimental-ray-sort-4bit", "experimental-ray-sort-2bit"])
-def test_ray_sort_changes_nothing(bits, monkeypatch):
+@pytest.mark.parametrize("bits,unfused", [(4, "0"), (2, "0"), (4, "1")], ids=["experimental-ray-sort-4bit", "experimental-ray-sort-2bit", "experimental-ray-sort-unfused"])
+def test_ray_sort_changes_nothing(bits, unfused, monkeypatch):
     """PTD_PT_RAY_SORT (opt-in): rays are TRACED in (origin cell, direction octant) bin order, every record stays in its slot -
     PathSegments, ShadeableIntersections, live counts, the final partition layout and the G-buffer must all be bit-identical to
     the default scheduling, on a mesh scene (BVH) with the geoms in play too."""
     capi = _capi()
     monkeypatch.setenv("PTD_PT_RAY_SORT_BITS", str(bits))
     monkeypatch.setenv("PTD_PT_RAY_SORT_FROM", "1")                    # bin every bounce after the camera rays (default: from bounce 2)
+    monkeypatch.setenv("PTD_PT_RAY_SORT_UNFUSED", unfused)             # 0: pt_shade writes the keys / histogram; 1: separate ray_bin_hist pass
     monkeypatch.delenv("PTD_PT_RAY_SORT", raising=False)
     sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
     sc.set_resolution(160, 96)
@@ -232,7 +233,7 @@ def test_ray_sort_changes_nothing(bits, monkeypatch):
         _same(pa, pb, "bounce %d paths" % k)
         _same(ia, ib, "bounce %d intersections" % k)
     _same(a[3], b[3], "final partition layout")
-    assert b[4] == a[4] + 3 * (sc.counts()[3] - 1)                # three binning kernels per bounce >= 1
+    assert b[4] == a[4] + (3 if unfused == "1" else 2) * (sc.counts()[3] - 1)   # scan + scatter (+ the key pass when not fused) per bounce >= 1
 
 
 @pytest.mark.parametrize("res", [(160, 96), (800, 600)], ids=["experimental-wide-lookback-30tiles", "experimental-wide-lookback-938tiles"])
