@@ -272,3 +272,17 @@ def test_cli_surface_and_error_behaviour_without_a_gpu(tmp_path):
     if capi.device_count() == 0:
         r = subprocess.run([cli, os.path.join(SCENES, "cornell_64x48.txt"), "--frames", "1"], capture_output=True, text=True)
         assert r.returncode == 2 and "no CPU fallback" in r.stdout + r.stderr
+
+
+def test_python_constants_match_the_header():
+    """capi.py mirrors include/ptd.h by hand: every flag / mode / status value must agree with the header's enums."""
+    hdr = open(os.path.join(ROOT, "include", "ptd.h")).read()
+    vals = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(PTD_[A-Z0-9_]+)\s*=\s*(-?\d+)u?\b", hdr)}
+    pairs = {"PTD_PT_SORT_MATERIAL": capi.PT_SORT_MATERIAL, "PTD_PT_TRACE": capi.PT_TRACE, "PTD_PT_NO_BVH": capi.PT_NO_BVH,
+             "PTD_PT_KEEP_TERMINATED": capi.PT_KEEP_TERMINATED, "PTD_PT_GATED_MAIL": capi.PT_GATED_MAIL, "PTD_PT_RAY_SORT": capi.PT_RAY_SORT,
+             "PTD_DN_FP32": capi.DN_FP32, "PTD_DN_TF32": capi.DN_TF32, "PTD_DN_3XTF32": capi.DN_3XTF32, "PTD_DN_F16": capi.DN_F16,
+             "PTD_DN_FP32_BATCH_STATS": capi.DN_FP32_BATCH_STATS}
+    for name, py in pairs.items():
+        assert vals[name] == py, name
+    pt_flags = [v for k, v in vals.items() if k.startswith("PTD_PT_")]
+    assert len(set(pt_flags)) == len(pt_flags) and all(v & (v - 1) == 0 for v in pt_flags)       # distinct single bits
