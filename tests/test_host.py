@@ -277,7 +277,7 @@ def test_cli_surface_and_error_behaviour_without_a_gpu(tmp_path):
 def test_python_constants_match_the_header():
     """capi.py mirrors include/ptd.h by hand: every flag / mode / status value must agree with the header's enums."""
     hdr = open(os.path.join(ROOT, "include", "ptd.h")).read()
-    vals = {m.group(1): int(m.group(2)) for m in re.finditer(r"\b(PTD_[A-Z0-9_]+)\s*=\s*(-?\d+)u?\b", hdr)}
+    vals = {m.group(1): int(m.group(2)) for m in re.finditer(r"^\s*(PTD_[A-Z0-9_]+) = (-?\d+)u?[, ]", hdr, re.M)}      # enumerator lines only
     pairs = {"PTD_PT_SORT_MATERIAL": capi.PT_SORT_MATERIAL, "PTD_PT_TRACE": capi.PT_TRACE, "PTD_PT_NO_BVH": capi.PT_NO_BVH,
              "PTD_PT_KEEP_TERMINATED": capi.PT_KEEP_TERMINATED, "PTD_PT_GATED_MAIL": capi.PT_GATED_MAIL, "PTD_PT_RAY_SORT": capi.PT_RAY_SORT,
              "PTD_DN_FP32": capi.DN_FP32, "PTD_DN_TF32": capi.DN_TF32, "PTD_DN_3XTF32": capi.DN_3XTF32, "PTD_DN_F16": capi.DN_F16,
