@@ -5,7 +5,7 @@ Semantics frozen by SURVEY.md decisions D1/D3: eval-mode BatchNorm (test.py:35),
 frames and zeroed when `reset` (forward(x, j) with j == 0, model.py:121-128), input zero-padded bottom/right
 to a multiple of 32 and the output cropped.
 
-Pinned by tests/test_oracle_dn.py against tests/golden/dn_*.npz, which tools/make_golden_dn.py produced by
+Pinned by tests/test_oracle_dn.py against tests/golden/dn_*.npz, which tests/tools/make_golden_dn.py produced by
 importing the reference's own AutoEncoder from /root/reference/training (same weights, same inputs).
 Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may import this.
 """

@@ -7,7 +7,7 @@
  *
  * Pinned (tests/test_oracle_pt.py) against oracle/_ref's ref_cpu_render() -- the reference's own
  * __host__ __device__ functions compiled as host code -- bit for bit on the committed scenes, and
- * against the golden vectors under tests/golden/ produced by tools/make_golden_pt.py.
+ * against the golden vectors under tests/golden/ produced by tests/tools/make_golden_pt.py.
  *
  * Build: gcc -O2 -ffp-contract=off -fopenmp -shared -fPIC pt_oracle.c -lm   (no FMA contraction:
  * x86-64 host code of the reference is compiled without FMA as well).

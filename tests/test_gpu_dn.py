@@ -1,13 +1,13 @@
 """GPU parity tests of the denoiser hot path (HP-2), through the C ABI (libptd.so).
 
-Checkers: tests/golden/dn_*.npz (outputs of the reference's own AutoEncoder, tools/make_golden_dn.py) and
+Checkers: tests/golden/dn_*.npz (outputs of the reference's own AutoEncoder, tests/tools/make_golden_dn.py) and
 oracle/dn_oracle.py (pinned against the same golden files) on further seeded inputs.
 Stated tolerances (outputs are O(1)):
   PTD_DN_FP32  (FFMA convs)                 max-abs <= 1e-4, rel-L2 <= 1e-5   - fp32 re-association only
   PTD_DN_TF32  (tcgen05 kind::tf32 convs)   max-abs <= 2e-2, rel-L2 <= 5e-3   - 10-bit-mantissa operands, fp32 accumulate
                                             (what libtorch itself does for convs on Ampere+ with cudnn.allow_tf32 = True)
   PTD_DN_3XTF32 (hi/lo split operands)      max-abs <= 3e-4, rel-L2 <= 1e-4   - hi*hi + hi*lo + lo*hi on the tensor cores, fp32 accumulate
-                                            (measured 3.4e-5 / 1.0e-5: ~80x tighter than tf32, ~10x looser than FFMA - tools/dn_accuracy.py)
+                                            (measured 3.4e-5 / 1.0e-5: ~80x tighter than tf32, ~10x looser than FFMA - tests/tools/dn_accuracy.py)
   PTD_DN_F16   (fp16 storage, kind::f16)    same bound: fp16 has the same 10-bit mantissa, fp32 accumulate, fp32 output frame
 """
 import os

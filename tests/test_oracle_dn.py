@@ -1,5 +1,5 @@
 """CPU tests: the denoiser oracle (oracle/dn_oracle.py) against golden outputs of the reference's own
-AutoEncoder (tools/make_golden_dn.py), plus the weight container round trip."""
+AutoEncoder (tests/tools/make_golden_dn.py), plus the weight container round trip."""
 import os
 
 import numpy as np
@@ -27,7 +27,7 @@ def test_oracle_matches_reference_model_golden(name):
 def test_oracle_batch_stats_mode_matches_reference_in_training_mode():
     """the module traced by convert_to_torchscript.py:26-30 is never put in eval mode - BatchNorm normalises with the
     statistics of its current input and j == 0 zeroes the hidden state on every call.  Golden = the reference AutoEncoder in
-    train() mode (tools/make_golden_dn.py); it must differ from the eval-mode forward, or the mode would be untested."""
+    train() mode (tests/tools/make_golden_dn.py); it must differ from the eval-mode forward, or the mode would be untested."""
     g = np.load(os.path.join(GOLDEN, "dn_traced_96x160.npz"))
     sd = weights.synthetic_state_dict(1234)
     O = DenoiserOracle(sd, batch_stats=True)

@@ -1,5 +1,5 @@
 """CPU tests: the plain-C path-trace oracle (oracle/pt_oracle.c) against the golden vectors produced from the
-reference's own host/device functions (tools/make_golden_pt.py), the survey's known-answer vectors, and -
+reference's own host/device functions (tests/tools/make_golden_pt.py), the survey's known-answer vectors, and -
 when oracle/_ref is present - the reference build itself on further seeded cases.  Bit-exact throughout."""
 import ctypes as C
 import glob

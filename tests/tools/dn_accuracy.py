@@ -6,7 +6,7 @@ import tempfile
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 from ai_path_tracer_denoiser_b200 import capi, weights  # noqa: E402
 from oracle.dn_oracle import DenoiserOracle, synthetic_gbuffer  # noqa: E402
