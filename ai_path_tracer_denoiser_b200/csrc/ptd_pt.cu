@@ -62,6 +62,7 @@ struct PtKernelParams {
     int refill;                     // refill threshold of the binned trace kernel
     // pt_shade<.., .., true>: the survivors' bin keys and the next bounce's histogram are produced while the rays are still in registers
     ptd_aabb bin_box; int bin_bits; unsigned* bin_keys; int* bin_hist_next;
+    int sstack_off;                 // pt_trace<.., .., true>: byte offset of the shared-memory traversal stacks inside the dynamic shared memory
 };
 
 using namespace ptm;
@@ -144,10 +145,18 @@ __device__ __forceinline__ void write_miss(const TraceOut& o, int idx) {
     }
 }
 
-template <bool FIRST, bool BINNED = false>
+// SSTACK (PTD_PT_SMEM_STACK=1, opt-in): the first TR_SSTACK entries of every lane's traversal stack live in shared memory, laid out
+// [entry][thread] so that a warp's push / pop is one conflict-free shared-memory access whatever the lanes' stack depths are.  In local
+// memory the same push / pop touches one 128-byte line per distinct depth in the warp (~7 L1 wavefronts) - about 15 % of pt_trace's L1
+// traffic.  The host probe sees at most 14 live entries on C3; deeper entries fall back to the local array.
+#define TR_SSTACK 16
+#define TR_PUSH(v) do { ++sp; if (SSTACK && sp < TR_SSTACK) s_stack[sp * TR_BLOCK + tid] = (v); else stack[sp] = (v); } while (0)
+#define TR_POP() ((SSTACK && sp < TR_SSTACK) ? s_stack[(sp--) * TR_BLOCK + tid] : stack[sp--])
+template <bool FIRST, bool BINNED = false, bool SSTACK = false>
 __global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKernelParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ptd_geom* s_geoms = reinterpret_cast<ptd_geom*>(smem_raw);
+    int* s_stack = SSTACK ? reinterpret_cast<int*>(smem_raw + p.sstack_off) : nullptr;
     const unsigned FULL = 0xffffffffu;
     const int tid = threadIdx.x, lane = tid & 31;
     const int n = FIRST ? p.P : p.counts[p.bounce];
@@ -223,7 +232,8 @@ __global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKern
                             idirx = rix; idiry = riy; idirz = riz;
                             oodx = ray.o.x * idirx; oody = ray.o.y * idiry; oodz = ray.o.z * idirz;
                             nearx = idirx < 0.0f; neary = idiry < 0.0f; nearz = idirz < 0.0f;     // 0: the lo plane is entered first, 1: the hi plane
-                            stack[0] = PT_SENTINEL; sp = 0; node = 0;
+                            if (SSTACK) s_stack[tid] = PT_SENTINEL; else stack[0] = PT_SENTINEL;
+                            sp = 0; node = 0;
                         } else {                                                       // PTD_PT_NO_BVH: the reference's loop, test aid
                             for (int f = 0; f < p.nfaces; ++f) {
                                 const ptd_face* fc = &p.faces[f];
@@ -273,14 +283,14 @@ __global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKern
                     PT_CSWAP(d0, c0, d1, c1) PT_CSWAP(d2, c2, d3, c3) PT_CSWAP(d0, c0, d2, c2) PT_CSWAP(d1, c1, d3, c3) PT_CSWAP(d1, c1, d2, c2)
 #undef PT_CSWAP
                     // the nearest hit child is visited next, the others wait on the stack, farthest at the bottom
-                    if (d3 < FLT_MAX) stack[++sp] = c3;
-                    if (d2 < FLT_MAX) stack[++sp] = c2;
-                    if (d1 < FLT_MAX) stack[++sp] = c1;
-                    node = d0 < FLT_MAX ? c0 : stack[sp--];
+                    if (d3 < FLT_MAX) TR_PUSH(c3);
+                    if (d2 < FLT_MAX) TR_PUSH(c2);
+                    if (d1 < FLT_MAX) TR_PUSH(c1);
+                    if (d0 < FLT_MAX) node = c0; else node = TR_POP();
                     if (node < 0 && leaf >= 0) {            // first leaf found: postpone it and keep walking (speculatively)
                         searching = false;
                         leaf = node;
-                        node = stack[sp--];
+                        node = TR_POP();
                     }
                 }
             }
@@ -298,7 +308,7 @@ __global__ void __launch_bounds__(TR_BLOCK, TR_MIN_BLOCKS) pt_trace(const PtKern
                     if (++tri == tri_end) {
                         leaf = node;                        // a second leaf may be waiting in `node`
                         if (node < 0) {
-                            node = stack[sp--];
+                            node = TR_POP();
                             const int code = ~leaf; tri = code >> 4; tri_end = tri + (code & 15) + 1;
                         }
                     }
@@ -723,6 +733,7 @@ struct ptd_pt {
     int timed_launches = 0;
     int bvh_nodes = 0, bvh_leaves = 0, bvh_max_leaf = 0, bvh_max_depth = 0;
     bool wide_lookback = false;                              // PTD_PT_WIDE_LOOKBACK=1
+    bool smem_stack = false;                                 // PTD_PT_SMEM_STACK=1
     // PTD_PT_RAY_SORT
     bool bin_fused = true;
     int bin_bits = 0, bin_refill = TR_REFILL, nbins = 0, bin_from = 2;   // bounce 1 is still origin-coherent by pixel order: binning starts at bounce 2
@@ -777,6 +788,7 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
     if (!(sc->faces.size() > 0) || (flags & PTD_PT_NO_BVH)) flags &= ~(unsigned)PTD_PT_RAY_SORT;      // binning only pays for BVH traversal
     h->device = device; h->flags = flags;
     if (const char* e = getenv("PTD_PT_WIDE_LOOKBACK")) h->wide_lookback = atoi(e) > 0;
+    if (const char* e = getenv("PTD_PT_SMEM_STACK")) h->smem_stack = atoi(e) > 0;
     h->cam = sc->camera; h->mesh_box = sc->mesh_box;
     h->W = sc->camera.res_x; h->H = sc->camera.res_y; h->Pfull = h->W * h->H; h->depth = sc->trace_depth;
     h->row0 = row0; h->rows = rows; h->P = h->W * rows;
@@ -856,7 +868,9 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
     {
         int sms = 148, per_sm = 8;
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pt_trace<false>, TR_BLOCK, (sizeof(ptd_geom) + sizeof(ptd_aabb)) * std::min(h->ngeoms, 64));
+        const size_t geom_smem = (sizeof(ptd_geom) + sizeof(ptd_aabb)) * std::min(h->ngeoms, 64);
+        if (h->smem_stack) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pt_trace<false, false, true>, TR_BLOCK, ((geom_smem + 15) & ~(size_t)15) + TR_SSTACK * TR_BLOCK * 4);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pt_trace<false>, TR_BLOCK, geom_smem);
         if (const char* e = getenv("PTD_TRACE_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // tuning knob: leave room for a concurrent kernel
         h->trace_blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (h->P + TR_BLOCK - 1) / TR_BLOCK));   // persistent: every resident warp pulls rays
     }
@@ -891,7 +905,8 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
     for (int r = 0; r < PT_MAX_RANKS; ++r) p.peer_mail[r] = h->peer_mail[r];
     p.counts = h->d_counts; p.gbuf = gbuf; p.image = h->d_image; p.dead = h->d_dead;
     p.sort_keys = h->d_keys; p.trace_paths = h->d_trace_paths;
-    const size_t smem = p.geoms_in_smem ? (sizeof(ptd_geom) + sizeof(ptd_aabb)) * h->ngeoms : 0;
+    size_t smem = p.geoms_in_smem ? (sizeof(ptd_geom) + sizeof(ptd_aabb)) * h->ngeoms : 0;
+    if (h->smem_stack) { p.sstack_off = (int)((smem + 15) & ~(size_t)15); smem = (size_t)p.sstack_off + TR_SSTACK * TR_BLOCK * 4; }
     const bool sort = (h->flags & PTD_PT_SORT_MATERIAL) != 0;
     // keys are written at compacted indices by pt_shade unless a material sort permutes the paths afterwards (or PTD_PT_RAY_SORT_UNFUSED=1)
     const bool bin_fused = !sort && h->bin_fused;
@@ -914,7 +929,10 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
         p.status = h->d_status + (size_t)b * h->ntiles;
         p.ticket = h->d_ticket + 2 * b; p.ticket2 = h->d_ticket + 2 * b + 1;
         p.isx = h->d_trace_isx ? h->d_trace_isx + (size_t)b * h->P : h->d_isx;
-        if (b == 0) pt_trace<true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+        if (b == 0) {
+            if (h->smem_stack) pt_trace<true, false, true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+            else pt_trace<true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+        }
         else if ((h->flags & PTD_PT_RAY_SORT) && b >= h->bin_from) {
             // bin the live rays of this bounce, then trace them in bin order (timed together with the trace kernel they serve)
             int* hist = h->d_bin_hist + (size_t)b * h->nbins;
@@ -926,9 +944,11 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
             sort_scan<<<1, 1024, 0, st>>>(hist, h->nbins);
             ray_bin_scatter<<<blocks, 256, 0, st>>>(h->d_bin_keys, h->d_counts + b, hist, h->d_bin_order);
             p.order = h->d_bin_order; p.refill = h->bin_refill;
-            pt_trace<false, true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+            if (h->smem_stack) pt_trace<false, true, true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+            else pt_trace<false, true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
             h->launches += 2;
         }
+        else if (h->smem_stack) pt_trace<false, false, true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
         else pt_trace<false><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
         mark();
         if (b > 0 && h->rank > 0 && (h->flags & PTD_PT_GATED_MAIL)) {     // (timed together with the shade kernel it gates)

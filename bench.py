@@ -175,7 +175,7 @@ def run_autotune(args):
     gain, never the benchmark.  Returns {feature: outcome} for the JSON line."""
     out = {}
     features = (("ray_sort", "PTD_PT_RAY_SORT", [{}, {"PTD_PT_RAY_SORT_REFILL": "8"}, {"PTD_PT_RAY_SORT_FROM": "1"}]),     # knob variants tried once the plain one passed
-                ("wide_lookback", "PTD_PT_WIDE_LOOKBACK", [{}]), ("pdl", "PTD_DN_PDL", [{}]))
+                ("wide_lookback", "PTD_PT_WIDE_LOOKBACK", [{}]), ("smem_stack", "PTD_PT_SMEM_STACK", [{}]), ("pdl", "PTD_DN_PDL", [{}]))
     for feature, var, variants in features:
         if var in os.environ:                                            # the caller decided
             out[feature] = {"used": os.environ[var] not in ("", "0"), "why": "%s set by the caller" % var}

@@ -48,7 +48,7 @@ def test_autotune_switches_on_only_verified_faster_opt_ins(monkeypatch):
     spec = importlib.util.spec_from_file_location("ptd_bench_autotune", os.path.join(ROOT, "bench.py"))
     bench = importlib.util.module_from_spec(spec)
     spec.loader.exec_module(bench)
-    for k in ("PTD_PT_RAY_SORT", "PTD_PT_RAY_SORT_REFILL", "PTD_PT_RAY_SORT_FROM", "PTD_PT_WIDE_LOOKBACK", "PTD_DN_PDL"):
+    for k in ("PTD_PT_RAY_SORT", "PTD_PT_RAY_SORT_REFILL", "PTD_PT_RAY_SORT_FROM", "PTD_PT_WIDE_LOOKBACK", "PTD_PT_SMEM_STACK", "PTD_DN_PDL"):
         monkeypatch.delenv(k, raising=False)
     calls = []
 
@@ -57,7 +57,7 @@ def test_autotune_switches_on_only_verified_faster_opt_ins(monkeypatch):
         knobs = dict(a.split("=", 1) for a in cmd if "=" in a and a.startswith("PTD_"))
         calls.append((feature, knobs))
         table = {("ray_sort", ()): (True, 4.0, 3.5), ("ray_sort", (("PTD_PT_RAY_SORT_REFILL", "8"),)): (True, 4.0, 3.3),
-                 ("ray_sort", (("PTD_PT_RAY_SORT_FROM", "1"),)): (True, 4.0, 3.6), ("wide_lookback", ()): (True, 4.0, 3.97), ("pdl", ()): (False, 0.8, 0.7)}
+                 ("ray_sort", (("PTD_PT_RAY_SORT_FROM", "1"),)): (True, 4.0, 3.6), ("wide_lookback", ()): (True, 4.0, 3.97), ("smem_stack", ()): (True, 4.0, 3.8), ("pdl", ()): (False, 0.8, 0.7)}
         ok, base, feat = table[(feature, tuple(sorted(knobs.items())))]
         return types.SimpleNamespace(returncode=0, stdout="banner\n" + json.dumps({"feature": feature, "ok": ok, "base_ms": base, "feat_ms": feat}) + "\n", stderr="")
 
@@ -68,7 +68,8 @@ def test_autotune_switches_on_only_verified_faster_opt_ins(monkeypatch):
     assert os.environ.get("PTD_PT_RAY_SORT") == "1" and os.environ.get("PTD_PT_RAY_SORT_REFILL") == "8" and "PTD_PT_RAY_SORT_FROM" not in os.environ
     assert not out["wide_lookback"]["used"] and "PTD_PT_WIDE_LOOKBACK" not in os.environ          # bit-identical but only 1 % faster
     assert not out["pdl"]["used"] and "PTD_DN_PDL" not in os.environ                              # faster but not bit-identical
-    for k in ("PTD_PT_RAY_SORT", "PTD_PT_RAY_SORT_REFILL"):
+    assert out["smem_stack"]["used"] and os.environ.get("PTD_PT_SMEM_STACK") == "1"                 # bit-identical and 5 % faster
+    for k in ("PTD_PT_RAY_SORT", "PTD_PT_RAY_SORT_REFILL", "PTD_PT_SMEM_STACK"):
         monkeypatch.delenv(k, raising=False)
     monkeypatch.setenv("PTD_DN_PDL", "0")                                                            # the caller decided: no self-check for it
     calls.clear()

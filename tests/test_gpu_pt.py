@@ -257,6 +257,28 @@ def test_wide_lookback_changes_nothing(res, monkeypatch):
         _same(pa, pb, "bounce %d paths" % k)
 
 
+@pytest.mark.parametrize("combo", [{"PTD_PT_SMEM_STACK": "1"}, {"PTD_PT_SMEM_STACK": "1", "PTD_PT_RAY_SORT": "1", "PTD_PT_RAY_SORT_FROM": "1"}],
+                         ids=["experimental-smem-stack", "experimental-smem-stack-with-ray-sort"])
+def test_smem_stack_changes_nothing(combo, monkeypatch):
+    """PTD_PT_SMEM_STACK=1 (opt-in): the top 16 entries of every lane's BVH traversal stack live in shared memory.  Same traversal,
+    same records - alone and together with the ray binning."""
+    capi = _capi()
+    sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
+    sc.set_resolution(320, 200)
+    for k in ("PTD_PT_SMEM_STACK", "PTD_PT_RAY_SORT", "PTD_PT_RAY_SORT_FROM"):
+        monkeypatch.delenv(k, raising=False)
+    ref = capi.PathTracer(sc, flags=capi.PT_TRACE)
+    g_ref = ref.render_host()
+    for k, v in combo.items():
+        monkeypatch.setenv(k, v)
+    pt = capi.PathTracer(sc, flags=capi.PT_TRACE)
+    g = pt.render_host()
+    assert g.tobytes() == g_ref.tobytes() and pt.live_counts() == ref.live_counts()
+    for b in range(ref.live_counts()[1]):
+        _same(pt.dump_paths(b), ref.dump_paths(b), "bounce %d paths" % b)
+        _same(pt.dump_intersections(b), ref.dump_intersections(b), "bounce %d intersections" % b)
+
+
 @pytest.mark.parametrize("mode", ["experimental-gated-mail"])
 def test_row_strips_gated_mail(mode):
     """PTD_PT_GATED_MAIL (the flag the opt-in two-stream strip loop needs, PTD_STRIP_PIPELINE=1): the live-count mail is awaited by a

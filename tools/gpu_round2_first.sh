@@ -21,10 +21,11 @@ if [ "$WHAT" = single ]; then
   PTD_PT_RAY_SORT=1 PTD_PT_RAY_SORT_FROM=1 timeout 400 python bench.py $B > "$OUT/bench_raysort_from1.json" 2> "$OUT/bench_raysort_from1.err"
   PTD_PT_RAY_SORT=1 timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_raysort_serial.json" 2> "$OUT/bench_raysort_serial.err"
   timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_default_serial.json" 2> "$OUT/bench_default_serial.err"
+  PTD_PT_SMEM_STACK=1 timeout 400 python bench.py $B > "$OUT/bench_smem_stack.json" 2> "$OUT/bench_smem_stack.err"; echo "smem stack rc=$?"
   PTD_PT_WIDE_LOOKBACK=1 timeout 400 python bench.py $B > "$OUT/bench_wide_lookback.json" 2> "$OUT/bench_wide_lookback.err"; echo "wide look-back rc=$?"
   PTD_DN_PDL=1 timeout 400 python bench.py $B > "$OUT/bench_pdl.json" 2> "$OUT/bench_pdl.err"; echo "pdl rc=$?"
   PTD_DN_PDL=1 timeout 400 python bench.py $B --no-pipeline > "$OUT/bench_pdl_serial.json" 2> "$OUT/bench_pdl_serial.err"
-  for f in ray_sort wide_lookback pdl; do timeout 200 python tools/selfcheck.py $f > "$OUT/selfcheck_$f.json" 2> "$OUT/selfcheck_$f.err"; echo "selfcheck $f rc=$?"; cat "$OUT/selfcheck_$f.json"; done
+  for f in ray_sort wide_lookback smem_stack pdl; do timeout 200 python tools/selfcheck.py $f > "$OUT/selfcheck_$f.json" 2> "$OUT/selfcheck_$f.err"; echo "selfcheck $f rc=$?"; cat "$OUT/selfcheck_$f.json"; done
   timeout 900 python bench.py > "$OUT/bench_plain_default.json" 2> "$OUT/bench_plain_default.err"; echo "plain default (autotune + e2e auto) rc=$?"
   timeout 400 python bench.py $B --e2e fused > "$OUT/bench_e2e_fused.json" 2> "$OUT/bench_e2e_fused.err"; echo "fused rc=$?"
   python - "$OUT" <<'PY'

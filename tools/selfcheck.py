@@ -5,6 +5,7 @@ of its own (bench.py's --autotune runs it as a subprocess, so a fault in an opt-
     FEATURE     switch (read when the handle is created)      compared on the bench workload
     ray_sort    PTD_PT_RAY_SORT=1      coherent ray binning    G-buffer + live counts of 4 frames, bit for bit; ms per path-trace frame
     wide_lookback PTD_PT_WIDE_LOOKBACK=1 block-wide look-back  same
+    smem_stack  PTD_PT_SMEM_STACK=1    traversal stack in shared memory: same
     pdl         PTD_DN_PDL=1           programmatic dependent launch of the convs: denoised frames of a 4-frame recurrence, bit for bit;
                                                                ms per denoiser forward
 
@@ -20,7 +21,7 @@ import tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
-SWITCH = {"ray_sort": "PTD_PT_RAY_SORT", "wide_lookback": "PTD_PT_WIDE_LOOKBACK", "pdl": "PTD_DN_PDL"}
+SWITCH = {"ray_sort": "PTD_PT_RAY_SORT", "wide_lookback": "PTD_PT_WIDE_LOOKBACK", "smem_stack": "PTD_PT_SMEM_STACK", "pdl": "PTD_DN_PDL"}
 
 
 def main():
@@ -63,7 +64,7 @@ def main():
         return e0.elapsed_time(e1) / n
 
     detail = {}
-    if args.feature in ("ray_sort", "wide_lookback"):
+    if args.feature in ("ray_sort", "wide_lookback", "smem_stack"):
         base = capi.PathTracer(sc)
         os.environ[var] = "1"
         os.environ.update(knobs)
