@@ -206,6 +206,40 @@ def run_autotune(args):
             os.environ[var] = "1"
             os.environ.update(best[1])
             out[feature]["knobs"] = best[1]
+            out[feature]["ratio"] = best[0]
+    # the path-tracer opt-ins were checked one by one; together they select kernel variants none of those runs launched: check the set
+    pt_on = [(f, v) for f, v, _ in features[:3] if out.get(f, {}).get("used") and "tried" in out[f]]
+    if len(pt_on) >= 2:
+        combined = {"features": [f for f, _ in pt_on]}
+        keep_all = False
+        try:
+            cmd = [sys.executable, os.path.join(ROOT, "tools", "selfcheck.py"), pt_on[0][0], "--config", args.config, "--mode", args.mode]
+            for f, v in pt_on[1:]:
+                cmd += ["--env", "%s=1" % v]
+            for f, _ in pt_on:
+                for k, val in out[f].get("knobs", {}).items():
+                    cmd += ["--env", "%s=%s" % (k, val)]
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=150)
+            line = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+            if r.returncode == 0 and line:
+                d = json.loads(line[-1])
+                combined.update({"bit_identical": bool(d["ok"]), "base_ms": d["base_ms"], "feat_ms": d["feat_ms"]})
+                keep_all = bool(d["ok"]) and d["feat_ms"] / d["base_ms"] < min(out[f]["ratio"] for f, _ in pt_on)
+            else:
+                combined["why"] = "self-check failed (rc %d): %s" % (r.returncode, (r.stderr or r.stdout).strip()[-200:])
+        except Exception as exc:                                         # noqa: BLE001
+            combined["why"] = "self-check did not finish: %s" % str(exc)[:200]
+        combined["used"] = keep_all
+        out["pt_combined"] = combined
+        if not keep_all:                                                 # keep only the single best one
+            best_f = min(pt_on, key=lambda fv: out[fv[0]]["ratio"])[0]
+            for f, v in pt_on:
+                if f != best_f:
+                    os.environ.pop(v, None)
+                    for k in out[f].get("knobs", {}):
+                        os.environ.pop(k, None)
+                    out[f]["used"] = False
+                    out[f]["why"] = "not better together with %s" % best_f
     return out
 
 

@@ -58,12 +58,17 @@ def test_autotune_switches_on_only_verified_faster_opt_ins(monkeypatch):
         calls.append((feature, knobs))
         table = {("ray_sort", ()): (True, 4.0, 3.5), ("ray_sort", (("PTD_PT_RAY_SORT_REFILL", "8"),)): (True, 4.0, 3.3),
                  ("ray_sort", (("PTD_PT_RAY_SORT_FROM", "1"),)): (True, 4.0, 3.6), ("wide_lookback", ()): (True, 4.0, 3.97), ("smem_stack", ()): (True, 4.0, 3.8), ("pdl", ()): (False, 0.8, 0.7)}
-        ok, base, feat = table[(feature, tuple(sorted(knobs.items())))]
+        if any(k in ("PTD_PT_SMEM_STACK", "PTD_PT_WIDE_LOOKBACK", "PTD_PT_RAY_SORT") for k in knobs):      # the combined check of the enabled set
+            ok, base, feat = combined
+        else:
+            ok, base, feat = table[(feature, tuple(sorted(knobs.items())))]
         return types.SimpleNamespace(returncode=0, stdout="banner\n" + json.dumps({"feature": feature, "ok": ok, "base_ms": base, "feat_ms": feat}) + "\n", stderr="")
 
     monkeypatch.setattr(bench.subprocess, "run", fake_run)
     import argparse
+    combined = (True, 4.0, 3.1)                                        # both together: better than the best single one (3.3)
     out = bench.run_autotune(argparse.Namespace(config="C3", mode="f16"))
+    assert out["pt_combined"]["used"] and out["pt_combined"]["features"] == ["ray_sort", "smem_stack"]
     assert out["ray_sort"]["used"] and out["ray_sort"]["knobs"] == {"PTD_PT_RAY_SORT_REFILL": "8"} and len(out["ray_sort"]["tried"]) == 3
     assert os.environ.get("PTD_PT_RAY_SORT") == "1" and os.environ.get("PTD_PT_RAY_SORT_REFILL") == "8" and "PTD_PT_RAY_SORT_FROM" not in os.environ
     assert not out["wide_lookback"]["used"] and "PTD_PT_WIDE_LOOKBACK" not in os.environ          # bit-identical but only 1 % faster
@@ -75,3 +80,18 @@ def test_autotune_switches_on_only_verified_faster_opt_ins(monkeypatch):
     calls.clear()
     out = bench.run_autotune(argparse.Namespace(config="C3", mode="f16"))
     assert "pdl" not in [c[0] for c in calls] and out["pdl"]["used"] is False
+    # ... and when the set is not better than its best member, only that member stays on
+    for k in ("PTD_PT_RAY_SORT", "PTD_PT_RAY_SORT_REFILL", "PTD_PT_SMEM_STACK"):
+        monkeypatch.delenv(k, raising=False)
+    monkeypatch.delenv("PTD_DN_PDL", raising=False)
+    combined = (True, 4.0, 3.4)
+    out = bench.run_autotune(argparse.Namespace(config="C3", mode="f16"))
+    assert not out["pt_combined"]["used"] and out["ray_sort"]["used"] and not out["smem_stack"]["used"]
+    assert os.environ.get("PTD_PT_RAY_SORT") == "1" and "PTD_PT_SMEM_STACK" not in os.environ
+    combined = (False, 4.0, 2.0)                                       # together they are not bit-identical: same fallback
+    for k in ("PTD_PT_RAY_SORT", "PTD_PT_RAY_SORT_REFILL", "PTD_PT_SMEM_STACK"):
+        monkeypatch.delenv(k, raising=False)
+    out = bench.run_autotune(argparse.Namespace(config="C3", mode="f16"))
+    assert not out["pt_combined"]["used"] and "PTD_PT_SMEM_STACK" not in os.environ and os.environ.get("PTD_PT_RAY_SORT") == "1"
+    for k in ("PTD_PT_RAY_SORT", "PTD_PT_RAY_SORT_REFILL", "PTD_PT_SMEM_STACK"):
+        os.environ.pop(k, None)
