@@ -176,7 +176,11 @@ def run_autotune(args):
     out = {}
     features = (("ray_sort", "PTD_PT_RAY_SORT", [{}, {"PTD_PT_RAY_SORT_REFILL": "8"}, {"PTD_PT_RAY_SORT_FROM": "1"}]),     # knob variants tried once the plain one passed
                 ("wide_lookback", "PTD_PT_WIDE_LOOKBACK", [{}]), ("smem_stack", "PTD_PT_SMEM_STACK", [{}]), ("pdl", "PTD_DN_PDL", [{}]))
+    t_begin = time.time()
     for feature, var, variants in features:
+        if time.time() - t_begin > 240:                                  # the whole bench has to finish within minutes
+            out[feature] = {"used": False, "why": "autotune time budget (240 s) spent"}
+            continue
         if var in os.environ:                                            # the caller decided
             out[feature] = {"used": os.environ[var] not in ("", "0"), "why": "%s set by the caller" % var}
             continue
