@@ -36,7 +36,7 @@ ptd_dn_forward_host ptd_dn_create_strip ptd_dn_padded_size ptd_dn_dump_hidden pt
 ptd_pt_launches_last_render ptd_dn_profile ptd_dn_launch_times ptd_dn_launch_name ptd_pt_profile
 ptd_pt_launch_times ptd_dn_strip_partition ptd_dn_strip_info_size ptd_dn_strip_export ptd_dn_strip_connect
 ptd_dn_forward_group ptd_pt_create_strip ptd_pt_strip_info_size ptd_pt_strip_export ptd_pt_strip_connect
-ptd_pt_render_group ptd_frame_host ptd_bvh_probe ptd_bvh_probe_order""".split()
+ptd_pt_render_group ptd_frame_host ptd_frame_submit ptd_frame_wait ptd_bvh_probe ptd_bvh_probe_order""".split()
 
 
 class PtdError(RuntimeError):
@@ -77,6 +77,8 @@ def lib():
         L.ptd_pt_destroy.restype = None
         L.ptd_pt_render.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_pt_render_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.ptd_frame_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+        L.ptd_frame_wait.argtypes = [C.c_void_p]
         L.ptd_frame_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_bvh_probe_order.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_double)]
         L.ptd_bvh_probe.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_double)]
@@ -275,6 +277,20 @@ class PathTracer:
             camp = cam.ctypes.data
         check(lib().ptd_frame_host(self.h, dn.h, camp, iter, 1 if reset else 0, g.ctypes.data if want_gbuffer else None, rgb.ctypes.data), "ptd_frame_host")
         return g, rgb
+
+    def frame_submit(self, dn, rgb_out, gbuf_out=None, cam=None, iter=1, reset=False):
+        """ptd_frame_submit: enqueue one frame; rgb_out [3,H,W] / gbuf_out [10,H,W] are float32 numpy arrays (or anything with .ctypes /
+        .data_ptr()) that must stay alive until the matching frame_wait()."""
+        def ptr(a):
+            return None if a is None else (C.c_void_p(a.data_ptr()) if hasattr(a, "data_ptr") else a.ctypes.data)
+        camp = None
+        if cam is not None:
+            cam = np.ascontiguousarray(cam, CAM_DT).reshape(1)
+            camp = cam.ctypes.data
+        check(lib().ptd_frame_submit(self.h, dn.h, camp, iter, 1 if reset else 0, ptr(gbuf_out), ptr(rgb_out)), "ptd_frame_submit")
+
+    def frame_wait(self):
+        check(lib().ptd_frame_wait(self.h), "ptd_frame_wait")
 
     def render(self, gbuf_dev_ptr, cam=None, iter=1, stream=None):
         camp = None

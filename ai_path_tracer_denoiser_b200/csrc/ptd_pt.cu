@@ -732,6 +732,12 @@ struct ptd_pt {
     std::vector<cudaEvent_t> events;
     int timed_launches = 0;
     int bvh_nodes = 0, bvh_leaves = 0, bvh_max_leaf = 0, bvh_max_depth = 0;
+    // ptd_frame_submit / ptd_frame_wait: two frame slots, three streams (path trace, denoise + frame copy, G-buffer copy)
+    cudaStream_t fr_stream[3] = {nullptr, nullptr, nullptr};
+    float* fr_gbuf[2] = {nullptr, nullptr}; float* fr_rgb[2] = {nullptr, nullptr};
+    cudaEvent_t fr_ev_pt[2] = {nullptr, nullptr}, fr_ev_done[2] = {nullptr, nullptr}, fr_ev_gcopy[2] = {nullptr, nullptr};
+    bool fr_has_gcopy[2] = {false, false};
+    long long fr_submitted = 0, fr_waited = 0;
     bool wide_lookback = false;                              // PTD_PT_WIDE_LOOKBACK=1
     bool smem_stack = false;                                 // PTD_PT_SMEM_STACK=1
     // PTD_PT_RAY_SORT
@@ -756,6 +762,13 @@ extern "C" void ptd_pt_destroy(ptd_pt* h) {
     cudaFree(h->d_trace_paths); cudaFree(h->d_trace_isx); cudaFree(h->d_mail); cudaFree(h->d_bin_keys); cudaFree(h->d_bin_order); cudaFree(h->d_frame_rgb);
     for (int r = 0; r < PT_MAX_RANKS; ++r) if (h->peer_mail[r] && h->peer_ipc[r]) cudaIpcCloseMemHandle(h->peer_mail[r]);
     if (h->host_stream[0]) { cudaStreamDestroy(h->host_stream[0]); cudaStreamDestroy(h->host_stream[1]); cudaEventDestroy(h->host_event); }
+    for (int i = 0; i < 3; ++i) if (h->fr_stream[i]) { cudaStreamSynchronize(h->fr_stream[i]); cudaStreamDestroy(h->fr_stream[i]); }
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(h->fr_gbuf[i]); cudaFree(h->fr_rgb[i]);
+        if (h->fr_ev_pt[i]) cudaEventDestroy(h->fr_ev_pt[i]);
+        if (h->fr_ev_done[i]) cudaEventDestroy(h->fr_ev_done[i]);
+        if (h->fr_ev_gcopy[i]) cudaEventDestroy(h->fr_ev_gcopy[i]);
+    }
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
     delete h;
 }
@@ -1125,6 +1138,68 @@ extern "C" ptd_status ptd_frame_host(ptd_pt* h, ptd_dn* dn, const ptd_camera* ca
     CUDA_TRY(cudaMemcpyAsync(rgb_host, h->d_frame_rgb, 3 * plane, cudaMemcpyDeviceToHost, h->host_stream[0]));
     CUDA_TRY(cudaStreamSynchronize(h->host_stream[1]));
     CUDA_TRY(cudaStreamSynchronize(h->host_stream[0]));
+    return PTD_OK;
+}
+
+// ---- the same frame, asynchronously: submit frame k + 1, then wait for frame k ----------------------------------------------------
+// ptd_frame_submit enqueues a whole frame - path trace on one stream, denoiser + the copy of the denoised frame on a second, the
+// optional G-buffer copy on a third - into one of two buffer slots and returns at once; ptd_frame_wait blocks until the OLDEST
+// submitted frame has reached the caller's host buffers.  With one frame in flight while the next is submitted, the path trace of
+// frame k + 1 overlaps the denoiser and the PCIe copies of frame k (the reference's loop is strictly serial, main.cpp:120-168).
+// At most two frames may be in flight; frames complete in submission order; the recurrent state is carried in that order.
+static ptd_status frame_ring_init(ptd_pt* h) {
+    if (h->fr_stream[0]) return PTD_OK;
+    const size_t plane = sizeof(float) * (size_t)h->Pfull;
+    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&h->fr_stream[i], cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CUDA_TRY(cudaMalloc((void**)&h->fr_gbuf[i], 10 * plane));
+        CUDA_TRY(cudaMalloc((void**)&h->fr_rgb[i], 3 * plane));
+        CUDA_TRY(cudaMemset(h->fr_gbuf[i], 0, 10 * plane));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->fr_ev_pt[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->fr_ev_done[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->fr_ev_gcopy[i], cudaEventDisableTiming));
+    }
+    CUDA_TRY(cudaDeviceSynchronize());                                  // the memsets ran on the legacy stream
+    return PTD_OK;
+}
+extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host) {
+    if (!h || !dn || !rgb_host || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_submit: bad argument");
+    int dn_device = 0, dn_H = 0, dn_W = 0, dn_strip = 0;
+    ptd_dn_describe(dn, &dn_device, &dn_H, &dn_W, &dn_strip);
+    if (h->nranks > 1 || h->rows != h->H || dn_strip) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_frame_submit: row-strip handles take device pointers (ptd_pt_render + ptd_dn_forward)");
+    if (dn_device != h->device || dn_H != h->H || dn_W != h->W) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_submit: the denoiser handle is for %dx%d on device %d, the path tracer for %dx%d on device %d", dn_W, dn_H, dn_device, h->W, h->H, h->device);
+    if (h->fr_submitted - h->fr_waited >= 2) PTD_FAIL(PTD_ERR_STATE, "ptd_frame_submit: two frames are in flight - call ptd_frame_wait first");
+    CUDA_TRY(cudaSetDevice(h->device));
+    ptd_status rc = frame_ring_init(h);
+    if (rc != PTD_OK) return rc;
+    const int i = h->fr_submitted & 1;                                  // this slot's previous frame (two submissions ago) has been waited for
+    const size_t plane = sizeof(float) * (size_t)h->Pfull;
+    cudaStream_t s_pt = h->fr_stream[0], s_dn = h->fr_stream[1], s_cp = h->fr_stream[2];
+    rc = pt_run(h, cam, iter, h->fr_gbuf[i], s_pt, 0, h->depth);
+    if (rc != PTD_OK) return rc;
+    CUDA_TRY(cudaEventRecord(h->fr_ev_pt[i], s_pt));
+    h->fr_has_gcopy[i] = host_tensor != nullptr;
+    if (host_tensor) {
+        CUDA_TRY(cudaStreamWaitEvent(s_cp, h->fr_ev_pt[i], 0));
+        CUDA_TRY(cudaMemcpyAsync(host_tensor, h->fr_gbuf[i], 10 * plane, cudaMemcpyDeviceToHost, s_cp));
+        CUDA_TRY(cudaEventRecord(h->fr_ev_gcopy[i], s_cp));
+    }
+    CUDA_TRY(cudaStreamWaitEvent(s_dn, h->fr_ev_pt[i], 0));
+    rc = ptd_dn_forward(dn, h->fr_gbuf[i], h->fr_rgb[i], reset_hidden, s_dn);
+    if (rc != PTD_OK) return rc;
+    CUDA_TRY(cudaMemcpyAsync(rgb_host, h->fr_rgb[i], 3 * plane, cudaMemcpyDeviceToHost, s_dn));
+    CUDA_TRY(cudaEventRecord(h->fr_ev_done[i], s_dn));
+    h->fr_submitted += 1;
+    return PTD_OK;
+}
+extern "C" ptd_status ptd_frame_wait(ptd_pt* h) {
+    if (!h) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_wait: null handle");
+    if (h->fr_waited == h->fr_submitted) PTD_FAIL(PTD_ERR_STATE, "ptd_frame_wait: no frame in flight");
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int i = h->fr_waited & 1;
+    CUDA_TRY(cudaEventSynchronize(h->fr_ev_done[i]));
+    if (h->fr_has_gcopy[i]) CUDA_TRY(cudaEventSynchronize(h->fr_ev_gcopy[i]));
+    h->fr_waited += 1;
     return PTD_OK;
 }
 

@@ -159,6 +159,13 @@ ptd_status ptd_dn_forward_host(ptd_dn*, const float* gbuffer_host, float* rgb_ho
  * G-buffer exactly as pathtrace.cu:525 leaves it in scene->state.host_tensor; its copy overlaps the later bounces and the denoiser.
  * Both handles must live on the same device and cover the whole frame.  Pinned host memory makes the copies asynchronous. */
 ptd_status ptd_frame_host(ptd_pt*, ptd_dn*, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host);
+/* The same frame asynchronously.  ptd_frame_submit enqueues path trace + denoise + host copies of one frame and returns at once;
+ * ptd_frame_wait blocks until the OLDEST submitted frame has reached its host buffers.  Submit frame k + 1 before waiting for frame k
+ * and the path trace of k + 1 overlaps the denoiser and the PCIe copies of k.  At most two frames in flight; frames complete in
+ * submission order (so the recurrent state is carried in that order); the host buffers of a frame must stay valid, and should be
+ * pinned, until its ptd_frame_wait returns.  Results are bit-identical to ptd_frame_host / the two-call path. */
+ptd_status ptd_frame_submit(ptd_pt*, ptd_dn*, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host);
+ptd_status ptd_frame_wait(ptd_pt*);
 /* ---- row-strip mode: the denoiser of ONE frame tiled over several GPUs ----------------------------
  * A strip handle owns padded rows [row0, row0 + rows) (multiples of 32) of the frame.  Its convs store their first / last
  * output row directly into the neighbour strips' halo rows over NVLink (peer pointers) and raise a flag there; the

@@ -60,3 +60,39 @@ def test_frame_host_equals_the_two_host_calls(tmp_path, mode):
         if g is not None:
             assert g.tobytes() == g_ref.tobytes(), k
         assert rgb.tobytes() == rgb_ref.tobytes(), k
+
+
+@pytest.mark.parametrize("mode", ["experimental-frame-submit-wait"])
+def test_frame_submit_wait_equals_the_two_host_calls(tmp_path, mode):
+    """ptd_frame_submit / ptd_frame_wait (one frame in flight while the next is submitted) == ptd_pt_render_host + ptd_dn_forward_host,
+    bit for bit over a recurrent sequence, with and without the host copy of the G-buffer; call-order errors are reported, not ignored."""
+    from ai_path_tracer_denoiser_b200 import capi, weights
+    if capi.device_count() < 1:
+        pytest.fail("no CUDA device")
+    wfile = weights.save_weights(weights.synthetic_state_dict(1234), str(tmp_path / "w.ptdw"))
+    sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
+    sc.set_resolution(160, 96)
+    n = 7
+    cams = [capi.frame_camera(sc.camera[0], k) for k in range(n)]
+    pt_a, dn_a = capi.PathTracer(sc), capi.Denoiser(wfile, 96, 160, flags=capi.DN_TF32)
+    ref = []
+    for k, cam in enumerate(cams):
+        g = pt_a.render_host(cam)
+        ref.append((g, dn_a.forward_host(g, reset=(k == 0))))
+    pt_b, dn_b = capi.PathTracer(sc), capi.Denoiser(wfile, 96, 160, flags=capi.DN_TF32)
+    with pytest.raises(capi.PtdError):
+        pt_b.frame_wait()                                              # nothing in flight
+    rgb = [np.zeros((3, 96, 160), np.float32) for _ in range(n)]
+    gb = [np.zeros((10, 96, 160), np.float32) if k % 3 != 2 else None for k in range(n)]
+    pt_b.frame_submit(dn_b, rgb[0], gb[0], cam=cams[0], reset=True)
+    for k in range(1, n):
+        pt_b.frame_submit(dn_b, rgb[k], gb[k], cam=cams[k])
+        if k == 1:
+            with pytest.raises(capi.PtdError):
+                pt_b.frame_submit(dn_b, rgb[k], gb[k], cam=cams[k])   # a third frame in flight
+        pt_b.frame_wait()                                              # frame k - 1 is complete
+        assert rgb[k - 1].tobytes() == ref[k - 1][1].tobytes(), k - 1
+        if gb[k - 1] is not None:
+            assert gb[k - 1].tobytes() == ref[k - 1][0].tobytes(), k - 1
+    pt_b.frame_wait()
+    assert rgb[n - 1].tobytes() == ref[n - 1][1].tobytes()
