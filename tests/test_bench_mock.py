@@ -22,7 +22,7 @@ class _FakeLib:
         self.real, self.fail, self.calls = real, set(fail), []
 
     def __getattr__(self, name):
-        if not name.startswith(("ptd_pt_", "ptd_dn_", "ptd_frame_")):
+        if not name.startswith(("ptd_pt_", "ptd_dn_", "ptd_frame_")) or name == "ptd_dn_strip_partition":     # pure host arithmetic
             return getattr(self.real, name)
 
         def f(*a):
@@ -173,3 +173,41 @@ def test_selfcheck_tool_runs(bench_env, capsys, feature, monkeypatch):
     handles = [env for k, env in seen if k == kind]
     assert var not in handles[-2] and handles[-1].get(var) == "1" and handles[-1].get("PTD_PT_RAY_SORT_REFILL") == "8"     # base, then the opt-in handle
     assert var not in os.environ and "PTD_PT_RAY_SORT_REFILL" not in os.environ
+
+
+def test_bench_strip_mode_host_logic_runs(bench_env, capsys, monkeypatch):
+    """The N > 1 leg of bench.py (one rank of a 2-rank job, torch.distributed replaced by no-ops, the supervised two-stream attempt switched
+    off as the driver's child runs would have it): strips, serial frame loop, pipelined read-back, replicas context, JSON."""
+    bench, lib = bench_env
+    from ai_path_tracer_denoiser_b200 import capi, tiling
+    import torch.distributed as dist
+    PT, DN = capi.PathTracer, capi.Denoiser
+
+    class PT2(PT):
+        def __init__(self, scene, device=0, flags=0, strip=None):
+            super().__init__(scene, device, flags, strip)
+            if strip is not None:
+                self.P = self.W * strip[1]
+        def export_info(self): return b"p" * 8
+        def connect(self, infos, rank): assert len(infos) == 2
+
+    class DN2(DN):
+        def export_info(self): return b"d" * 8
+        def connect(self, infos, rank): assert len(infos) == 2
+
+    monkeypatch.setattr(capi, "PathTracer", PT2)
+    monkeypatch.setattr(capi, "Denoiser", DN2)
+    monkeypatch.setattr(tiling, "exchange_blobs", lambda blob, d=None, world=1: [blob] * world)
+    for name in ("init_process_group", "barrier", "destroy_process_group", "all_reduce"):
+        monkeypatch.setattr(dist, name, lambda *a, **k: None)
+    real_tensor = torch.tensor
+    monkeypatch.setattr(torch, "tensor", lambda *a, **k: real_tensor(*a, **{kk: v for kk, v in k.items() if kk != "device"}))
+    monkeypatch.setattr(torch, "device", lambda *a, **k: "cpu")
+    for k, v in (("WORLD_SIZE", "2"), ("RANK", "0"), ("LOCAL_RANK", "0"), ("PTD_STRIP_PIPELINE", "0")):
+        monkeypatch.setenv(k, v)
+    d = _run(bench, capsys, ["--gpus", "2", "--config", "C2", "--steps", "3", "--warmup", "3"])
+    assert d["n_gpus"] == 2 and d["scaling"] == "strong" and d["config"]["frame_loop"].startswith("serial")
+    assert d["e2e"]["h2d_bytes_per_step"] == 84 and "replicas" in d and "autotune" not in d["config"] and "cpu_baseline" not in d
+    monkeypatch.setenv("PTD_STRIP_PIPELINE", "1")                      # what the supervised child runs with
+    d = _run(bench, capsys, ["--gpus", "2", "--config", "C2", "--steps", "3", "--warmup", "3"])
+    assert d["config"]["frame_loop"].startswith("two streams") and "strip_loop" in d["config"]
