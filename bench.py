@@ -247,7 +247,7 @@ def run_autotune(args):
     return out
 
 
-def try_pipelined_strips(argv, rank, world, child_timeout=360):
+def try_pipelined_strips(argv, rank, world, child_timeout=240):
     """N > 1: the two-stream frame loop in strip mode (PTD_STRIP_PIPELINE=1: gated live-count mail) measured 20-34 %
     more frames/s than the serial loop, but it has not been soaked since the gated mail was written.  So it is tried FIRST, as a complete
     benchmark run in a child process group (one child per rank, its own rendezvous port, every device-side wait traps after 20 s);
