@@ -21,6 +21,14 @@ def pytest_collection_modifyitems(config, items):
     if late:
         ids = {id(it) for it in late}
         items[:] = [it for it in items if id(it) not in ids] + late
+    # The "experimental" cases cover code paths written after round 1's GPU budget was spent: never run on a GPU yet,
+    # all opt-in, and bench.py re-verifies each of them at run time before using it.  They are part of the suite only on request
+    # (PTD_OPTIN_TESTS=1, as tools/gpu_round2_first.sh sets it), so that `pytest -m gpu` reports the validated configuration.
+    if os.environ.get("PTD_OPTIN_TESTS") != "1":
+        skip = pytest.mark.skip(reason="opt-in code path not yet validated on a GPU: set PTD_OPTIN_TESTS=1 to run it")
+        for it in items:
+            if "experimental" in it.nodeid:
+                it.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

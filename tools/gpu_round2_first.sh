@@ -12,7 +12,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$
 B="--steps 100 --warmup 5 --no-cpu-baseline --no-autotune"      # explicit A/B runs below; the last single-GPU run is the plain default (autotune on)
 if [ "$WHAT" = single ]; then
   timeout 120 tools/microbench/umma_rate 2048 > "$OUT/umma_rate.txt" 2>&1; echo "umma_rate rc=$?"; head -40 "$OUT/umma_rate.txt"
-  timeout 1200 python -m pytest tests -m gpu -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -4 "$OUT/pytest_gpu.log"
+  PTD_OPTIN_TESTS=1 timeout 1200 python -m pytest tests -m gpu -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -4 "$OUT/pytest_gpu.log"
   timeout 400 python bench.py $B > "$OUT/bench_default.json" 2> "$OUT/bench_default.err"; echo "default rc=$?"
   for cfg in "4 22" "4 8" "5 22" "3 22"; do
     set -- $cfg
