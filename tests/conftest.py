@@ -27,8 +27,8 @@ def pytest_collection_modifyitems(config, items):
     if os.environ.get("PTD_OPTIN_TESTS") != "1":
         skip = pytest.mark.skip(reason="opt-in code path not yet validated on a GPU: set PTD_OPTIN_TESTS=1 to run it")
         for it in items:
-            if "experimental" in it.nodeid:
-                it.add_marker(skip)
+            if "experimental" in it.nodeid or "replicated" in it.nodeid:     # (replicated levels: validated bit-exact with 8 processes, profiles/r02k_*;
+                it.add_marker(skip)                                          #  the single-GPU lock-step form of that opt-in has not run since it became opt-in)
 
 
 @pytest.fixture(scope="session")
