@@ -41,6 +41,7 @@ PY
 else
   TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29533"
   timeout 300 $TR tools/check_strips_multi.py > "$OUT/check_n$N.log" 2>&1; echo "strip parity rc=$?"; tail -$N "$OUT/check_n$N.log"
+  PTD_STRIP_PIPELINE=1 timeout 300 $TR tools/check_strips_multi.py 1280 720 4 > "$OUT/check_n${N}_gated_mail_720p.log" 2>&1; echo "strip parity with the gated mail rc=$?"; tail -$N "$OUT/check_n${N}_gated_mail_720p.log"
   timeout 900 $TR bench.py --gpus $N --steps 100 --warmup 5 > "$OUT/bench_n${N}_plain_default.json" 2> "$OUT/bench_n${N}_plain_default.err"; echo "plain default (supervised two-stream attempt) rc=$?"
   timeout 300 $TR bench.py --gpus $N $B > "$OUT/bench_n${N}_serial.json" 2> "$OUT/bench_n${N}_serial.err"; echo "serial rc=$?"
   for rep in 1 2 3; do
