@@ -490,6 +490,23 @@ def main():
     roof["peak_source"] = peaks["source"] + ("; tf32 peak = measured bf16 burst / 2" if roof["bound"] == "tensor" or "tensor_tflops" in roof else "")
     roof["per_layer_ms"] = {n: round(float(m), 4) for (n, _), m in zip(dn_named, dn_ms)}
     roof["per_bounce_ms"] = {"pt_trace": [round(float(m), 4) for m in pt_ms[0::2]], "pt_shade": [round(float(m), 4) for m in pt_ms[1::2]]}
+    # What DOES bound pt_trace: the L1 data pipe (one wavefront per distinct 128-byte line per load).  Host-side model (ptd_bvh_probe_order:
+    # the BVH4 traversal of pt_trace restated on the CPU over incoherent probe rays, 7 loads per node visit + 3 per triangle test) against the
+    # time measured above for the secondary bounces; the ncu capture of bounce 1 (profiles/r01u_ncu_pt.txt) reads 83 % for this pipe.
+    if nfaces and rank == 0 and len(pt_ms) >= 4:
+        try:
+            pr = (C.c_double * 8)()
+            capi.check(L.ptd_bvh_probe_order(sc.h, 64000, 7, 4, pr), "ptd_bvh_probe_order")
+            sec_rays = float(sum(ll[1:]))
+            sec_ms = float(sum(pt_ms[2::2]))
+            sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+            sms = torch.cuda.get_device_properties(local).multi_processor_count
+            wf_per_clk_sm = sec_rays * pr[0] / (sec_ms * 1e-3 * sm_mhz * 1e6 * sms)
+            roof["l1_model"] = dict(kernel="pt_trace (bounces >= 1)", wavefronts_per_ray_arrival_order=round(pr[0], 1), wavefronts_per_ray_binned=round(pr[1], 1),
+                                    achieved_wavefronts_per_clk_per_sm=round(wf_per_clk_sm, 3), peak=1.0, frac=round(wf_per_clk_sm, 3),
+                                    note="host-side model of the traversal on incoherent probe rays (the real bounce-1 rays are more coherent), not a hardware counter")
+        except Exception as exc:                         # noqa: BLE001 - a diagnostic, never worth the benchmark
+            roof["l1_model"] = {"error": str(exc)[:120]}
     roof["kernels"] = kernels
 
     # ---- end to end ----

@@ -73,6 +73,7 @@ def bench_env(monkeypatch):
         def wait_event(self, e): pass
         def synchronize(self): pass
 
+    monkeypatch.setattr(torch.cuda, "get_device_properties", lambda d: types.SimpleNamespace(multi_processor_count=148))
     monkeypatch.setattr(torch.cuda, "set_device", lambda d: None)
     monkeypatch.setattr(torch.cuda, "synchronize", lambda *a: None)
     monkeypatch.setattr(torch.cuda, "Event", Ev)
@@ -211,3 +212,13 @@ def test_bench_strip_mode_host_logic_runs(bench_env, capsys, monkeypatch):
     monkeypatch.setenv("PTD_STRIP_PIPELINE", "1")                      # what the supervised child runs with
     d = _run(bench, capsys, ["--gpus", "2", "--config", "C2", "--steps", "3", "--warmup", "3"])
     assert d["config"]["frame_loop"].startswith("two streams") and "strip_loop" in d["config"]
+
+
+def test_bench_mesh_config_adds_the_l1_model(bench_env, capsys):
+    """C3 (a mesh scene): the roofline object also carries the host-side L1-wavefront model of pt_trace (ptd_bvh_probe_order is real host
+    code even here)."""
+    bench, lib = bench_env
+    d = _run(bench, capsys, ["--config", "C3", "--steps", "2", "--warmup", "3", "--no-cpu-baseline", "--e2e", "calls", "--no-autotune"])
+    m = d["roofline"]["l1_model"]
+    assert "error" not in m and 60 < m["wavefronts_per_ray_binned"] < m["wavefronts_per_ray_arrival_order"] < 250 and m["frac"] > 0
+    assert d["config"]["triangles"] > 200000
