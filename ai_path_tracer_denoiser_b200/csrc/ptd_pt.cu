@@ -1075,9 +1075,10 @@ extern "C" ptd_status ptd_pt_strip_connect(ptd_pt* h, const void* infos, int nra
     return PTD_OK;
 }
 
+extern "C" ptd_status ptd_frame_wait(ptd_pt* h);
 extern "C" ptd_status ptd_pt_render_host(ptd_pt* h, const ptd_camera* cam, int iter, float* host_tensor) {
     if (!h || !host_tensor || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_render_host: bad argument");
-    if (h->fr_submitted != h->fr_waited) PTD_FAIL(PTD_ERR_STATE, "ptd_pt_render_host: a frame submitted with ptd_frame_submit is still in flight - call ptd_frame_wait first");
+    while (h->fr_waited < h->fr_submitted) { ptd_status rc_ = ptd_frame_wait(h); if (rc_ != PTD_OK) return rc_; }   // frames submitted asynchronously complete first
     CUDA_TRY(cudaSetDevice(h->device));
     if (!h->host_stream[0]) {
         CUDA_TRY(cudaStreamCreateWithFlags(&h->host_stream[0], cudaStreamNonBlocking));
@@ -1108,7 +1109,7 @@ extern "C" ptd_status ptd_pt_render_host(ptd_pt* h, const ptd_camera* cam, int i
 // download (host_tensor, optional) overlaps the remaining bounces and the denoiser.
 extern "C" ptd_status ptd_frame_host(ptd_pt* h, ptd_dn* dn, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host) {
     if (!h || !dn || !rgb_host || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_host: bad argument");
-    if (h->fr_submitted != h->fr_waited) PTD_FAIL(PTD_ERR_STATE, "ptd_frame_host: a frame submitted with ptd_frame_submit is still in flight - call ptd_frame_wait first");
+    while (h->fr_waited < h->fr_submitted) { ptd_status rc_ = ptd_frame_wait(h); if (rc_ != PTD_OK) return rc_; }   // frames submitted asynchronously complete first
     int dn_device = 0, dn_H = 0, dn_W = 0, dn_strip = 0;
     ptd_dn_describe(dn, &dn_device, &dn_H, &dn_W, &dn_strip);
     if (h->nranks > 1 || h->rows != h->H || dn_strip) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_frame_host: row-strip handles take device pointers (ptd_pt_render + ptd_dn_forward)");
