@@ -25,7 +25,7 @@ CAM_DT = np.dtype([("res", "<i4", 2), ("pos", "<f4", 3), ("lookat", "<f4", 3), (
 AABB_DT = np.dtype([("lb", "<f4", 3), ("ub", "<f4", 3)])
 
 PT_SORT_MATERIAL, PT_TRACE, PT_NO_BVH, PT_KEEP_TERMINATED, PT_GATED_MAIL, PT_RAY_SORT = 1, 2, 4, 8, 16, 32
-DN_FP32, DN_TF32, DN_3XTF32, DN_F16, DN_FP32_BATCH_STATS = 0, 1, 2, 3, 4
+DN_FP32, DN_TF32, DN_3XTF32, DN_F16, DN_FP32_BATCH_STATS, DN_2XF16 = 0, 1, 2, 3, 4, 5
 
 EXPORTS = """ptd_last_error ptd_version ptd_sizeof ptd_device_count ptd_scene_load ptd_scene_from_arrays ptd_scene_free
 ptd_scene_counts ptd_scene_geoms ptd_scene_materials ptd_scene_faces ptd_scene_mesh_box ptd_scene_camera

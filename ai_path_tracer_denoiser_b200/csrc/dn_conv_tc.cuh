@@ -21,8 +21,8 @@
 //   * epilogue (4 warps, thread = pixel): tcgen05.ld 32x32b.x16 -> bias/BatchNorm(eval)/LeakyReLU -> one float4 per channel
 //     quad (a warp stores 4 x 128 contiguous bytes), MaxPool2d(2) fused through two warp shuffles (the 2x2 window lives in
 //     one warp), activations rounded to tf32 (RN) so the next layer's operand truncation is exact.
-// Warp roles: 0 = TMA producer, 1 = MMA issuer (one lane), 2 = TMEM allocator, 4..11 = epilogue (two warps per TMEM lane
-// quarter, alternating 16-column chunks, so every SM sub-partition has two epilogue warps to hide latency).  Pipelines: up
+// Warp roles: 0..7 = epilogue (two warps per TMEM lane quarter, alternating 16-column chunks, so every SM sub-partition has two
+// epilogue warps to hide latency), 8 = TMA producer, 9 = TMEM allocator, 10 = barrier init, 11 = MMA issuer (one lane; the highest warp id).  Pipelines: up
 // to 8 smem stages (full/empty mbarriers) and 2 TMEM accumulator buffers (tmem_full/tmem_empty), persistent CTAs, one per SM.
 #pragma once
 #include <cuda.h>
@@ -30,6 +30,7 @@
 #include <cuda_fp16.h>
 #include <cstdint>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 #include "ptd_internal.h"
 
@@ -41,9 +42,16 @@
 #define TC_QUAD_PITCH (TC_HALO_H * TC_ROW_PITCH)        // 2880 B: one channel quad of the halo tile
 #define TC_A_BYTES (4 * TC_QUAD_PITCH)                  // 11520 B: 16 channels
 #define TC_MAX_STAGES 8
-#define TC_THREADS 384                                  // warps 0-3: TMA / MMA / TMEM alloc / idle; warps 4-11: epilogue
-#define TC_TMEM_COLS 256
-#define TC_ACC_COLS 128
+#define TC_THREADS 384                                  // warps 0-7: epilogue; 8: TMA producer; 9: TMEM allocator; 10: barrier init; 11: MMA issuer
+#define TC_EPI_WARPS 8
+#define TC_WARP_TMA 8
+#define TC_WARP_ALLOC 9
+#define TC_WARP_INIT 10
+#define TC_WARP_MMA 11
+#define TC_TMEM_COLS 512                                // the whole tensor memory of the SM (one CTA per SM)
+#define TC_ACC_COLS 128                                 // widest accumulator (padded Cout)
+#define TC_MAX_BUFS 4                                   // accumulator buffers in flight between the MMA issuer and the epilogue
+#define TC_MAX_SEGS 4                                   // split-operand modes: main accumulators per buffer
 #define TC_SMEM_BUDGET (200 * 1024)
 
 // An activation tensor in HBM: channel VECTORS of 16 bytes - [cp*esize/16][rows + 2][W][16 B] - i.e. quads of fp32 ("CHW4", esize 4)
@@ -109,7 +117,15 @@ struct __align__(64) TcParams {
     int lrelu_first, round_out;
     DnTensor out, pool_out;
     TcStripLink link;
-    int pdl;                             // launched with programmatic stream serialization (appended: the offsets above are the validated ones)
+    int pdl;                             // launched with programmatic stream serialization
+    // accumulators in tensor memory: `nbuf` buffers of `buf_cols` columns; a buffer = nseg main accumulators [+ one correction accumulator]
+    // of coutp columns each.  Split-operand modes (x3) keep the small cross terms (hi x lo, lo x hi) out of the large hi x hi sums and cut
+    // the hi x hi chain into nseg pieces - tcgen05.mma truncates on every accumulate (tools/microbench/umma_accum), so one long chain loses
+    // ~10x the accuracy the operand split buys; the epilogue adds the pieces in fp32 (round to nearest).
+    int nseg, nbuf, buf_cols;
+    uint32_t seg_start;                  // bit c: chunk c starts the next main accumulator
+    float corr_scale;                    // the correction accumulator's scale: 1 (3xTF32) or 2^-11 (2xF16: lo operands are stored x 2^11)
+    int linked;                          // row-strip mode: some TcStripLink pointer is set (selects the kernel variant with the peer stores)
 };
 
 struct TcConvPlan {
@@ -235,7 +251,7 @@ __device__ __forceinline__ void mma_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a
 namespace tc {
 // 16 consecutive output channels [c0, c0 + 16) of one pixel -> the tensor's channel vectors (row: address of the pixel in vector 0)
 __device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, const float* o) {
-    if (t.lo_off) {                                        // 3xTF32: hi = tf32(v), lo = tf32(v - hi)
+    if (t.lo_off && t.esize == 4) {                        // 3xTF32: hi = tf32(v), lo = tf32(v - hi)
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
             float hi[4], lo[4];
@@ -244,6 +260,22 @@ __device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, c
             float* d = row + (size_t)(c0 / 4 + qd) * t.quad_stride();
             *reinterpret_cast<float4*>(d) = make_float4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<float4*>(d + t.lo_off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
+        }
+    } else if (t.lo_off) {                               // 2xF16: hi = f16(v), lo = f16((v - hi) * 2^11) - the residual scaled into fp16's normal range
+#pragma unroll
+        for (int oc = 0; oc < 2; ++oc) {
+            uint32_t hw[4], lw[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const float v0 = o[8 * oc + 2 * e], v1 = o[8 * oc + 2 * e + 1];
+                const __half2 h = __floats2half2_rn(v0, v1);
+                const float2 hf = __half22float2(h);
+                const __half2 l = __floats2half2_rn((v0 - hf.x) * 2048.0f, (v1 - hf.y) * 2048.0f);
+                hw[e] = *reinterpret_cast<const uint32_t*>(&h); lw[e] = *reinterpret_cast<const uint32_t*>(&l);
+            }
+            float* d = row + (size_t)(c0 / 8 + oc) * t.quad_stride();
+            *reinterpret_cast<uint4*>(d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
+            *reinterpret_cast<uint4*>(d + t.lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
     } else if (t.esize == 4) {
 #pragma unroll
@@ -260,10 +292,19 @@ __device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, c
         }
     }
 }
-// K-major no-swizzle descriptors, split into 32-bit words: lo = start >> 4 | (LBO >> 4) << 16, hi = SBO >> 4 | version 1 << 14
+// K-major no-swizzle descriptors, split into 32-bit words: lo = start >> 4 | (LBO >> 4) << 16, hi = SBO >> 4 | version 1 << 14.
+//
+// The issue loop is the kernel's critical path for the N = 32 layers: one M = 128 x N = 32 MMA occupies the tensor pipe's shared-memory
+// operand fetch for (4096 + 1024) B / 128 B/clk = 40 cycles (tools/microbench/umma_rate, profiles/r3c_umma_rate.txt: 41.7 cycles per MMA
+// measured, whatever the layout, the data, the number of accumulators or the traffic beside it), and the MMA queue is shallow, so every
+// cycle the issuing warp spends between two chunks beyond what the queue covers is a cycle the pipe starves (round 1: 70 cycles per tf32
+// MMA, 92 per f16 MMA = 49 per MMA + ~1500 per tile of bookkeeping - integer divisions, parameter reloads, recomputed tap offsets).
+// Hence: nested loops instead of div/mod, every parameter hoisted into registers, running descriptor bases, tap offsets computed once
+// per phase, and the issuing warp is the CTA's highest warp id (the SM sub-partition's arbiter favours it over the epilogue warps it
+// shares its scheduler with).
 template <int NTAPS, bool HALF>
 __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full, uint64_t* empty,
-                                         uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int lane) {
+                                         uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base) {
     // instruction descriptor: D = f32, A = B = tf32 (format 2) or f16 (format 0), both K-major, N = coutp, M = 128
     const uint32_t fmt = HALF ? 0u : 2u;
     const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.coutp >> 3) << 17) | ((128u >> 4) << 24);
@@ -272,48 +313,72 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
     const uint32_t a_lbo = (uint32_t)(TC_QUAD_PITCH >> 4) << 16;              // LBO = next channel quad
     const uint32_t b_lbo = (uint32_t)p.coutp << 16;                           // (coutp * 16 B) >> 4: next k quad of the same tap
     const uint32_t b_kstep = (uint32_t)p.coutp * 2u;                          // (coutp * 32 B) >> 4: one K = 8 step
-    const int nchunks = p.n0 + p.n1, npass = p.x3 ? 3 : 1;
-    const uint32_t sa0 = smem_u32(smem_a) >> 4, sb0 = smem_u32(smem_b) >> 4;
-    const uint32_t b_stage16 = p.b_stage_bytes >> 4;
+    const int nchunks = p.n0 + p.n1, npass = p.x3 ? 3 : 1, nphases = p.nphases, total = p.total_items, stages = p.stages;
+    const bool resident = p.resident != 0, x3 = p.x3 != 0;
+    const uint32_t sa0 = (smem_u32(smem_a) >> 4) | a_lbo, sb0 = (smem_u32(smem_b) >> 4) | b_lbo;
+    const uint32_t b_stage16 = p.b_stage_bytes >> 4, a_stage16 = TC_A_BYTES >> 4;
+    const uint32_t b_chunk16 = b_stage16 * (x3 ? 2u : 1u);                    // resident weights: blocks of one chunk (hi [, lo])
+    const uint32_t d_tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);          // provably warp-uniform
+    // chunks whose source holds only two channel vectors there (one K step; the other two vectors are TMA zero fill): bit c
+    uint32_t one_step = 0;
+    for (int c = 0; c < nchunks; ++c)
+        if ((c < p.n0 ? p.v0 - 4 * c : p.v1 - 4 * (c - p.n0)) <= 2) one_step |= 1u << c;
+    uint32_t aoff[NTAPS];
+#pragma unroll
+    for (int t = 0; t < NTAPS; ++t) aoff[t] = (uint32_t)(((1 + p.dy[0][t]) * TC_ROW_PITCH + (1 + p.dx[0][t]) * 16) >> 4);
     int stage = 0; uint32_t phase = 0;
-    int acc = 0; uint32_t acc_phase = 0;
-    for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-        const int ph = item % p.nphases;
-        uint32_t aoff[NTAPS];
+    uint32_t a_base = sa0;
+    int buf = 0; uint32_t buf_phase = 0;
+    const int nbuf = p.nbuf, nseg = p.nseg;
+    const uint32_t buf_cols = (uint32_t)p.buf_cols, seg_start = p.seg_start, coutp = (uint32_t)p.coutp;
+    for (int item = blockIdx.x; item < total; item += gridDim.x) {
+        uint32_t b_base = sb0;
+        if (nphases > 1) {                                                    // the four 2x2-tap phase GEMMs of an upsampling layer
+            const int ph = item & 3;
 #pragma unroll
-        for (int t = 0; t < NTAPS; ++t) aoff[t] = (uint32_t)(((1 + p.dy[ph][t]) * TC_ROW_PITCH + (1 + p.dx[ph][t]) * 16) >> 4);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        fence_after_sync();
-        const uint32_t d_tmem = __shfl_sync(0xffffffffu, tmem_base, 0) + (uint32_t)acc * TC_ACC_COLS;   // provably warp-uniform
-        for (int e = 0; e < nchunks * npass; ++e) {
-            const int c = e / npass, pass = e - c * npass;
-            mbar_wait(&full[stage], phase);
-            fence_after_sync();
-            const uint32_t a_base = (sa0 + (uint32_t)stage * (TC_A_BYTES >> 4)) | a_lbo;
-            // resident weights: block (phase, chunk) [x3: hi block, lo block]; passes 0 and 2 use the hi block, pass 1 the lo block
-            const uint32_t b_blk = p.x3 ? (uint32_t)((ph * nchunks + c) * 2 + (pass == 1 ? 1 : 0)) : (uint32_t)(ph * nchunks + c);
-            const uint32_t b_base = (sb0 + (p.resident ? b_blk : (uint32_t)stage) * b_stage16) | b_lbo;
-            // a source's last chunk may hold only two channel vectors (one K step); the other two are TMA zero fill
-            const bool two = (c < p.n0 ? p.v0 - 4 * c : p.v1 - 4 * (c - p.n0)) > 2;
-            if (elect_one()) {
-#pragma unroll
-                for (int t = 0; t < NTAPS; ++t) {
-                    mma_w<HALF>(d_tmem, a_base + aoff[t], a_hi, b_base + (uint32_t)(t * 2) * b_kstep, b_hi, idesc, t ? 1u : (e ? 1u : 0u));
-                    if (two) mma_w<HALF>(d_tmem, a_base + aoff[t] + (2u * TC_QUAD_PITCH >> 4), a_hi, b_base + (uint32_t)(t * 2 + 1) * b_kstep, b_hi, idesc, 1u);
-                }
-                mma_commit(&empty[stage]);                                    // frees the smem stage when the MMAs retire
-                if (e == nchunks * npass - 1) mma_commit(&tmem_full[acc]);    // accumulator complete -> epilogue
-            }
-            __syncwarp();
-            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            for (int t = 0; t < NTAPS; ++t) aoff[t] = (uint32_t)(((1 + p.dy[ph][t]) * TC_ROW_PITCH + (1 + p.dx[ph][t]) * 16) >> 4);
+            b_base += (uint32_t)(ph * nchunks) * b_chunk16;
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
+        fence_after_sync();
+        const uint32_t d_buf = d_tmem0 + (uint32_t)buf * buf_cols;
+        uint32_t started = 0, seg = 0;                                        // accumulators of this buffer that hold a partial sum already
+        for (int c = 0; c < nchunks; ++c) {
+            const bool two = !((one_step >> c) & 1u);
+            if (c && ((seg_start >> c) & 1u)) ++seg;
+            for (int pass = 0; pass < npass; ++pass) {
+                mbar_wait(&full[stage], phase);
+                fence_after_sync();
+                // resident weights: block (phase, chunk) [x3: hi block, lo block]; passes 0 and 2 use the hi block, pass 1 the lo block
+                const uint32_t b_cur = resident ? b_base + (pass == 1 ? b_stage16 : 0u) : sb0 + (uint32_t)stage * b_stage16;
+                const bool last = c == nchunks - 1 && pass == npass - 1;
+                // hi x hi -> main accumulator `seg`; the cross terms (passes 1, 2) -> the correction accumulator behind the mains
+                const uint32_t ai = pass == 0 ? seg : (uint32_t)nseg;
+                const uint32_t d_tmem = d_buf + ai * coutp;
+                const uint32_t accumulate = (started >> ai) & 1u;
+                started |= 1u << ai;
+                if (elect_one()) {
+#pragma unroll
+                    for (int t = 0; t < NTAPS; ++t) {
+                        mma_w<HALF>(d_tmem, a_base + aoff[t], a_hi, b_cur + (uint32_t)(t * 2) * b_kstep, b_hi, idesc, t ? 1u : accumulate);
+                        if (two) mma_w<HALF>(d_tmem, a_base + aoff[t] + (2u * TC_QUAD_PITCH >> 4), a_hi, b_cur + (uint32_t)(t * 2 + 1) * b_kstep, b_hi, idesc, 1u);
+                    }
+                    mma_commit(&empty[stage]);                                // frees the smem stage when the MMAs retire
+                    if (last) mma_commit(&tmem_full[buf]);                    // accumulators complete -> epilogue
+                }
+                __syncwarp();
+                a_base += a_stage16;
+                if (++stage == stages) { stage = 0; phase ^= 1; a_base = sa0; }
+            }
+            b_base += b_chunk16;
+        }
+        if (++buf == nbuf) { buf = 0; buf_phase ^= 1; }
     }
 }
 }  // namespace tc
 
 // shared memory carve-up (offsets from the 1024-aligned base): [A stage 0..S) | B (resident: whole layer; streamed: S stages) | barriers
-template <bool HALF>
+template <bool HALF, bool LINKED>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -323,8 +388,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint64_t* full = (uint64_t*)(smem_b + ((b_bytes + 15) & ~(size_t)15));
     uint64_t* empty = full + TC_MAX_STAGES;
     uint64_t* tmem_full = empty + TC_MAX_STAGES;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* wfull = tmem_empty + 2;
+    uint64_t* tmem_empty = tmem_full + TC_MAX_BUFS;
+    uint64_t* wfull = tmem_empty + TC_MAX_BUFS;
     uint32_t* tmem_base_slot = (uint32_t*)(wfull + 1);
     float4* s_par = (float4*)(((uintptr_t)(tmem_base_slot + 1) + 15) & ~(uintptr_t)15);                  // per output channel: (s1, b1, s2, b2), out = lrelu(acc*s1 + b1)*s2 + b2
 
@@ -337,25 +402,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // <= 1/8 resolution have fewer tiles than SMs and sit at a 12-17 us launch + prologue floor each; this hides the prologue.
     if (p.pdl) asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
-    if (warp == 0 && lane == 0) {
+    if (warp == TC_WARP_TMA && lane == 0) {
         tc::prefetch_tmap(&p.mapA0);
         if (p.n1) tc::prefetch_tmap(&p.mapA1);
         if (p.x3) { tc::prefetch_tmap(&p.mapA0lo); if (p.n1) tc::prefetch_tmap(&p.mapA1lo); }
     }
-    if (warp == 1 && lane == 0) {
+    if (warp == TC_WARP_INIT && lane == 0) {
         for (int s = 0; s < TC_MAX_STAGES; ++s) { tc::mbar_init(&full[s], 1); tc::mbar_init(&empty[s], 1); }
-        for (int a = 0; a < 2; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], 8); }
+        for (int a = 0; a < TC_MAX_BUFS; ++a) { tc::mbar_init(&tmem_full[a], 1); tc::mbar_init(&tmem_empty[a], TC_EPI_WARPS); }
         tc::mbar_init(wfull, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
+    if (warp == TC_WARP_ALLOC) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tc::smem_u32(tmem_base_slot)), "n"(TC_TMEM_COLS) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    if (warp >= 4) {
+    if (warp < TC_EPI_WARPS) {
         // conv bias + BatchNorm(eval) + LeakyReLU as one branch-free form: BN->LReLU layers use (scale, shift', 1, 0),
         // the LReLU->BN layer (encoder layer2's first conv, model.py:30-32) uses (1, bias, scale, shift)
-        for (int c = threadIdx.x - 128; c < p.coutp; c += TC_THREADS - 128) {
+        for (int c = threadIdx.x; c < p.coutp; c += TC_EPI_WARPS * 32) {
             const float sc = __ldg(&p.scale[c]), sh = __ldg(&p.shift[c]), bi = __ldg(&p.bias[c]);
             s_par[c] = p.lrelu_first ? make_float4(1.0f, bi, sc, sh) : make_float4(sc, sh, 1.0f, 0.0f);
         }
@@ -365,13 +430,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     tc::fence_after_sync();
     const uint32_t tmem_base = *tmem_base_slot;
 
-    if (warp == 0) {
+    if (warp == TC_WARP_TMA) {
         // ===== TMA producer: warp-uniform loop, one elected lane issues (same reason as the MMA role below) ==========
         // row-strip mode: the apron rows of the sources are written by the neighbour GPUs; wait for this frame's flags
         bool waited = false;
         PtdSpinGuard guard;                                            // traps after PTD_SPIN_TIMEOUT_NS instead of hanging the GPU
+        if (LINKED)
         for (int i = 0; i < 4; ++i)
             if (p.link.wait[i]) { while ((int)(tc::ld_acquire_sys(p.link.wait[i]) - p.link.wait_epoch[i]) < 0) guard.tick(); waited = true; }
+        if (LINKED)
         for (int i = 0; i < 8; ++i)
             if (p.link.gather_wait[i]) { while ((int)(tc::ld_acquire_sys(p.link.gather_wait[i]) - p.link.epoch) < 0) guard.tick(); waited = true; }
         if (waited) asm volatile("fence.proxy.async;" ::: "memory");   // generic-proxy acquire -> async-proxy (TMA) reads
@@ -386,72 +453,109 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous launch has completed and its stores are visible
         int stage = 0; uint32_t phase = 0;
         const uint32_t stage_tx = TC_A_BYTES + (p.resident ? 0u : p.b_stage_bytes);
+        const int npass = p.x3 ? 3 : 1, n0 = p.n0;
         for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const int ph = item % p.nphases, tile = item / p.nphases;
-            const int x0 = (tile % p.tiles_x) * TC_TILE_W, y0 = (tile / p.tiles_x) * TC_TILE_H + p.src_yoff;
-            const int npass = p.x3 ? 3 : 1;
-            for (int e = 0; e < nchunks * npass; ++e) {
-                const int c = e / npass, pass = e - c * npass;
-                tc::mbar_wait(&empty[stage], phase ^ 1);
-                if (tc::elect_one()) {
-                    tc::mbar_expect_tx(&full[stage], stage_tx);
-                    // halo tile origin: pixel (x0 - 1, y0 - 1) = buffer row y0 (apron offset +1); x < 0 / x >= W are zero filled
-                    const CUtensorMap* map = c < p.n0 ? (pass == 2 ? &p.mapA0lo : &p.mapA0) : (pass == 2 ? &p.mapA1lo : &p.mapA1);
-                    tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, map, &full[stage], (x0 - 1) * (HALF ? 8 : 4), y0, (c < p.n0 ? c : c - p.n0) * 4);
-                    if (!p.resident) {
-                        const size_t blk = p.x3 ? (size_t)((ph * nchunks + c) * 2 + (pass == 1 ? 1 : 0)) : (size_t)(ph * nchunks + c);
-                        tc::bulk_load(smem_b + (size_t)stage * p.b_stage_bytes, (const uint8_t*)p.wpack + blk * p.b_stage_bytes, p.b_stage_bytes, &full[stage]);
+            const int ph = p.nphases > 1 ? (item & 3) : 0, tile = p.nphases > 1 ? (item >> 2) : item;
+            const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+            const int x0 = tx * TC_TILE_W, y0 = ty * TC_TILE_H + p.src_yoff;
+            for (int c = 0; c < nchunks; ++c) {
+                for (int pass = 0; pass < npass; ++pass) {
+                    tc::mbar_wait(&empty[stage], phase ^ 1);
+                    if (tc::elect_one()) {
+                        tc::mbar_expect_tx(&full[stage], stage_tx);
+                        // halo tile origin: pixel (x0 - 1, y0 - 1) = buffer row y0 (apron offset +1); x < 0 / x >= W are zero filled
+                        const CUtensorMap* map = c < n0 ? (pass == 2 ? &p.mapA0lo : &p.mapA0) : (pass == 2 ? &p.mapA1lo : &p.mapA1);
+                        tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, map, &full[stage], (x0 - 1) * (HALF ? 8 : 4), y0, (c < n0 ? c : c - n0) * 4);
+                        if (!p.resident) {
+                            const size_t blk = p.x3 ? (size_t)((ph * nchunks + c) * 2 + (pass == 1 ? 1 : 0)) : (size_t)(ph * nchunks + c);
+                            tc::bulk_load(smem_b + (size_t)stage * p.b_stage_bytes, (const uint8_t*)p.wpack + blk * p.b_stage_bytes, p.b_stage_bytes, &full[stage]);
+                        }
                     }
+                    __syncwarp();
+                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
-                __syncwarp();
-                if (++stage == p.stages) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1) {
+    } else if (warp == TC_WARP_MMA) {
         // ===== MMA issuer: the whole warp runs the (warp-uniform) loop so that descriptors live in uniform registers;
         //       one elected lane issues.  One tcgen05.mma costs a handful of uniform-datapath adds here - issued from divergent
         //       code the same loop cost ~135 cycles per MMA (R2UR + ELECT sequences) and was the kernel's bottleneck.
         if (p.resident) { tc::mbar_wait(wfull, 0); tc::fence_after_sync(); }
-        if (p.ntaps == 9) tc::mma_role<9, HALF>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, lane);
-        else tc::mma_role<4, HALF>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, lane);
-    } else if (warp >= 4) {
+        if (p.ntaps == 9) tc::mma_role<9, HALF>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base);
+        else tc::mma_role<4, HALF>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base);
+    } else if (warp < TC_EPI_WARPS) {
         // ===== epilogue: TMEM -> registers -> bias/BN/LeakyReLU -> CHW4 ============================================
+        // Two warps per SM sub-partition run this loop; with the N = 32 layers' MMAs at ~750 (f16) .. 1500 (tf32) cycles per tile it has
+        // to stay at a few hundred instructions per tile: the row-strip stores exist only in the LINKED variant of the kernel, every
+        // parameter is in a register, one integer division per tile.
         const int q = warp & 3;                                    // TMEM lane quarter this warp may read
-        const int half = (warp - 4) >> 2;                          // which of the alternating 16-column chunks this warp takes
+        const int half = warp >> 2;                                // which of the alternating 16-column chunks this warp takes
         const int m = q * 32 + lane;                               // pixel of the tile == TMEM lane
         const int ty = m >> 3, tx = m & 7;
-        int acc = 0; uint32_t acc_phase = 0;
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const int ph = item % p.nphases, tile = item / p.nphases;
-            const int x = (tile % p.tiles_x) * TC_TILE_W + tx, y = (tile / p.tiles_x) * TC_TILE_H + ty;
-            const bool valid = x < p.Ws && y < p.Hs;
-            const int oy = p.out_mul * y + (p.nphases > 1 ? (ph >> 1) : 0), ox = p.out_mul * x + (p.nphases > 1 ? (ph & 1) : 0);
-            float* orow = p.out.base + ((size_t)(oy + 1) * p.out.W + ox) * 4;
-            const size_t poff = ((size_t)((y >> 1) + p.link.pool_yoff + 1) * p.pool_out.W + (x >> 1)) * 4;
-            float* prow = p.pool_out.base ? p.pool_out.base + poff : nullptr;
-            tc::mbar_wait(&tmem_full[acc], acc_phase);
+        const int coutp = p.coutp, nphases = p.nphases, tiles_x = p.tiles_x, Ws = p.Ws, Hs = p.Hs, out_mul = p.out_mul, total = p.total_items;
+        const int nbuf = p.nbuf, nacc = p.nseg + (p.x3 ? 1 : 0), x3 = p.x3;
+        const uint32_t buf_cols = (uint32_t)p.buf_cols;
+        const float corr_scale = p.corr_scale;
+        const bool round_out = !HALF && p.round_out && !p.x3;     // fp16 storage rounds in the conversion, the split modes split in store16
+        const DnTensor out = p.out, pool_out = p.pool_out;
+        const int pool_yoff = LINKED ? p.link.pool_yoff : 0;
+        int buf = 0; uint32_t buf_phase = 0;
+        for (int item = blockIdx.x; item < total; item += gridDim.x) {
+            const int ph = nphases > 1 ? (item & 3) : 0, tile = nphases > 1 ? (item >> 2) : item;
+            const int tyi = tile / tiles_x, txi = tile - tyi * tiles_x;
+            const int x = txi * TC_TILE_W + tx, y = tyi * TC_TILE_H + ty;
+            const bool valid = x < Ws && y < Hs;
+            const int oy = out_mul * y + (ph >> 1), ox = out_mul * x + (ph & 1);
+            float* orow = out.base + ((size_t)(oy + 1) * out.W + ox) * 4;
+            const size_t poff = ((size_t)((y >> 1) + pool_yoff + 1) * pool_out.W + (x >> 1)) * 4;
+            float* prow = pool_out.base ? pool_out.base + poff : nullptr;
+            tc::mbar_wait(&tmem_full[buf], buf_phase);
             tc::fence_after_sync();
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)acc * TC_ACC_COLS;
-            for (int c0 = half * 16; c0 < p.coutp; c0 += 32) {
-                uint32_t r[16];
-                tc::tmem_ld16(taddr + c0, r);
-                tc::tmem_ld_wait();
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * buf_cols;
+            for (int c0 = half * 16; c0 < coutp; c0 += 32) {
+                float acc[16];
+                {
+                    uint32_t r[16];
+                    int a = nacc - 1;
+                    if (x3) {                                      // correction accumulator (scaled) + the last main accumulator
+                        uint32_t r2[16];
+                        tc::tmem_ld16(taddr + (uint32_t)(a * coutp + c0), r);
+                        tc::tmem_ld16(taddr + (uint32_t)((a - 1) * coutp + c0), r2);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] = fmaf(__uint_as_float(r[j]), corr_scale, __uint_as_float(r2[j]));
+                        a -= 2;
+                    } else {
+                        tc::tmem_ld16(taddr + (uint32_t)(a * coutp + c0), r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
+                        a -= 1;
+                    }
+                    for (; a >= 0; --a) {
+                        tc::tmem_ld16(taddr + (uint32_t)(a * coutp + c0), r);
+                        tc::tmem_ld_wait();
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+                    }
+                }
                 float o[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) {
                     const float4 k = s_par[c0 + j];                // broadcast LDS.128
-                    float v = fmaf(__uint_as_float(r[j]), k.x, k.y);
+                    float v = fmaf(acc[j], k.x, k.y);
                     v = fmaxf(v, 0.1f * v);                        // LeakyReLU(0.1)
                     v = fmaf(v, k.z, k.w);
-                    o[j] = (!HALF && p.round_out && !p.x3) ? tc::round_tf32(v) : v;   // fp16 storage rounds in the conversion, 3xTF32 splits in store16
+                    o[j] = round_out ? tc::round_tf32(v) : v;
                 }
                 if (valid) {
-                    tc::store16(p.out, orow, c0, o);
-                    // row-strip mode: our first / last row is the neighbour's bottom / top apron row - stored straight over NVLink
-                    if (oy == 0 && p.link.out_up.base)
-                        tc::store16(p.link.out_up, p.link.out_up.base + ((size_t)(p.link.out_up.rows + 1) * p.out.W + ox) * 4, c0, o);
-                    if (oy == p.out.rows - 1 && p.link.out_down.base)
-                        tc::store16(p.link.out_down, p.link.out_down.base + (size_t)ox * 4, c0, o);
+                    tc::store16(out, orow, c0, o);
+                    if (LINKED) {                                  // row-strip mode: our first / last row is the neighbour's bottom / top apron row - stored straight over NVLink
+                        if (oy == 0 && p.link.out_up.base)
+                            tc::store16(p.link.out_up, p.link.out_up.base + ((size_t)(p.link.out_up.rows + 1) * out.W + ox) * 4, c0, o);
+                        if (oy == out.rows - 1 && p.link.out_down.base)
+                            tc::store16(p.link.out_down, p.link.out_down.base + (size_t)ox * 4, c0, o);
+                    }
                 }
                 if (prow) {                                        // MaxPool2d(2): partners are lanes ^1 (x) and ^8 (y)
 #pragma unroll
@@ -460,27 +564,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         o[j] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
                     }
                     if (valid && !(tx & 1) && !(ty & 1)) {
-                        tc::store16(p.pool_out, prow, c0, o);
+                        tc::store16(pool_out, prow, c0, o);
+                        if (LINKED) {
 #pragma unroll 1
-                        for (int r = 0; r < 8; ++r)
-                            if (p.link.gather_base[r]) { DnTensor t = p.pool_out; t.base = p.link.gather_base[r]; tc::store16(t, t.base + poff, c0, o); }
-                        if ((y >> 1) == 0 && p.link.pool_up.base)
-                            tc::store16(p.link.pool_up, p.link.pool_up.base + ((size_t)(p.link.pool_up.rows + 1) * p.pool_out.W + (x >> 1)) * 4, c0, o);
-                        if ((y >> 1) == p.pool_out.rows - 1 && p.link.pool_down.base)
-                            tc::store16(p.link.pool_down, p.link.pool_down.base + (size_t)(x >> 1) * 4, c0, o);
+                            for (int r = 0; r < 8; ++r)
+                                if (p.link.gather_base[r]) { DnTensor t = pool_out; t.base = p.link.gather_base[r]; tc::store16(t, t.base + poff, c0, o); }
+                            if ((y >> 1) == 0 && p.link.pool_up.base)
+                                tc::store16(p.link.pool_up, p.link.pool_up.base + ((size_t)(p.link.pool_up.rows + 1) * pool_out.W + (x >> 1)) * 4, c0, o);
+                            if ((y >> 1) == pool_out.rows - 1 && p.link.pool_down.base)
+                                tc::store16(p.link.pool_down, p.link.pool_down.base + (size_t)(x >> 1) * 4, c0, o);
+                        }
                     }
                 }
             }
             tc::fence_before_sync();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&tmem_empty[acc]);
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (lane == 0) tc::mbar_arrive(&tmem_empty[buf]);
+            if (++buf == nbuf) { buf = 0; buf_phase ^= 1; }
         }
     }
-    if (p.link.done && warp >= 4) __threadfence_system();          // our apron stores into the neighbours' memory, before the flag
+    if (LINKED && p.link.done && warp < TC_EPI_WARPS) __threadfence_system();          // our apron stores into the neighbours' memory, before the flag
     tc::fence_before_sync();
     __syncthreads();
-    if (p.link.done && threadIdx.x == 0) {
+    if (LINKED && p.link.done && threadIdx.x == 0) {
         // last CTA of the launch: every CTA's stores are ordered before its counter increment, so the flags can be raised
         __threadfence();
         const uint32_t old = atomicAdd(p.link.done, 1u);
@@ -492,7 +598,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 if (p.link.gather_sig[i]) tc::st_release_sys(p.link.gather_sig[i], p.link.epoch);
         }
     }
-    if (warp == 2) {
+    if (warp == TC_WARP_ALLOC) {
         tc::fence_after_sync();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TC_TMEM_COLS) : "memory");
     }
@@ -568,7 +674,20 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     p.tiles_x = (Ws + TC_TILE_W - 1) / TC_TILE_W; p.tiles_y = (Hs + TC_TILE_H - 1) / TC_TILE_H;
     p.total_items = p.tiles_x * p.tiles_y * p.nphases;
     p.x3 = d.src0.lo_off ? 1 : 0;
-    if (p.x3 && (half || (d.src1.base && !d.src1.lo_off))) PTD_FAIL(PTD_ERR_ARG, "tc conv: 3xTF32 needs fp32 hi/lo sources");
+    if (p.x3 && d.src1.base && !d.src1.lo_off) PTD_FAIL(PTD_ERR_ARG, "tc conv: split-operand modes need hi/lo copies of both sources");
+    // accumulators (see TcParams): buffers of nseg main accumulators [+ the correction accumulator], at least two buffers in 512 columns
+    {
+        const int max_accs = (TC_TMEM_COLS / 2) / coutp;
+        p.nseg = p.x3 ? std::max(1, std::min(std::min(TC_MAX_SEGS, max_accs - 1), nch)) : 1;
+        p.buf_cols = (p.nseg + p.x3) * coutp;
+        p.nbuf = std::min(TC_MAX_BUFS, TC_TMEM_COLS / p.buf_cols);
+        if (p.nbuf < 2) PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: %d accumulators of %d columns do not fit twice in tensor memory", p.nseg + p.x3, coutp);
+        p.seg_start = 0;
+        for (int c = 1; c < nch; ++c)
+            if ((c * p.nseg) / nch != ((c - 1) * p.nseg) / nch) p.seg_start |= 1u << c;
+        p.corr_scale = half ? 1.0f / 2048.0f : 1.0f;
+        if (nch > 32) PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: %d channel chunks (> 32)", nch);
+    }
     const int nblk = p.x3 ? 2 : 1;                           // weight blocks per (phase, chunk): hi [, lo]
     p.b_stage_bytes = (uint32_t)(p.ntaps * coutp * 64);
     p.w_total_bytes = (uint32_t)(p.nphases * nch * nblk) * p.b_stage_bytes;
@@ -600,8 +719,11 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
                     const int cl = c < c0p ? c : c - c0p, chunk = (c < c0p ? 0 : p.n0) + cl / CH, r = cl % CH;
                     const int epv = CH / 4, kstep = r / (2 * epv), kq = (r % (2 * epv)) / epv, ke = r % epv;
                     const size_t off = (((((size_t)((ph * nch + chunk) * nblk) * p.ntaps + t) * 2 + kstep) * 2 + kq) * (size_t)coutp + (size_t)n) * epv + ke;
-                    if (half) pack_h[off] = __float2half_rn(s);
-                    else {
+                    if (half) {
+                        const __half hi = __float2half_rn(s);
+                        pack_h[off] = hi;
+                        if (p.x3) pack_h[off + (size_t)p.b_stage_bytes / 2] = __float2half_rn((s - __half2float(hi)) * 2048.0f);   // lo block, scaled like the activations' lo copy
+                    } else {
                         const float hi = host_round_tf32(s);
                         pack[off] = hi;
                         if (p.x3) pack[off + (size_t)p.b_stage_bytes / 4] = host_round_tf32(s - hi);   // the lo block follows the hi block
@@ -643,9 +765,11 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     plan.grid = p.total_items < sms ? p.total_items : sms;
-    plan.smem = (size_t)p.stages * TC_A_BYTES + ((b_bytes + 15) & ~(size_t)15) + 1024 + 256 + TC_ACC_COLS * 16;
-    if (cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess)
+    plan.smem = (size_t)p.stages * TC_A_BYTES + ((b_bytes + 15) & ~(size_t)15) + 1024 + 512 + TC_ACC_COLS * 16;
+    if (cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
+        cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess)
         PTD_FAIL(PTD_ERR_CUDA, "tc conv: cannot reserve shared memory: %s", cudaGetErrorString(cudaGetLastError()));
     plan.valid = 1;
     return PTD_OK;
@@ -653,19 +777,17 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
 
 inline ptd_status tc_conv_launch(TcConvPlan& plan, cudaStream_t st, int* launches, bool* pooled) {
     if (!plan.valid) PTD_FAIL(PTD_ERR_STATE, "tc conv: plan not built");
-    if (plan.p.pdl) {
-        cudaLaunchConfig_t cfg;
-        memset(&cfg, 0, sizeof cfg);
-        cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = plan.smem; cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        attr[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        const cudaError_t e = plan.p.half ? cudaLaunchKernelEx(&cfg, conv_tc_kernel<true>, plan.p) : cudaLaunchKernelEx(&cfg, conv_tc_kernel<false>, plan.p);
-        if (e != cudaSuccess) PTD_FAIL(PTD_ERR_CUDA, "tc conv: cudaLaunchKernelEx failed: %s", cudaGetErrorString(e));
-    }
-    else if (plan.p.half) conv_tc_kernel<true><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.p);
-    else conv_tc_kernel<false><<<plan.grid, TC_THREADS, plan.smem, st>>>(plan.p);
+    void (*kern)(const TcParams) = plan.p.half ? (plan.p.linked ? conv_tc_kernel<true, true> : conv_tc_kernel<true, false>)
+                                               : (plan.p.linked ? conv_tc_kernel<false, true> : conv_tc_kernel<false, false>);
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = plan.smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = plan.p.pdl ? 1 : 0;
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, plan.p);
+    if (e != cudaSuccess) PTD_FAIL(PTD_ERR_CUDA, "tc conv: cudaLaunchKernelEx failed: %s", cudaGetErrorString(e));
     if (launches) ++*launches;
     if (pooled) *pooled = plan.p.pool_out.base != nullptr;
     return PTD_OK;

@@ -1,6 +1,6 @@
 // ptd_cli - headless drop-in for the reference executable's frame loop (Inference/src/main.cpp:47-87, :120-168).
 //
-//   ptd_cli SCENEFILE.txt [--weights model.ptdw] [--frames N] [--dphi RAD] [--mode tf32|f16|fp32|3xtf32|traced] [--sort-material]
+//   ptd_cli SCENEFILE.txt [--weights model.ptdw] [--frames N] [--dphi RAD] [--mode tf32|f16|2xf16|fp32|3xtf32|traced] [--sort-material]
 //           [--res W H] [--depth D] [--out PREFIX] [--device K] [--host-roundtrip] [--serial] [--reset-every N] [--quiet]
 //
 // `ptd_cli SCENEFILE.txt` is the reference's command line (main.cpp:50-56).  Every frame repeats runCuda(): the orbit camera is
@@ -111,7 +111,7 @@ static bool write_pfm(const std::string& path, const float* rgb, int W, int H) {
 
 int main(int argc, char** argv) {
     if (argc < 2) {
-        printf("Usage: %s SCENEFILE.txt [--weights model.ptdw] [--frames N] [--dphi RAD] [--mode tf32|f16|fp32|3xtf32|traced] [--sort-material]\n"
+        printf("Usage: %s SCENEFILE.txt [--weights model.ptdw] [--frames N] [--dphi RAD] [--mode tf32|f16|2xf16|fp32|3xtf32|traced] [--sort-material]\n"
                "       [--res W H] [--depth D] [--out PREFIX] [--device K] [--host-roundtrip] [--serial] [--reset-every N] [--quiet]\n", argv[0]);   // main.cpp:50-53
         return 1;
     }
@@ -143,6 +143,7 @@ int main(int argc, char** argv) {
     else if (mode == "fp32") dn_flags = PTD_DN_FP32;
     else if (mode == "3xtf32") dn_flags = PTD_DN_3XTF32;
     else if (mode == "f16") dn_flags = PTD_DN_F16;
+    else if (mode == "2xf16") dn_flags = PTD_DN_2XF16;
     else if (mode == "traced") dn_flags = PTD_DN_FP32_BATCH_STATS;     // what the reference's TorchScript export runs; combine with --reset-every 1
     else { fprintf(stderr, "ptd_cli: unknown --mode %s\n", mode.c_str()); return 1; }
 

@@ -268,8 +268,11 @@ __global__ void chw4_to_nchw(const DnTensor in, int C, float* __restrict__ out) 
     if (in.esize == 4) {
         const size_t o = (size_t)(c >> 2) * in.quad_stride() + ((size_t)(y + 1) * W + x) * 4 + (c & 3);
         out[i] = in.lo_off ? in.base[o] + in.base[o + in.lo_off] : in.base[o];
+    } else {
+        const float* v8 = in.base + (size_t)(c >> 3) * in.quad_stride() + ((size_t)(y + 1) * W + x) * 4;
+        const float hi = __half2float(reinterpret_cast<const __half*>(v8)[c & 7]);
+        out[i] = in.lo_off ? hi + __half2float(reinterpret_cast<const __half*>(v8 + in.lo_off)[c & 7]) * (1.0f / 2048.0f) : hi;      // 2xF16: lo is stored x 2^11
     }
-    else out[i] = __half2float(reinterpret_cast<const __half*>(in.base + (size_t)(c >> 3) * in.quad_stride() + ((size_t)(y + 1) * W + x) * 4)[c & 7]);
 }
 
 // ---- weights ---------------------------------------------------------------------------------------------------------
@@ -393,7 +396,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     if (!weights_path || !out || H <= 0 || W <= 0) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: bad argument");
     *out = nullptr;
     if (ptd_device_count() <= device || device < 0) PTD_FAIL(PTD_ERR_CUDA, "ptd_dn_create: CUDA device %d not available (no CPU fallback exists)", device);
-    if (flags != PTD_DN_FP32 && flags != PTD_DN_TF32 && flags != PTD_DN_F16 && flags != PTD_DN_3XTF32 && flags != PTD_DN_FP32_BATCH_STATS) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: unknown flags %u", flags);
+    if (flags != PTD_DN_FP32 && flags != PTD_DN_TF32 && flags != PTD_DN_F16 && flags != PTD_DN_3XTF32 && flags != PTD_DN_2XF16 && flags != PTD_DN_FP32_BATCH_STATS) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create: unknown flags %u", flags);
     const int Hp = (H + 31) / 32 * 32, Wp = (W + 31) / 32 * 32;
     if (!strip) { row0 = 0; rows = Hp; }
     if (row0 < 0 || rows <= 0 || row0 % 32 || rows % 32 || row0 + rows > Hp) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_create_strip: rows [%d, %d) must be multiples of 32 inside the padded frame of %d rows", row0, row0 + rows, Hp);
@@ -422,13 +425,13 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
 
     // ---- activation arena: every tensor the convs read or write, one allocation (one IPC handle per strip) ----
     size_t arena_bytes = 0;
-    const int act_esize = flags == PTD_DN_F16 ? 2 : 4;       // fp16 activations everywhere but the network's output
+    const int act_esize = (flags == PTD_DN_F16 || flags == PTD_DN_2XF16) ? 2 : 4;       // fp16 activations everywhere but the network's output
     auto tnew = [&](int c, int lvl, int esize = 0) -> int {
         DnTensor t;
         const bool full = strip && lvl >= h->repl_level;                // replicated level: every strip holds the whole tensor
         t.cp = cpad(c); t.rows = (full ? Hp : rows) >> lvl; t.W = Wp >> lvl; t.esize = esize ? esize : act_esize;
         h->tensor_level.push_back(lvl); h->tensor_full.push_back(full ? 1 : 0);
-        const bool pair = flags == PTD_DN_3XTF32 && esize == 0;        // hi copy followed by the lo copy
+        const bool pair = (flags == PTD_DN_3XTF32 || flags == PTD_DN_2XF16) && esize == 0;        // hi copy followed by the lo copy
         if (pair) t.lo_off = (t.floats() + 255) & ~(size_t)255;
         h->tensors.push_back(t);
         h->tensor_off.push_back(arena_bytes);
@@ -738,6 +741,7 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
             } else if (L.pool != -1 && h->tensor_full[L.pool] && !h->tensor_full[o]) {
                 k.pool_yoff = h->row0 >> h->tensor_level[L.pool];           // a single strip that is not the whole frame cannot exist; kept for symmetry
             }
+            plan.p.linked = h->nranks > 1 ? 1 : 0;
             plan.p.pdl = (h->pdl && li > 0 && !h->profiling) ? 1 : 0;       // the first conv follows pack_gbuffer, which does not trigger early
             ptd_status rc = tc_conv_launch(plan, st, &h->launches, nullptr);
             if (rc != PTD_OK) return rc;

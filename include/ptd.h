@@ -138,9 +138,14 @@ ptd_status ptd_bvh_probe_order(const ptd_scene*, int nrays, unsigned seed, int c
 enum {
     PTD_DN_FP32 = 0u,             /* fp32 FFMA convolutions (strict-parity path)                                   */
     PTD_DN_TF32 = 1u,             /* tcgen05 kind::tf32 tensor-core convolutions, fp32 accumulate in TMEM (default of the CLI) */
-    PTD_DN_3XTF32 = 2u,           /* tcgen05 kind::tf32 with hi/lo operand splitting (hi*hi + hi*lo + lo*hi): fp32-class accuracy on the tensor cores */
+    PTD_DN_3XTF32 = 2u,           /* tcgen05 kind::tf32 with hi/lo operand splitting (hi*hi + hi*lo + lo*hi, the cross terms in their own accumulator) */
     PTD_DN_F16 = 3u,              /* fp16 activation storage (same 10-bit mantissa as tf32, half the HBM / shared-memory bytes) + tcgen05 kind::f16,
                                      fp32 accumulate; the denoised frame itself is written in fp32.  Same stated tolerance as PTD_DN_TF32. */
+    PTD_DN_2XF16 = 5u,            /* THE CONTRACT MODE of the tensor-core engine (rel-L2 <= 1e-5, max-abs <= 1e-4 against the fp32 reference model):
+                                     every fp32 value v is stored as two fp16 numbers, hi = f16(v) and lo = f16((v - hi) * 2^11) - 22 mantissa bits - and
+                                     every conv runs hi*hi + (hi*lo + lo*hi) * 2^-11 on tcgen05 kind::f16 (K = 16 per MMA: half the MMAs of 3xTF32), the
+                                     hi*hi chain cut into up to four TMEM accumulators and the cross terms kept in a fifth, summed in fp32 by the
+                                     epilogue.  Same bytes per activation as fp32 storage.  |G-buffer values| are clamped to 65504 (fp16 range). */
     PTD_DN_FP32_BATCH_STATS = 4u  /* TorchScript-export compatibility: the fp32 engine with every BatchNorm normalising by the
                                      statistics of its current input, as the module traced by convert_to_torchscript.py:26-30 (never put in
                                      eval mode) does; call with reset_hidden = 1 every frame to mimic its j == 0.  Slow path (4 launches per layer). */

@@ -101,7 +101,7 @@ def dn_720p_reference():
     return xs, refs, hidden
 
 
-@pytest.mark.parametrize("mode", ["fp32", "3xtf32", "tf32", "f16"])
+@pytest.mark.parametrize("mode", ["fp32", "2xf16", "3xtf32", "tf32", "f16"])
 def test_denoiser_720p_three_recurrent_frames_vs_oracle(mode, dn_720p_reference, tmp_path):
     capi = _capi()
     from ai_path_tracer_denoiser_b200 import weights

@@ -19,7 +19,7 @@ from conftest import GOLDEN
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": (1e-4, 1e-5), "3xtf32": (3e-4, 1e-4), "tf32": (2e-2, 5e-3), "f16": (2e-2, 5e-3)}
+TOL = {"fp32": (1e-4, 1e-5), "2xf16": (1e-4, 1e-5), "3xtf32": (1e-4, 1e-5), "tf32": (2e-2, 5e-3), "f16": (2e-2, 5e-3)}
 
 
 def _capi():
@@ -41,10 +41,10 @@ def _err(y, ref):
 
 
 def _mode(capi, mode):
-    return {"fp32": capi.DN_FP32, "tf32": capi.DN_TF32, "f16": capi.DN_F16, "3xtf32": capi.DN_3XTF32}[mode]
+    return {"fp32": capi.DN_FP32, "tf32": capi.DN_TF32, "f16": capi.DN_F16, "3xtf32": capi.DN_3XTF32, "2xf16": capi.DN_2XF16}[mode]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "f16", "3xtf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "f16", "3xtf32", "2xf16"])
 @pytest.mark.parametrize("name", ["dn_64x96", "dn_32x32"])
 def test_matches_reference_model_golden(name, mode, wfile):
     capi = _capi()
@@ -60,7 +60,7 @@ def test_matches_reference_model_golden(name, mode, wfile):
     assert ma <= 4 * TOL[mode][0], ma
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "f16", "3xtf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "f16", "3xtf32", "2xf16"])
 def test_pad_crop_recurrence_and_reset_vs_oracle(mode, wfile):
     """Non-/32 frame (zero pad bottom/right, crop; decision D3), 5-frame recurrence, then a reset."""
     capi = _capi()
@@ -87,7 +87,7 @@ def test_pad_crop_recurrence_and_reset_vs_oracle(mode, wfile):
     assert again.tobytes() == first.tobytes()                                # reset really zeroes the six hidden states
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32", "f16", "3xtf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "f16", "3xtf32", "2xf16"])
 def test_full_size_720p_properties(mode, wfile):
     """BASELINE size (720p -> 736x1280 padded): finite, deterministic, translation-consistent in the interior
     (a frame shifted by 32 px gives the shifted output away from the borders: the net is fully convolutional)."""
@@ -116,7 +116,7 @@ def repl_levels(request, monkeypatch):
     return request.param
 
 
-@pytest.mark.parametrize("mode", ["tf32", "f16", "3xtf32"])
+@pytest.mark.parametrize("mode", ["tf32", "f16", "3xtf32", "2xf16"])
 @pytest.mark.parametrize("nstrips", [2, 3])
 def test_row_strips_equal_the_full_frame(nstrips, mode, wfile, repl_levels):
     """Multi-GPU tiling on ONE device: the frame cut into row strips (32-row aligned, uneven), each strip a handle with its

@@ -35,7 +35,8 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint
 }
 
 // a, b: operand tiles already in the dense no-swizzle K-major core-matrix layout (element (row, 16-byte k vector v) at (row / 8) * 256 + v * 128 + (row % 8) * 16)
-__global__ void __launch_bounds__(128, 1) umma_accum_kernel(const uint8_t* a, const uint8_t* b, int reps, int tf32, float* out) {
+// schedule entry: a tile index | b tile index << 8 | accumulator << 16 (accumulator k = TMEM columns [16k, 16k + 16)); sched == nullptr: MMA r uses tile r % T_TILES
+__global__ void __launch_bounds__(128, 1) umma_accum_kernel(const uint8_t* a, const uint8_t* b, int reps, int tf32, float* out, const uint32_t* sched, int nacc) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* sa = smem;
@@ -50,7 +51,7 @@ __global__ void __launch_bounds__(128, 1) umma_accum_kernel(const uint8_t* a, co
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 32;" ::"r"(smem_u32(&tmem_slot)) : "memory");
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 256;" ::"r"(smem_u32(&tmem_slot)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -64,12 +65,17 @@ __global__ void __launch_bounds__(128, 1) umma_accum_kernel(const uint8_t* a, co
         uint32_t pred;
         asm volatile("{\n\t.reg .pred P;\n\telect.sync _|P, 0xffffffff;\n\tselp.u32 %0, 1, 0, P;\n\t}" : "=r"(pred));
         if (pred) {
+            uint32_t started = 0;
             for (int i = 0; i < reps; ++i) {
-                const int t = i % T_TILES;
-                const uint64_t ad = make_desc(smem_u32(sa + t * A_TILE), 128, 256);
-                const uint64_t bd = make_desc(smem_u32(sb + t * B_TILE), 128, 256);
-                if (tf32) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(i ? 1 : 0) : "memory");
-                else asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem), "l"(ad), "l"(bd), "r"(idesc), "r"(i ? 1 : 0) : "memory");
+                const uint32_t e = sched ? sched[i] : (uint32_t)((i % T_TILES) | ((i % T_TILES) << 8));
+                const uint32_t acc = e >> 16;
+                const uint64_t ad = make_desc(smem_u32(sa + (e & 255u) * A_TILE), 128, 256);
+                const uint64_t bd = make_desc(smem_u32(sb + ((e >> 8) & 255u) * B_TILE), 128, 256);
+                const uint32_t accumulate = (started >> acc) & 1u;
+                started |= 1u << acc;
+                const uint32_t tmem_d = tmem + acc * NCOL;
+                if (tf32) asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc), "r"(accumulate) : "memory");
+                else asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\ttcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d), "l"(ad), "l"(bd), "r"(idesc), "r"(accumulate) : "memory");
             }
             asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar)) : "memory");
         }
@@ -77,19 +83,24 @@ __global__ void __launch_bounds__(128, 1) umma_accum_kernel(const uint8_t* a, co
     }
     asm volatile("{\n\t.reg .pred P1;\n\tW:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n\t@P1 bra D;\n\tbra W;\n\tD:\n\t}" ::"r"(smem_u32(&bar)) : "memory");
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t r[16];
-    const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-                   "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-                 : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    for (int j = 0; j < 16; ++j) out[threadIdx.x * 16 + j] = __uint_as_float(r[j]);
+    float total[16];
+    for (int j = 0; j < 16; ++j) total[j] = 0.f;
+    for (int k = nacc - 1; k >= 0; --k) {                       // smallest-magnitude accumulators first (the correction terms), fp32 round-to-nearest adds
+        uint32_t r[16];
+        const uint32_t taddr = tmem + ((uint32_t)(warp * 32) << 16) + (uint32_t)k * NCOL;
+        asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+                     : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                       "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+                     : "r"(taddr));
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+        for (int j = 0; j < 16; ++j) total[j] += __uint_as_float(r[j]);
+    }
+    for (int j = 0; j < 16; ++j) out[threadIdx.x * 16 + j] = total[j];
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 1) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 32;" ::"r"(tmem) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 256;" ::"r"(tmem) : "memory");
     }
 }
 
@@ -141,7 +152,7 @@ int main() {
             CHECK(cudaMemcpy(d_b, pb.data(), pb.size(), cudaMemcpyHostToDevice));
             const int REPS[] = {1, 2, 4, 18, 72, 216, 1024};
             for (int reps : REPS) {
-                umma_accum_kernel<<<1, 128, 96 * 1024>>>(d_a, d_b, reps, tf32, d_out);
+                umma_accum_kernel<<<1, 128, 96 * 1024>>>(d_a, d_b, reps, tf32, d_out, nullptr, 1);
                 CHECK(cudaDeviceSynchronize());
                 std::vector<float> out(128 * 16);
                 CHECK(cudaMemcpy(out.data(), d_out, out.size() * 4, cudaMemcpyDeviceToHost));
@@ -172,6 +183,91 @@ int main() {
                 printf("%-6s %-9s %5d |", tf32 ? "tf32" : "f16", data == 0 ? "positive" : "signed", reps);
                 for (int i = 0; i < 3; ++i) printf(" %+9.2f %8.2f %8.2f |", st[i][0] / cnt, std::sqrt(st[i][1] / cnt), st[i][2]);
                 printf(" %8.1f%% %8.1f%%\n", 100.0 * eq_rn / cnt, 100.0 * eq_rz / cnt);
+            }
+        }
+    // ---- part 2: fp32 dot products of length K_total through split operands, the conv engine's chunk order ----------------------------
+    // a = activations (post-LeakyReLU statistics: 0.55 |N(0,1)| mostly positive), b = weights N(0, 1); fp32 values split into
+    //   3xTF32:  hi = tf32(v), lo = tf32(v - hi);  passes per K step: hi*hi, hi*lo, lo*hi  (kind::tf32, K = 8 per MMA)
+    //   2xF16 :  hi = f16(v),  lo = f16((v - hi) * 2^11)   (operands pre-scaled into fp16's normal range);  passes hi*hi | hi*lo, lo*hi, the
+    //            correction accumulator scaled back by 2^-11 in the epilogue  (kind::f16, K = 16 per MMA)   [two accumulators only]
+    // with the three passes chained into ONE accumulator (what PTD_DN_3XTF32 did in round 1), into TWO (main: hi*hi, correction: the cross
+    // terms; summed in fp32 after the loop), and into main accumulators split every `seg` K steps (fewer truncating adds per accumulator).
+    printf("# split-operand dot products, M = 128 x N = 16 outputs; error vs the exact (double) dot product of the fp32 operands\n");
+    printf("%-8s %7s %-34s %12s %12s %12s\n", "scheme", "K", "accumulators", "rel-L2", "max rel", "mean signed");
+    uint32_t* d_sched; CHECK(cudaMalloc(&d_sched, 4096 * 4));
+    for (int scheme = 0; scheme < 2; ++scheme)                      // 0: 3xTF32, 1: 2xF16
+        for (int Ktot : {144, 576, 1824}) {
+            const int K = scheme == 0 ? 8 : 16, steps = Ktot / K, epv = K / 2;
+            if (steps > T_TILES / 2 * 8) {}
+            // operands: `steps` K-steps, but only T_TILES / 2 = 8 distinct (hi, lo) tile pairs fit in shared memory: step s uses pair s % 8
+            const int NP = T_TILES / 2;
+            std::vector<float> A((size_t)NP * 128 * K), B((size_t)NP * NCOL * K);
+            uint64_t seed = 99 + scheme;
+            auto nrm = [&]() { double u1 = urand(seed) + 1e-12, u2 = urand(seed); return std::sqrt(-2.0 * std::log(u1)) * std::cos(6.283185307179586 * u2); };
+            for (auto& v : A) { double g = nrm(); v = (float)(g > 0 ? 0.55 * g : 0.055 * g); }
+            for (auto& v : B) v = (float)(0.06 * nrm());
+            std::vector<uint8_t> pa(T_TILES * A_TILE, 0), pb(T_TILES * B_TILE, 0);
+            auto put = [&](std::vector<uint8_t>& dst, size_t tile_off, int row, int k, float v) {
+                const size_t off = tile_off + (size_t)(row / 8) * 256 + (size_t)(k / epv) * 128 + (size_t)(row % 8) * 16 + (size_t)(k % epv) * (scheme == 0 ? 4 : 2);
+                if (scheme == 0) memcpy(&dst[off], &v, 4);
+                else { __half h = __float2half_rn(v); memcpy(&dst[off], &h, 2); }
+            };
+            const float lo_scale = scheme == 0 ? 1.f : 2048.f;
+            auto split = [&](float v, float& hi, float& lo) {
+                if (scheme == 0) { hi = round_tf32(v); lo = round_tf32(v - hi); }
+                else { hi = __half2float(__float2half_rn(v)); lo = __half2float(__float2half_rn((v - hi) * lo_scale)); }
+            };
+            for (int t = 0; t < NP; ++t) {                           // tile 2t = hi, tile 2t + 1 = lo
+                for (int m = 0; m < 128; ++m) for (int k = 0; k < K; ++k) { float hi, lo; split(A[((size_t)t * 128 + m) * K + k], hi, lo); put(pa, (size_t)(2 * t) * A_TILE, m, k, hi); put(pa, (size_t)(2 * t + 1) * A_TILE, m, k, lo); }
+                for (int n = 0; n < NCOL; ++n) for (int k = 0; k < K; ++k) { float hi, lo; split(B[((size_t)t * NCOL + n) * K + k], hi, lo); put(pb, (size_t)(2 * t) * B_TILE, n, k, hi); put(pb, (size_t)(2 * t + 1) * B_TILE, n, k, lo); }
+            }
+            CHECK(cudaMemcpy(d_a, pa.data(), pa.size(), cudaMemcpyHostToDevice));
+            CHECK(cudaMemcpy(d_b, pb.data(), pb.size(), cudaMemcpyHostToDevice));
+            std::vector<double> exact(128 * NCOL, 0.0);
+            for (int m = 0; m < 128; ++m) for (int n = 0; n < NCOL; ++n) { double e = 0; for (int st = 0; st < steps; ++st) { const int t = st % NP; for (int k = 0; k < K; ++k) e += (double)A[((size_t)t * 128 + m) * K + k] * (double)B[((size_t)t * NCOL + n) * K + k]; } exact[m * NCOL + n] = e; }
+            struct Var { const char* name; int nmain; int split_corr; };
+            const Var vars[] = {{"one (hi*hi, hi*lo, lo*hi chained)", 1, 0}, {"two (main | correction)", 1, 1}, {"main split in 4 | correction", 4, 1}, {"main split in 12 | correction", 12, 1}, {"single pass hi*hi only", 1, 2}};
+            for (const Var& v : vars) {
+                if (scheme == 1 && v.split_corr == 0) continue;      // 2xF16 needs the correction accumulator (it carries the 2^11 scale)
+                std::vector<uint32_t> sc;
+                for (int st = 0; st < steps; ++st) {
+                    const uint32_t t = (uint32_t)(st % NP), hi = 2 * t, lo = 2 * t + 1;
+                    const uint32_t main_acc = (uint32_t)((long long)st * v.nmain / steps), corr_acc = v.split_corr ? (uint32_t)v.nmain : main_acc;
+                    sc.push_back(hi | (hi << 8) | (main_acc << 16));
+                    if (v.split_corr != 2) { sc.push_back(hi | (lo << 8) | (corr_acc << 16)); sc.push_back(lo | (hi << 8) | (corr_acc << 16)); }
+                }
+                const int nacc = v.nmain + (v.split_corr == 1 ? 1 : 0);
+                CHECK(cudaMemcpy(d_sched, sc.data(), sc.size() * 4, cudaMemcpyHostToDevice));
+                if (scheme == 1 && v.split_corr == 1) {
+                    // the correction accumulator holds 2^11 x the cross terms: the kernel's plain sum would be wrong, so read the accumulators separately:
+                    // run twice, main accumulators only (nacc - 1) and all, and combine on the host: total = main + (all - main) / 2^11
+                    std::vector<float> o_main(128 * 16), o_all(128 * 16);
+                    umma_accum_kernel<<<1, 128, 96 * 1024>>>(d_a, d_b, (int)sc.size(), scheme == 0, d_out, d_sched, nacc - 1); CHECK(cudaDeviceSynchronize());
+                    CHECK(cudaMemcpy(o_main.data(), d_out, o_main.size() * 4, cudaMemcpyDeviceToHost));
+                    // correction alone: a schedule view where the kernel sums only accumulator index nmain -> emulate by summing all then subtracting is lossy; instead remap: correction to accumulator 0, mains shifted up, and read 1
+                    std::vector<uint32_t> sc2 = sc;
+                    for (auto& e : sc2) { const uint32_t acc = e >> 16; e = (e & 0xffffu) | ((acc == (uint32_t)v.nmain ? 0u : acc + 1u) << 16); }
+                    CHECK(cudaMemcpy(d_sched, sc2.data(), sc2.size() * 4, cudaMemcpyHostToDevice));
+                    umma_accum_kernel<<<1, 128, 96 * 1024>>>(d_a, d_b, (int)sc2.size(), scheme == 0, d_out, d_sched, 1); CHECK(cudaDeviceSynchronize());
+                    CHECK(cudaMemcpy(o_all.data(), d_out, o_all.size() * 4, cudaMemcpyDeviceToHost));
+                    double s2 = 0, r2 = 0, mx = 0, ms = 0;
+                    for (int i = 0; i < 128 * NCOL; ++i) { const float tot = o_main[i] + o_all[i] * (1.0f / 2048.0f); const double e = (double)tot - exact[i]; s2 += e * e; r2 += exact[i] * exact[i]; mx = std::fmax(mx, std::fabs(e) / (std::fabs(exact[i]) + 1e-3)); ms += e / (std::fabs(exact[i]) + 1e-3); }
+                    printf("%-8s %7d %-34s %12.3e %12.3e %+12.3e\n", "2xF16", Ktot, v.name, std::sqrt(s2 / r2), mx, ms / (128.0 * NCOL));
+                    continue;
+                }
+                umma_accum_kernel<<<1, 128, 96 * 1024>>>(d_a, d_b, (int)sc.size(), scheme == 0, d_out, d_sched, nacc);
+                CHECK(cudaDeviceSynchronize());
+                std::vector<float> o(128 * 16);
+                CHECK(cudaMemcpy(o.data(), d_out, o.size() * 4, cudaMemcpyDeviceToHost));
+                double s2 = 0, r2 = 0, mx = 0, ms = 0;
+                for (int i = 0; i < 128 * NCOL; ++i) { const double e = (double)o[i] - exact[i]; s2 += e * e; r2 += exact[i] * exact[i]; mx = std::fmax(mx, std::fabs(e) / (std::fabs(exact[i]) + 1e-3)); ms += e / (std::fabs(exact[i]) + 1e-3); }
+                printf("%-8s %7d %-34s %12.3e %12.3e %+12.3e\n", scheme == 0 ? "3xTF32" : (v.split_corr == 2 ? "f16" : "2xF16"), Ktot, v.name, std::sqrt(s2 / r2), mx, ms / (128.0 * NCOL));
+            }
+            // reference points: fp32 FMA chain (what PTD_DN_FP32 does), in order
+            {
+                double s2 = 0, r2 = 0;
+                for (int m = 0; m < 128; ++m) for (int n = 0; n < NCOL; ++n) { float acc = 0.f; for (int st = 0; st < steps; ++st) { const int t = st % NP; for (int k = 0; k < K; ++k) acc = std::fmaf(A[((size_t)t * 128 + m) * K + k], B[((size_t)t * NCOL + n) * K + k], acc); } const double e = (double)acc - exact[m * NCOL + n]; s2 += e * e; r2 += exact[m * NCOL + n] * exact[m * NCOL + n]; }
+                printf("%-8s %7d %-34s %12.3e\n", "fp32", Ktot, "fmaf chain on the host", std::sqrt(s2 / r2));
             }
         }
     (void)add_rz;

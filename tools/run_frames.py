@@ -19,7 +19,7 @@ sc = capi.Scene(path=path)
 pt = capi.PathTracer(sc)
 wfile = os.path.join(tempfile.gettempdir(), "ptd_run_frames.ptdw")
 weights.save_weights(weights.synthetic_state_dict(1234), wfile)
-dn = capi.Denoiser(wfile, H, W, flags={"tf32": capi.DN_TF32, "f16": capi.DN_F16, "3xtf32": capi.DN_3XTF32, "fp32": capi.DN_FP32}[mode])
+dn = capi.Denoiser(wfile, H, W, flags={"tf32": capi.DN_TF32, "f16": capi.DN_F16, "3xtf32": capi.DN_3XTF32, "fp32": capi.DN_FP32, "2xf16": capi.DN_2XF16}[mode])
 g = torch.empty(10 * W * H, dtype=torch.float32, device="cuda")
 rgb = torch.empty(3 * W * H, dtype=torch.float32, device="cuda")
 L = capi.lib()

@@ -28,7 +28,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("feature", choices=sorted(SWITCH))
     ap.add_argument("--config", default="C3")
-    ap.add_argument("--mode", default="f16", choices=["tf32", "f16", "3xtf32"])
+    ap.add_argument("--mode", default="f16", choices=["tf32", "f16", "3xtf32", "2xf16"])
     ap.add_argument("--frames", type=int, default=12)
     ap.add_argument("--env", action="append", default=[], help="K=V set while the opt-in handle is created (tuning knobs of the feature)")
     args = ap.parse_args()
@@ -90,7 +90,7 @@ def main():
         detail["base_ms_again"] = base_ms2
         base_ms = min(base_ms, base_ms2)
     else:
-        flags = {"tf32": capi.DN_TF32, "f16": capi.DN_F16, "3xtf32": capi.DN_3XTF32}[args.mode]
+        flags = {"tf32": capi.DN_TF32, "f16": capi.DN_F16, "3xtf32": capi.DN_3XTF32, "2xf16": capi.DN_2XF16}[args.mode]
         wfile = os.path.join(tempfile.gettempdir(), "ptd_selfcheck_weights.ptdw")
         weights.save_weights(weights.synthetic_state_dict(1234), wfile)
         pt = capi.PathTracer(sc)
