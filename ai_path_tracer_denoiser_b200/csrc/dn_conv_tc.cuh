@@ -22,7 +22,8 @@
 //     quad (a warp stores 4 x 128 contiguous bytes), MaxPool2d(2) fused through two warp shuffles (the 2x2 window lives in
 //     one warp), activations rounded to tf32 (RN) so the next layer's operand truncation is exact.
 // Warp roles: 0..7 = epilogue (two warps per TMEM lane quarter, alternating 16-column chunks, so every SM sub-partition has two
-// epilogue warps to hide latency), 8 = TMA producer, 9 = TMEM allocator, 10 = barrier init, 11 = MMA issuer (one lane; the highest warp id).  Pipelines: up
+// epilogue warps to hide latency), 8 = TMA producer, 9 = TMEM allocator + barrier init, 10 and 11 = MMA issuers (one lane each) that take the
+// CTA's tiles alternately.  Pipelines: up
 // to 8 smem stages (full/empty mbarriers) and 2 TMEM accumulator buffers (tmem_full/tmem_empty), persistent CTAs, one per SM.
 #pragma once
 #include <cuda.h>
@@ -42,12 +43,13 @@
 #define TC_QUAD_PITCH (TC_HALO_H * TC_ROW_PITCH)        // 2880 B: one channel quad of the halo tile
 #define TC_A_BYTES (4 * TC_QUAD_PITCH)                  // 11520 B: 16 channels
 #define TC_MAX_STAGES 8
-#define TC_THREADS 384                                  // warps 0-7: epilogue; 8: TMA producer; 9: TMEM allocator; 10: barrier init; 11: MMA issuer
+#define TC_THREADS 384                                  // warps 0-7: epilogue; 8: TMA producer; 9: TMEM allocator + barrier init; 10, 11: MMA issuers
 #define TC_EPI_WARPS 8
 #define TC_WARP_TMA 8
 #define TC_WARP_ALLOC 9
-#define TC_WARP_INIT 10
-#define TC_WARP_MMA 11
+#define TC_WARP_INIT 9
+#define TC_WARP_MMA 10                                  // first of the TC_MMA_WARPS issuing warps
+#define TC_MMA_WARPS 2
 #define TC_TMEM_COLS 512                                // the whole tensor memory of the SM (one CTA per SM)
 #define TC_ACC_COLS 128                                 // widest accumulator (padded Cout)
 #define TC_MAX_BUFS 4                                   // accumulator buffers in flight between the MMA issuer and the epilogue
@@ -125,6 +127,7 @@ struct __align__(64) TcParams {
     int nseg, nbuf, buf_cols;
     uint32_t seg_start;                  // bit c: chunk c starts the next main accumulator
     float corr_scale;                    // the correction accumulator's scale: 1 (3xTF32) or 2^-11 (2xF16: lo operands are stored x 2^11)
+    int dbg;                             // PTD_DN_DEBUG (timing experiments only, results are garbage): 1 = no epilogue stores, 2 = no TMA loads, 4 = no TMEM loads
     int linked;                          // row-strip mode: some TcStripLink pointer is set (selects the kernel variant with the peer stores)
 };
 
@@ -213,6 +216,11 @@ __device__ __forceinline__ float round_tf32(float x) {
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
     return __uint_as_float(r);
 }
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {    // explicit shared-space load: through a generic pointer the compiler emits LD.E (address translation, long scoreboard)
+    float4 v;
+    asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
 __device__ __forceinline__ bool elect_one() {            // one lane of the (converged) warp, known to the compiler as such
     uint32_t pred;
     asm volatile(
@@ -293,26 +301,40 @@ __device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, c
     }
 }
 // K-major no-swizzle descriptors, split into 32-bit words: lo = start >> 4 | (LBO >> 4) << 16, hi = SBO >> 4 | version 1 << 14.
-//
+// One chunk (one shared-memory stage): NTAPS taps x (TWO ? 2 : 1) K steps into one accumulator.  Every descriptor is the stage's base plus
+// a compile-time constant (padded Cout, tap geometry and K-step pitch are template parameters), so an MMA costs two uniform adds and
+// the UTCHMMA itself.  a_base already carries the phase's tap origin and the LBO field, b_cur the LBO field.
+template <int NTAPS, bool HALF, int COUTP, bool TWO>
+__device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_base, uint32_t b_cur, uint32_t idesc, uint32_t accumulate) {
+    constexpr uint32_t a_hi = (uint32_t)(TC_ROW_PITCH >> 4) | (1u << 14);          // SBO = halo row pitch
+    constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);                  // SBO = next 8 output channels
+    constexpr uint32_t b_kstep = (uint32_t)COUTP * 2u;                            // (coutp * 32 B) >> 4: one K step
+#pragma unroll
+    for (int t = 0; t < NTAPS; ++t) {
+        // tap origin inside the halo tile in 16-byte units: 3x3 taps (dy, dx) = (t / 3 - 1, t % 3 - 1) from the tile's (1, 1); the 2x2 taps of an
+        // upsampling phase (ti, tj) = (t >> 1, t & 1) from the phase's origin
+        const uint32_t aoff = NTAPS == 9 ? (uint32_t)((t / 3) * (TC_ROW_PITCH >> 4) + t % 3) : (uint32_t)((t >> 1) * (TC_ROW_PITCH >> 4) + (t & 1));
+        mma_w<HALF>(d_tmem, a_base + aoff, a_hi, b_cur + (uint32_t)(t * 2) * b_kstep, b_hi, idesc, t ? 1u : accumulate);
+        if (TWO) mma_w<HALF>(d_tmem, a_base + aoff + (2u * TC_QUAD_PITCH >> 4), a_hi, b_cur + (uint32_t)(t * 2 + 1) * b_kstep, b_hi, idesc, 1u);
+    }
+}
+
 // The issue loop is the kernel's critical path for the N = 32 layers: one M = 128 x N = 32 MMA occupies the tensor pipe's shared-memory
-// operand fetch for (4096 + 1024) B / 128 B/clk = 40 cycles (tools/microbench/umma_rate, profiles/r3c_umma_rate.txt: 41.7 cycles per MMA
-// measured, whatever the layout, the data, the number of accumulators or the traffic beside it), and the MMA queue is shallow, so every
-// cycle the issuing warp spends between two chunks beyond what the queue covers is a cycle the pipe starves (round 1: 70 cycles per tf32
-// MMA, 92 per f16 MMA = 49 per MMA + ~1500 per tile of bookkeeping - integer divisions, parameter reloads, recomputed tap offsets).
-// Hence: nested loops instead of div/mod, every parameter hoisted into registers, running descriptor bases, tap offsets computed once
-// per phase, and the issuing warp is the CTA's highest warp id (the SM sub-partition's arbiter favours it over the epilogue warps it
-// shares its scheduler with).
-template <int NTAPS, bool HALF>
+// operand fetch for (4096 + 1024) B / 128 B/clk = 40 cycles (tools/microbench/umma_rate, profiles/r3b_*: 41.7 cycles per MMA measured,
+// whatever the layout, the data, the number of accumulators or the traffic beside it), and the MMA queue is only a couple of instructions
+// deep, so whatever the issuing thread does between two MMAs is time the pipe starves (round 1: 70 cycles per tf32 MMA, 92 per f16 MMA -
+// integer divisions, parameter reloads, recomputed tap offsets, ~10 instructions of descriptor arithmetic per MMA; profiles/r3c_*: a
+// dozen instructions more per 18 MMAs cost 7 cycles per MMA).  Hence: nested loops instead of div/mod, every parameter hoisted into
+// registers, compile-time descriptor offsets (issue_chunk), and TWO issuing warps that take the CTA's tiles alternately, so that one's
+// bookkeeping (barrier polls - slow while the tensor core owns the shared-memory pipe -, loop control) hides behind the other's MMAs.
+template <int NTAPS, bool HALF, int COUTP>
 __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full, uint64_t* empty,
-                                         uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base) {
+                                         uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int issuer) {
     // instruction descriptor: D = f32, A = B = tf32 (format 2) or f16 (format 0), both K-major, N = coutp, M = 128
-    const uint32_t fmt = HALF ? 0u : 2u;
-    const uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(p.coutp >> 3) << 17) | ((128u >> 4) << 24);
-    const uint32_t a_hi = (uint32_t)(TC_ROW_PITCH >> 4) | (1u << 14);          // SBO = halo row pitch
-    const uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);                  // SBO = next 8 output channels
-    const uint32_t a_lbo = (uint32_t)(TC_QUAD_PITCH >> 4) << 16;              // LBO = next channel quad
-    const uint32_t b_lbo = (uint32_t)p.coutp << 16;                           // (coutp * 16 B) >> 4: next k quad of the same tap
-    const uint32_t b_kstep = (uint32_t)p.coutp * 2u;                          // (coutp * 32 B) >> 4: one K = 8 step
+    constexpr uint32_t fmt = HALF ? 0u : 2u;
+    constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(COUTP >> 3) << 17) | ((128u >> 4) << 24);
+    constexpr uint32_t a_lbo = (uint32_t)(TC_QUAD_PITCH >> 4) << 16;              // LBO = next channel quad
+    constexpr uint32_t b_lbo = (uint32_t)COUTP << 16;                             // (coutp * 16 B) >> 4: next k quad of the same tap
     const int nchunks = p.n0 + p.n1, npass = p.x3 ? 3 : 1, nphases = p.nphases, total = p.total_items, stages = p.stages;
     const bool resident = p.resident != 0, x3 = p.x3 != 0;
     const uint32_t sa0 = (smem_u32(smem_a) >> 4) | a_lbo, sb0 = (smem_u32(smem_b) >> 4) | b_lbo;
@@ -323,22 +345,27 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
     uint32_t one_step = 0;
     for (int c = 0; c < nchunks; ++c)
         if ((c < p.n0 ? p.v0 - 4 * c : p.v1 - 4 * (c - p.n0)) <= 2) one_step |= 1u << c;
-    uint32_t aoff[NTAPS];
-#pragma unroll
-    for (int t = 0; t < NTAPS; ++t) aoff[t] = (uint32_t)(((1 + p.dy[0][t]) * TC_ROW_PITCH + (1 + p.dx[0][t]) * 16) >> 4);
-    int stage = 0; uint32_t phase = 0;
-    uint32_t a_base = sa0;
-    int buf = 0; uint32_t buf_phase = 0;
     const int nbuf = p.nbuf, nseg = p.nseg;
-    const uint32_t buf_cols = (uint32_t)p.buf_cols, seg_start = p.seg_start, coutp = (uint32_t)p.coutp;
-    for (int item = blockIdx.x; item < total; item += gridDim.x) {
-        uint32_t b_base = sb0;
+    const uint32_t buf_cols = (uint32_t)p.buf_cols, seg_start = p.seg_start;
+    // Issuer w takes the CTA's tiles w, w + TC_MMA_WARPS, ...; a tile's stages and its accumulator buffer belong to one issuer, so no MMA of
+    // the other issuer ever touches them (the first MMA into an accumulator overwrites it) and each issuer's tcgen05.commit covers exactly
+    // the MMAs it is meant to cover.  The stage / buffer rings are walked in tile order: an issuer skips the other issuers' slots.
+    const int units = nchunks * npass;                                        // shared-memory stages per tile
+    int stage = 0; uint32_t phase = 0;
+    int buf = 0; uint32_t buf_phase = 0;
+    auto skip = [&](int tiles) {
+        stage += tiles * units; while (stage >= stages) { stage -= stages; phase ^= 1; }
+        buf += tiles; while (buf >= nbuf) { buf -= nbuf; buf_phase ^= 1; }
+    };
+    skip(issuer);
+    for (int item = blockIdx.x + issuer * (int)gridDim.x; item < total; item += TC_MMA_WARPS * (int)gridDim.x) {
+        uint32_t b_base = sb0, a_ph = 0;
         if (nphases > 1) {                                                    // the four 2x2-tap phase GEMMs of an upsampling layer
             const int ph = item & 3;
-#pragma unroll
-            for (int t = 0; t < NTAPS; ++t) aoff[t] = (uint32_t)(((1 + p.dy[ph][t]) * TC_ROW_PITCH + (1 + p.dx[ph][t]) * 16) >> 4);
+            a_ph = (uint32_t)((ph >> 1) * (TC_ROW_PITCH >> 4) + (ph & 1));     // tap (0, 0) of phase (a, b) starts a rows / b pixels into the halo tile
             b_base += (uint32_t)(ph * nchunks) * b_chunk16;
         }
+        uint32_t a_base = sa0 + (uint32_t)stage * a_stage16 + a_ph;
         mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
         fence_after_sync();
         const uint32_t d_buf = d_tmem0 + (uint32_t)buf * buf_cols;
@@ -354,25 +381,23 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
                 const bool last = c == nchunks - 1 && pass == npass - 1;
                 // hi x hi -> main accumulator `seg`; the cross terms (passes 1, 2) -> the correction accumulator behind the mains
                 const uint32_t ai = pass == 0 ? seg : (uint32_t)nseg;
-                const uint32_t d_tmem = d_buf + ai * coutp;
+                const uint32_t d_tmem = d_buf + ai * (uint32_t)COUTP;
                 const uint32_t accumulate = (started >> ai) & 1u;
                 started |= 1u << ai;
                 if (elect_one()) {
-#pragma unroll
-                    for (int t = 0; t < NTAPS; ++t) {
-                        mma_w<HALF>(d_tmem, a_base + aoff[t], a_hi, b_cur + (uint32_t)(t * 2) * b_kstep, b_hi, idesc, t ? 1u : accumulate);
-                        if (two) mma_w<HALF>(d_tmem, a_base + aoff[t] + (2u * TC_QUAD_PITCH >> 4), a_hi, b_cur + (uint32_t)(t * 2 + 1) * b_kstep, b_hi, idesc, 1u);
-                    }
+                    if (two) issue_chunk<NTAPS, HALF, COUTP, true>(d_tmem, a_base, b_cur, idesc, accumulate);
+                    else issue_chunk<NTAPS, HALF, COUTP, false>(d_tmem, a_base, b_cur, idesc, accumulate);
                     mma_commit(&empty[stage]);                                // frees the smem stage when the MMAs retire
                     if (last) mma_commit(&tmem_full[buf]);                    // accumulators complete -> epilogue
                 }
                 __syncwarp();
                 a_base += a_stage16;
-                if (++stage == stages) { stage = 0; phase ^= 1; a_base = sa0; }
+                if (++stage == stages) { stage = 0; phase ^= 1; a_base = sa0 + a_ph; }
             }
             b_base += b_chunk16;
         }
         if (++buf == nbuf) { buf = 0; buf_phase ^= 1; }
+        skip(TC_MMA_WARPS - 1);
     }
 }
 }  // namespace tc
@@ -461,7 +486,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int c = 0; c < nchunks; ++c) {
                 for (int pass = 0; pass < npass; ++pass) {
                     tc::mbar_wait(&empty[stage], phase ^ 1);
-                    if (tc::elect_one()) {
+                    if (p.dbg & 2) { if (tc::elect_one()) tc::mbar_arrive(&full[stage]); }
+                    else if (tc::elect_one()) {
                         tc::mbar_expect_tx(&full[stage], stage_tx);
                         // halo tile origin: pixel (x0 - 1, y0 - 1) = buffer row y0 (apron offset +1); x < 0 / x >= W are zero filled
                         const CUtensorMap* map = c < n0 ? (pass == 2 ? &p.mapA0lo : &p.mapA0) : (pass == 2 ? &p.mapA1lo : &p.mapA1);
@@ -476,13 +502,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                 }
             }
         }
-    } else if (warp == TC_WARP_MMA) {
+    } else if (warp >= TC_WARP_MMA) {
         // ===== MMA issuer: the whole warp runs the (warp-uniform) loop so that descriptors live in uniform registers;
         //       one elected lane issues.  One tcgen05.mma costs a handful of uniform-datapath adds here - issued from divergent
         //       code the same loop cost ~135 cycles per MMA (R2UR + ELECT sequences) and was the kernel's bottleneck.
         if (p.resident) { tc::mbar_wait(wfull, 0); tc::fence_after_sync(); }
-        if (p.ntaps == 9) tc::mma_role<9, HALF>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base);
-        else tc::mma_role<4, HALF>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base);
+#define TC_ROLE(C) case C: if (p.ntaps == 9) tc::mma_role<9, HALF, C>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, warp - TC_WARP_MMA); \
+                            else tc::mma_role<4, HALF, C>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, warp - TC_WARP_MMA); break;
+        switch (p.coutp) { TC_ROLE(16) TC_ROLE(32) TC_ROLE(48) TC_ROLE(64) TC_ROLE(80) TC_ROLE(96) TC_ROLE(112) TC_ROLE(128) default: break; }
+#undef TC_ROLE
     } else if (warp < TC_EPI_WARPS) {
         // ===== epilogue: TMEM -> registers -> bias/BN/LeakyReLU -> CHW4 ============================================
         // Two warps per SM sub-partition run this loop; with the N = 32 layers' MMAs at ~750 (f16) .. 1500 (tf32) cycles per tile it has
@@ -498,6 +526,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const float corr_scale = p.corr_scale;
         const bool round_out = !HALF && p.round_out && !p.x3;     // fp16 storage rounds in the conversion, the split modes split in store16
         const DnTensor out = p.out, pool_out = p.pool_out;
+        const uint32_t s_par_addr = tc::smem_u32(s_par);
+        // While the MMAs stream operands the tensor core owns the shared-memory pipe (tools/microbench/umma_rate: an LDS.128 beside a
+        // saturated N = 32 MMA stream takes ~38 cycles), so the level-0 / level-1 epilogues must not touch shared memory per tile.
+        const bool reg_par = coutp <= 32, lrelu_first = p.lrelu_first != 0;
+        float pa[16], pb[16], pc[16];                              // BN -> LReLU: (scale, shift', -); LReLU -> BN: (bias, scale, shift)
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const int c = half * 16 + j;
+            const bool ok = reg_par && c < coutp;
+            const float sc = ok ? __ldg(&p.scale[c]) : 0.f, sh = ok ? __ldg(&p.shift[c]) : 0.f, bi = ok ? __ldg(&p.bias[c]) : 0.f;
+            pa[j] = lrelu_first ? bi : sc; pb[j] = lrelu_first ? sc : sh; pc[j] = sh;
+        }
         const int pool_yoff = LINKED ? p.link.pool_yoff : 0;
         int buf = 0; uint32_t buf_phase = 0;
         for (int item = blockIdx.x; item < total; item += gridDim.x) {
@@ -525,6 +565,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 #pragma unroll
                         for (int j = 0; j < 16; ++j) acc[j] = fmaf(__uint_as_float(r[j]), corr_scale, __uint_as_float(r2[j]));
                         a -= 2;
+                    } else if (p.dbg & 4) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) acc[j] = (float)(j + c0);
+                        a = -1;
                     } else {
                         tc::tmem_ld16(taddr + (uint32_t)(a * coutp + c0), r);
                         tc::tmem_ld_wait();
@@ -540,15 +584,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     }
                 }
                 float o[16];
+                if (reg_par) {                                     // N <= 32: this warp's 16 channels never change - parameters live in registers
 #pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float4 k = s_par[c0 + j];                // broadcast LDS.128
-                    float v = fmaf(acc[j], k.x, k.y);
-                    v = fmaxf(v, 0.1f * v);                        // LeakyReLU(0.1)
-                    v = fmaf(v, k.z, k.w);
-                    o[j] = round_out ? tc::round_tf32(v) : v;
+                    for (int j = 0; j < 16; ++j) {
+                        float v = lrelu_first ? acc[j] + pa[j] : fmaf(acc[j], pa[j], pb[j]);
+                        v = fmaxf(v, 0.1f * v);                    // LeakyReLU(0.1)
+                        if (lrelu_first) v = fmaf(v, pb[j], pc[j]);
+                        o[j] = round_out ? tc::round_tf32(v) : v;
+                    }
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        const float4 k = tc::lds128(s_par_addr + (uint32_t)(c0 + j) * 16u);    // broadcast LDS.128
+                        float v = fmaf(acc[j], k.x, k.y);
+                        v = fmaxf(v, 0.1f * v);
+                        v = fmaf(v, k.z, k.w);
+                        o[j] = round_out ? tc::round_tf32(v) : v;
+                    }
                 }
-                if (valid) {
+                if (valid && !(p.dbg & 1)) {
                     tc::store16(out, orow, c0, o);
                     if (LINKED) {                                  // row-strip mode: our first / last row is the neighbour's bottom / top apron row - stored straight over NVLink
                         if (oy == 0 && p.link.out_up.base)
@@ -563,7 +617,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         float v = fmaxf(o[j], __shfl_xor_sync(0xffffffffu, o[j], 1));
                         o[j] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
                     }
-                    if (valid && !(tx & 1) && !(ty & 1)) {
+                    if (valid && !(tx & 1) && !(ty & 1) && !(p.dbg & 1)) {
                         tc::store16(pool_out, prow, c0, o);
                         if (LINKED) {
 #pragma unroll 1
@@ -686,6 +740,7 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
         for (int c = 1; c < nch; ++c)
             if ((c * p.nseg) / nch != ((c - 1) * p.nseg) / nch) p.seg_start |= 1u << c;
         p.corr_scale = half ? 1.0f / 2048.0f : 1.0f;
+        if (const char* e = getenv("PTD_DN_DEBUG")) p.dbg = atoi(e);
         if (nch > 32) PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: %d channel chunks (> 32)", nch);
     }
     const int nblk = p.x3 ? 2 : 1;                           // weight blocks per (phase, chunk): hi [, lo]

@@ -39,6 +39,8 @@ struct Cfg {
     int trips;                // PER_TRIP MMAs each
     int nacc;                 // accumulators used round-robin (per MMA)
     int fill;                 // 0: shared memory zero filled; 1: pseudo-random finite operands (does the rate depend on the data?)
+    int proto;                // 1: the conv engine's stage protocol - warp 2 waits empty[s] and arrives full[s] (8 stages, no TMA), the MMA warp waits
+                              //    full[s], issues the trip's 18 MMAs and commits to empty[s]; 2: the same, and warp 3 waits for a per-tile commit (every 2 trips)
     int commit;               // 1: tcgen05.commit to an mbarrier after every trip of 18 MMAs (the conv engine frees a smem stage per chunk)
     int bg;                   // background traffic from warps 2-3 while the MMAs run: 0 none, 1 st.shared.v4 stream, 2 tcgen05.ld stream, 3 ld.shared.v4 stream
 };
@@ -69,6 +71,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(const Cfg c, unsigned
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     __shared__ uint64_t bar, bar2;
+    __shared__ uint64_t pfull[8], pempty[8], tfull[4], tempty[4];
     __shared__ uint32_t tmem_slot;
     __shared__ volatile int done_flag;
     const int warp = threadIdx.x >> 5;
@@ -86,6 +89,8 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(const Cfg c, unsigned
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&bar)));
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 100000;" ::"r"(smem_u32(&bar2)));
+        for (int i = 0; i < 8; ++i) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&pfull[i]))); asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&pempty[i]))); }
+        for (int i = 0; i < 4; ++i) { asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tfull[i]))); asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(smem_u32(&tempty[i]))); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -111,6 +116,13 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(const Cfg c, unsigned
         for (int trip = 0; trip < c.trips; ++trip) {
             const uint32_t a_base = (a0 + (uint32_t)at * (c.a_tile >> 4)) | a_lbo;
             const uint32_t b_base = (b0 + (uint32_t)bt * (c.b_tile >> 4)) | b_lbo;
+            const int pst = trip & 7; const uint32_t pph = (uint32_t)(trip >> 3) & 1u;
+            const int tb = (trip >> 1) & 3; const uint32_t tph = (uint32_t)(trip >> 3) & 1u;
+            if (c.proto) {
+                if (c.proto == 2 && !(trip & 1)) { asm volatile("{\n\t.reg .pred P1;\n\tWE:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DE;\n\tbra WE;\n\tDE:\n\t}" ::"r"(smem_u32(&tempty[tb])), "r"(tph ^ 1u) : "memory"); }
+                asm volatile("{\n\t.reg .pred P1;\n\tWF:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DF;\n\tbra WF;\n\tDF:\n\t}" ::"r"(smem_u32(&pfull[pst])), "r"(pph) : "memory");
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            }
             if (elect_one()) {
 #pragma unroll
                 for (int t = 0; t < PER_TRIP; ++t) {
@@ -120,6 +132,8 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(const Cfg c, unsigned
                     mma<TF32, A_TMEM>(d, a_lo, a_hi, b_lo, b_hi, idesc, (trip || t >= NACC) ? 1u : 0u, tmem + 256);
                 }
                 if (c.commit) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&bar2)) : "memory");
+                if (c.proto) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&pempty[pst])) : "memory");
+                if (c.proto == 2 && (trip & 1)) asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(&tfull[tb])) : "memory");
             }
             __syncwarp();
             if (++at == c.a_tiles) at = 0;
@@ -130,6 +144,21 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(const Cfg c, unsigned
         asm volatile("{\n\t.reg .pred P1;\n\tW:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n\t@P1 bra D;\n\tbra W;\n\tD:\n\t}" ::"r"(smem_u32(&bar)) : "memory");
         unsigned long long t1 = clock64();
         if (threadIdx.x == 0) { cycles_out[blockIdx.x] = t1 - t0; done_flag = 1; }
+    } else if (warp == 2 && c.proto) {
+        for (int trip = 0; trip < c.trips; ++trip) {
+            const int pst = trip & 7; const uint32_t pph = (uint32_t)(trip >> 3) & 1u;
+            asm volatile("{\n\t.reg .pred P1;\n\tWP:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DP;\n\tbra WP;\n\tDP:\n\t}" ::"r"(smem_u32(&pempty[pst])), "r"(pph ^ 1u) : "memory");
+            if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&pfull[pst])) : "memory");
+            __syncwarp();
+        }
+    } else if (warp == 3 && c.proto == 2) {
+        for (int trip = 1; trip < c.trips; trip += 2) {
+            const int tb = (trip >> 1) & 3; const uint32_t tph = (uint32_t)(trip >> 3) & 1u;
+            asm volatile("{\n\t.reg .pred P1;\n\tWT2:\n\tmbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t@P1 bra DT2;\n\tbra WT2;\n\tDT2:\n\t}" ::"r"(smem_u32(&tfull[tb])), "r"(tph) : "memory");
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            if (elect_one()) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(&tempty[tb])) : "memory");
+            __syncwarp();
+        }
     } else if (warp == 2 && c.bg >= 4) {
         // the conv engine's producer: halo-tile boxes (c.bg == 4: 10 px x 18 rows x 4 quads, rows of 160 B starting 16 B before a 128-byte
         // boundary; c.bg == 5: the same bytes as 128-byte-aligned rows) streamed into 4 scratch buffers at smem + 120 KB
@@ -166,7 +195,9 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(const Cfg c, unsigned
         uint8_t* scratch = smem + 164 * 1024 + (warp - 2) * 4096;
         const int lane = threadIdx.x & 31;
         uint32_t sink = 0;
+        unsigned long long iters_done = 0;
         while (!done_flag) {
+            ++iters_done;
             if (c.bg == 1) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k) reinterpret_cast<uint4*>(scratch)[k * 32 + lane] = make_uint4(k, lane, sink, 1);
@@ -185,6 +216,7 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(const Cfg c, unsigned
             }
         }
         if (sink == 0x12345678u) cycles_out[blockIdx.x + 1] = sink;
+        if (warp == 2 && (threadIdx.x & 31) == 0) cycles_out[gridDim.x + blockIdx.x] = iters_done;
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -285,11 +317,11 @@ int main(int argc, char** argv) {
     printf("%-6s %-8s %-22s %12s %12s\n", "kind", "data", "background", "cyc/MMA(1)", "cyc/MMA(all)");
     for (int tf32 = 0; tf32 < 2; ++tf32)
         for (int fill = 0; fill < 2; ++fill)
-            for (int bg = 0; bg < 7; ++bg) {
+            for (int bg = 0; bg < 9; ++bg) {
                 Cfg c = {};
                 if (bg >= 4 && fill) continue;
                 const uint32_t nb = 32;
-                c.n = 32; c.trips = trips; c.tf32 = tf32; c.nacc = 1; c.fill = fill; c.bg = bg == 4 ? 0 : (bg > 4 ? bg - 1 : bg); c.commit = bg == 4;
+                c.n = 32; c.trips = trips; c.tf32 = tf32; c.nacc = 1; c.fill = fill; c.bg = (bg == 4 || bg >= 7) ? 0 : (bg > 4 ? bg - 1 : bg); c.commit = bg == 4; c.proto = bg >= 7 ? bg - 6 : 0;
                 c.layout = 0; c.a_lbo = 2880; c.a_sbo = 160; c.a_kstep = 2 * 2880; c.a_tap = 16; c.a_tile = 11520;
                 c.b_lbo = nb * 16; c.b_sbo = 128; c.b_kstep = nb * 32; c.b_tap = nb * 64; c.b_tile = nb * 64 * 9;
                 c.a_tiles = (int)(96u * 1024u / (c.a_tile + 4096)); c.b_tiles = 1;                  // B region 96..117 KB, TMA scratch from 120 KB
@@ -310,8 +342,8 @@ int main(int argc, char** argv) {
                     cyc[all] = (double)mx / (trips * PER_TRIP);
                     CHECK(cudaMemcpy(&tma_issued, d_cycles + grid, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
                 }
-                const char* bgn[] = {"none", "st.shared.v4 stream", "tcgen05.ld stream", "ld.shared.v4 stream", "commit every 18 MMAs", "TMA 160-byte rows -16 B", "TMA 128-byte rows"};
-                printf("%-6s %-8s %-24s %12.1f %12.1f   TMA boxes per 18 MMAs (all): %.2f\n", tf32 ? "tf32" : "f16", fill ? "random" : "zeros", bgn[bg], cyc[0], cyc[1], bg >= 5 ? (double)tma_issued / trips : 0.0);
+                const char* bgn[] = {"none", "st.shared.v4 stream", "tcgen05.ld stream", "ld.shared.v4 stream", "commit every 18 MMAs", "TMA 160-byte rows -16 B", "TMA 128-byte rows", "stage protocol (full/empty)", "stage + tile protocol"};
+                printf("%-6s %-8s %-24s %12.1f %12.1f   background iterations per 18 MMAs (all): %.2f\n", tf32 ? "tf32" : "f16", fill ? "random" : "zeros", bgn[bg], cyc[0], cyc[1], (bg >= 5 || (bg >= 1 && bg <= 3)) ? (double)tma_issued / trips : 0.0);
             }
     cudaFree(d_cycles);
     return 0;
