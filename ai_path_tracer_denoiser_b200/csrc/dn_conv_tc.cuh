@@ -127,6 +127,7 @@ struct __align__(64) TcParams {
     int nseg, nbuf, buf_cols;
     uint32_t seg_start;                  // bit c: chunk c starts the next main accumulator
     float corr_scale;                    // the correction accumulator's scale: 1 (3xTF32) or 2^-11 (2xF16: lo operands are stored x 2^11)
+    int nissue;                          // MMA issuer warps in use (2 when the stage ring splits into two rings of >= 2 stages and nbuf is even)
     int dbg;                             // PTD_DN_DEBUG (timing experiments only, results are garbage): 1 = no epilogue stores, 2 = no TMA loads, 4 = no TMEM loads
     int linked;                          // row-strip mode: some TcStripLink pointer is set (selects the kernel variant with the peer stores)
 };
@@ -151,16 +152,21 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {          // one try_wait (the hardware suspends the thread for a bounded time)
+    uint32_t ok;
     asm volatile(
         "{\n\t"
         ".reg .pred P1;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P1;\n\t"
+        "}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
+// Every in-kernel wait is bounded: a protocol error traps (the next API call returns PTD_ERR_CUDA) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try(bar, parity)) return;
+    PtdSpinGuard guard;
+    while (!mbar_try(bar, parity)) guard.tick();
 }
 __device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
     asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
@@ -347,25 +353,24 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
         if ((c < p.n0 ? p.v0 - 4 * c : p.v1 - 4 * (c - p.n0)) <= 2) one_step |= 1u << c;
     const int nbuf = p.nbuf, nseg = p.nseg;
     const uint32_t buf_cols = (uint32_t)p.buf_cols, seg_start = p.seg_start;
-    // Issuer w takes the CTA's tiles w, w + TC_MMA_WARPS, ...; a tile's stages and its accumulator buffer belong to one issuer, so no MMA of
-    // the other issuer ever touches them (the first MMA into an accumulator overwrites it) and each issuer's tcgen05.commit covers exactly
-    // the MMAs it is meant to cover.  The stage / buffer rings are walked in tile order: an issuer skips the other issuers' slots.
-    const int units = nchunks * npass;                                        // shared-memory stages per tile
-    int stage = 0; uint32_t phase = 0;
-    int buf = 0; uint32_t buf_phase = 0;
-    auto skip = [&](int tiles) {
-        stage += tiles * units; while (stage >= stages) { stage -= stages; phase ^= 1; }
-        buf += tiles; while (buf >= nbuf) { buf -= nbuf; buf_phase ^= 1; }
-    };
-    skip(issuer);
-    for (int item = blockIdx.x + issuer * (int)gridDim.x; item < total; item += TC_MMA_WARPS * (int)gridDim.x) {
+    // Issuer w takes the CTA's tiles w, w + nissue, ... and owns ring w of the shared-memory stages (stages [w * S, (w + 1) * S), filled by
+    // the producer with exactly this issuer's tiles) and every nissue-th accumulator buffer (nbuf is even when nissue == 2): every mbarrier
+    // keeps a single waiter that sees each of its phases, so the parity waits cannot alias, no MMA of the other issuer ever touches this
+    // issuer's stages or accumulators (the first MMA into an accumulator overwrites it), and each tcgen05.commit covers the issuer's own MMAs.
+    const int nissue = p.nissue;
+    if (issuer >= nissue) return;
+    const int ring_stages = stages / nissue, stage0 = issuer * ring_stages;
+    const uint32_t sa_ring = sa0 + (uint32_t)stage0 * a_stage16;
+    int stage = 0; uint32_t phase = 0;                                        // position in this issuer's ring
+    int buf = issuer; uint32_t buf_phase = 0;
+    for (int item = blockIdx.x + issuer * (int)gridDim.x; item < total; item += nissue * (int)gridDim.x) {
         uint32_t b_base = sb0, a_ph = 0;
         if (nphases > 1) {                                                    // the four 2x2-tap phase GEMMs of an upsampling layer
             const int ph = item & 3;
             a_ph = (uint32_t)((ph >> 1) * (TC_ROW_PITCH >> 4) + (ph & 1));     // tap (0, 0) of phase (a, b) starts a rows / b pixels into the halo tile
             b_base += (uint32_t)(ph * nchunks) * b_chunk16;
         }
-        uint32_t a_base = sa0 + (uint32_t)stage * a_stage16 + a_ph;
+        uint32_t a_base = sa_ring + (uint32_t)stage * a_stage16 + a_ph;
         mbar_wait(&tmem_empty[buf], buf_phase ^ 1);
         fence_after_sync();
         const uint32_t d_buf = d_tmem0 + (uint32_t)buf * buf_cols;
@@ -374,10 +379,10 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
             const bool two = !((one_step >> c) & 1u);
             if (c && ((seg_start >> c) & 1u)) ++seg;
             for (int pass = 0; pass < npass; ++pass) {
-                mbar_wait(&full[stage], phase);
+                mbar_wait(&full[stage0 + stage], phase);
                 fence_after_sync();
                 // resident weights: block (phase, chunk) [x3: hi block, lo block]; passes 0 and 2 use the hi block, pass 1 the lo block
-                const uint32_t b_cur = resident ? b_base + (pass == 1 ? b_stage16 : 0u) : sb0 + (uint32_t)stage * b_stage16;
+                const uint32_t b_cur = resident ? b_base + (pass == 1 ? b_stage16 : 0u) : sb0 + (uint32_t)(stage0 + stage) * b_stage16;
                 const bool last = c == nchunks - 1 && pass == npass - 1;
                 // hi x hi -> main accumulator `seg`; the cross terms (passes 1, 2) -> the correction accumulator behind the mains
                 const uint32_t ai = pass == 0 ? seg : (uint32_t)nseg;
@@ -387,17 +392,17 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
                 if (elect_one()) {
                     if (two) issue_chunk<NTAPS, HALF, COUTP, true>(d_tmem, a_base, b_cur, idesc, accumulate);
                     else issue_chunk<NTAPS, HALF, COUTP, false>(d_tmem, a_base, b_cur, idesc, accumulate);
-                    mma_commit(&empty[stage]);                                // frees the smem stage when the MMAs retire
+                    mma_commit(&empty[stage0 + stage]);                       // frees the smem stage when the MMAs retire
                     if (last) mma_commit(&tmem_full[buf]);                    // accumulators complete -> epilogue
                 }
                 __syncwarp();
                 a_base += a_stage16;
-                if (++stage == stages) { stage = 0; phase ^= 1; a_base = sa0 + a_ph; }
+                if (++stage == ring_stages) { stage = 0; phase ^= 1; a_base = sa_ring + a_ph; }
             }
             b_base += b_chunk16;
         }
-        if (++buf == nbuf) { buf = 0; buf_phase ^= 1; }
-        skip(TC_MMA_WARPS - 1);
+        buf += nissue;
+        if (buf >= nbuf) { buf -= nbuf; buf_phase ^= 1; }
     }
 }
 }  // namespace tc
@@ -476,29 +481,44 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         __syncwarp();
         if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous launch has completed and its stores are visible
-        int stage = 0; uint32_t phase = 0;
         const uint32_t stage_tx = TC_A_BYTES + (p.resident ? 0u : p.b_stage_bytes);
-        const int npass = p.x3 ? 3 : 1, n0 = p.n0;
-        for (int item = blockIdx.x; item < p.total_items; item += gridDim.x) {
-            const int ph = p.nphases > 1 ? (item & 3) : 0, tile = p.nphases > 1 ? (item >> 2) : item;
-            const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
-            const int x0 = tx * TC_TILE_W, y0 = ty * TC_TILE_H + p.src_yoff;
+        const int npass = p.x3 ? 3 : 1, n0 = p.n0, nissue = p.nissue, ring_stages = p.stages / nissue;
+        // One stage ring per MMA issuer; the CTA's tiles alternate between the issuers, and the producer feeds the `nissue` tiles in flight
+        // unit by unit in turn, so that both issuers always have operands staged (feeding tile after tile would starve the second issuer
+        // whenever a tile has more units than a ring has stages).
+        int rstage[TC_MMA_WARPS] = {0, 0}; uint32_t rphase[TC_MMA_WARPS] = {0, 0};
+        for (int item0 = blockIdx.x; item0 < p.total_items; item0 += nissue * (int)gridDim.x) {
+            int x0[TC_MMA_WARPS], y0[TC_MMA_WARPS], ph[TC_MMA_WARPS]; bool live[TC_MMA_WARPS];
+#pragma unroll
+            for (int r = 0; r < TC_MMA_WARPS; ++r) {
+                const int item = item0 + r * (int)gridDim.x;
+                live[r] = r < nissue && item < p.total_items;
+                ph[r] = p.nphases > 1 ? (item & 3) : 0;
+                const int tile = p.nphases > 1 ? (item >> 2) : item;
+                const int ty = tile / p.tiles_x, tx = tile - ty * p.tiles_x;
+                x0[r] = tx * TC_TILE_W; y0[r] = ty * TC_TILE_H + p.src_yoff;
+            }
             for (int c = 0; c < nchunks; ++c) {
                 for (int pass = 0; pass < npass; ++pass) {
-                    tc::mbar_wait(&empty[stage], phase ^ 1);
-                    if (p.dbg & 2) { if (tc::elect_one()) tc::mbar_arrive(&full[stage]); }
-                    else if (tc::elect_one()) {
-                        tc::mbar_expect_tx(&full[stage], stage_tx);
-                        // halo tile origin: pixel (x0 - 1, y0 - 1) = buffer row y0 (apron offset +1); x < 0 / x >= W are zero filled
-                        const CUtensorMap* map = c < n0 ? (pass == 2 ? &p.mapA0lo : &p.mapA0) : (pass == 2 ? &p.mapA1lo : &p.mapA1);
-                        tc::tma_load_3d(smem_a + (size_t)stage * TC_A_BYTES, map, &full[stage], (x0 - 1) * (HALF ? 8 : 4), y0, (c < n0 ? c : c - n0) * 4);
-                        if (!p.resident) {
-                            const size_t blk = p.x3 ? (size_t)((ph * nchunks + c) * 2 + (pass == 1 ? 1 : 0)) : (size_t)(ph * nchunks + c);
-                            tc::bulk_load(smem_b + (size_t)stage * p.b_stage_bytes, (const uint8_t*)p.wpack + blk * p.b_stage_bytes, p.b_stage_bytes, &full[stage]);
+#pragma unroll
+                    for (int r = 0; r < TC_MMA_WARPS; ++r) {
+                        if (!live[r]) continue;
+                        const int sidx = r * ring_stages + rstage[r];
+                        tc::mbar_wait(&empty[sidx], rphase[r] ^ 1);
+                        if (p.dbg & 2) { if (tc::elect_one()) tc::mbar_arrive(&full[sidx]); }
+                        else if (tc::elect_one()) {
+                            tc::mbar_expect_tx(&full[sidx], stage_tx);
+                            // halo tile origin: pixel (x0 - 1, y0 - 1) = buffer row y0 (apron offset +1); x < 0 / x >= W are zero filled
+                            const CUtensorMap* map = c < n0 ? (pass == 2 ? &p.mapA0lo : &p.mapA0) : (pass == 2 ? &p.mapA1lo : &p.mapA1);
+                            tc::tma_load_3d(smem_a + (size_t)sidx * TC_A_BYTES, map, &full[sidx], (x0[r] - 1) * (HALF ? 8 : 4), y0[r], (c < n0 ? c : c - n0) * 4);
+                            if (!p.resident) {
+                                const size_t blk = p.x3 ? (size_t)((ph[r] * nchunks + c) * 2 + (pass == 1 ? 1 : 0)) : (size_t)(ph[r] * nchunks + c);
+                                tc::bulk_load(smem_b + (size_t)sidx * p.b_stage_bytes, (const uint8_t*)p.wpack + blk * p.b_stage_bytes, p.b_stage_bytes, &full[sidx]);
+                            }
                         }
+                        __syncwarp();
+                        if (++rstage[r] == ring_stages) { rstage[r] = 0; rphase[r] ^= 1; }
                     }
-                    __syncwarp();
-                    if (++stage == p.stages) { stage = 0; phase ^= 1; }
                 }
             }
         }
@@ -815,6 +835,10 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
         p.stages = (int)std::min<size_t>(TC_MAX_STAGES, budget / (TC_A_BYTES + p.b_stage_bytes));
         if (p.stages < 2) PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: a stage of %u B does not fit twice in shared memory", TC_A_BYTES + p.b_stage_bytes);
     }
+    // two MMA issuers need a stage ring each (>= 2 stages) and an even number of accumulator buffers (see mma_role)
+    p.nissue = (p.stages >= 4 && p.nbuf >= 2) ? TC_MMA_WARPS : 1;
+    if (const char* e = getenv("PTD_DN_ISSUERS")) { if (atoi(e) == 1) p.nissue = 1; }
+    if (p.nissue == 2) { p.stages &= ~1; p.nbuf &= ~1; }
     const size_t b_bytes = p.resident ? (size_t)p.w_total_bytes : (size_t)p.stages * p.b_stage_bytes;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
