@@ -264,8 +264,11 @@ __device__ __forceinline__ void mma_w(uint32_t tmem_d, uint32_t a_lo, uint32_t a
 
 namespace tc {
 // 16 consecutive output channels [c0, c0 + 16) of one pixel -> the tensor's channel vectors (row: address of the pixel in vector 0)
-__device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, const float* o) {
-    if (t.lo_off && t.esize == 4) {                        // 3xTF32: hi = tf32(v), lo = tf32(v - hi)
+// storage formats of an activation tensor: 0 = fp32 quads, 1 = fp16 octets, 2 = fp32 hi / lo pair (3xTF32), 3 = fp16 hi / lo pair (2xF16)
+__host__ __device__ __forceinline__ int tensor_format(const DnTensor& t) { return t.esize == 4 ? (t.lo_off ? 2 : 0) : (t.lo_off ? 3 : 1); }
+template <int FMT>
+__device__ __forceinline__ void store16_fmt(const DnTensor& t, float* row, int c0, const float* o) {
+    if (FMT == 2) {                                        // 3xTF32: hi = tf32(v), lo = tf32(v - hi)
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
             float hi[4], lo[4];
@@ -275,7 +278,7 @@ __device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, c
             *reinterpret_cast<float4*>(d) = make_float4(hi[0], hi[1], hi[2], hi[3]);
             *reinterpret_cast<float4*>(d + t.lo_off) = make_float4(lo[0], lo[1], lo[2], lo[3]);
         }
-    } else if (t.lo_off) {                               // 2xF16: hi = f16(v), lo = f16((v - hi) * 2^11) - the residual scaled into fp16's normal range
+    } else if (FMT == 3) {                                 // 2xF16: hi = f16(v), lo = f16((v - hi) * 2^11) - the residual scaled into fp16's normal range
 #pragma unroll
         for (int oc = 0; oc < 2; ++oc) {
             uint32_t hw[4], lw[4];
@@ -291,7 +294,7 @@ __device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, c
             *reinterpret_cast<uint4*>(d) = make_uint4(hw[0], hw[1], hw[2], hw[3]);
             *reinterpret_cast<uint4*>(d + t.lo_off) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
         }
-    } else if (t.esize == 4) {
+    } else if (FMT == 0) {
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd)
             *reinterpret_cast<float4*>(row + (size_t)(c0 / 4 + qd) * t.quad_stride()) = make_float4(o[4 * qd], o[4 * qd + 1], o[4 * qd + 2], o[4 * qd + 3]);
@@ -304,6 +307,14 @@ __device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, c
             v.x = *reinterpret_cast<uint32_t*>(&h0); v.y = *reinterpret_cast<uint32_t*>(&h1); v.z = *reinterpret_cast<uint32_t*>(&h2); v.w = *reinterpret_cast<uint32_t*>(&h3);
             *reinterpret_cast<uint4*>(row + (size_t)(c0 / 8 + oc) * t.quad_stride()) = v;
         }
+    }
+}
+__device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, const float* o) {      // format decided at run time (pack_gbuffer)
+    switch (tensor_format(t)) {
+        case 0: store16_fmt<0>(t, row, c0, o); break;
+        case 1: store16_fmt<1>(t, row, c0, o); break;
+        case 2: store16_fmt<2>(t, row, c0, o); break;
+        default: store16_fmt<3>(t, row, c0, o); break;
     }
 }
 // K-major no-swizzle descriptors, split into 32-bit words: lo = start >> 4 | (LBO >> 4) << 16, hi = SBO >> 4 | version 1 << 14.
@@ -408,7 +419,9 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
 }  // namespace tc
 
 // shared memory carve-up (offsets from the 1024-aligned base): [A stage 0..S) | B (resident: whole layer; streamed: S stages) | barriers
-template <bool HALF, bool LINKED>
+// FMT: storage format of the output (and pooled output) tensor - a template parameter, like LINKED, to keep the epilogue loop small: it
+// shares the instruction cache with the producer and the MMA issuers.
+template <bool HALF, bool LINKED, int FMT>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcParams p) {
     extern __shared__ uint8_t tc_smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -623,12 +636,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                     }
                 }
                 if (valid && !(p.dbg & 1)) {
-                    tc::store16(out, orow, c0, o);
+                    tc::store16_fmt<FMT>(out, orow, c0, o);
                     if (LINKED) {                                  // row-strip mode: our first / last row is the neighbour's bottom / top apron row - stored straight over NVLink
                         if (oy == 0 && p.link.out_up.base)
-                            tc::store16(p.link.out_up, p.link.out_up.base + ((size_t)(p.link.out_up.rows + 1) * out.W + ox) * 4, c0, o);
+                            tc::store16_fmt<FMT>(p.link.out_up, p.link.out_up.base + ((size_t)(p.link.out_up.rows + 1) * out.W + ox) * 4, c0, o);
                         if (oy == out.rows - 1 && p.link.out_down.base)
-                            tc::store16(p.link.out_down, p.link.out_down.base + (size_t)ox * 4, c0, o);
+                            tc::store16_fmt<FMT>(p.link.out_down, p.link.out_down.base + (size_t)ox * 4, c0, o);
                     }
                 }
                 if (prow) {                                        // MaxPool2d(2): partners are lanes ^1 (x) and ^8 (y)
@@ -638,15 +651,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         o[j] = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 8));
                     }
                     if (valid && !(tx & 1) && !(ty & 1) && !(p.dbg & 1)) {
-                        tc::store16(pool_out, prow, c0, o);
+                        tc::store16_fmt<FMT>(pool_out, prow, c0, o);
                         if (LINKED) {
 #pragma unroll 1
                             for (int r = 0; r < 8; ++r)
-                                if (p.link.gather_base[r]) { DnTensor t = pool_out; t.base = p.link.gather_base[r]; tc::store16(t, t.base + poff, c0, o); }
+                                if (p.link.gather_base[r]) { DnTensor t = pool_out; t.base = p.link.gather_base[r]; tc::store16_fmt<FMT>(t, t.base + poff, c0, o); }
                             if ((y >> 1) == 0 && p.link.pool_up.base)
-                                tc::store16(p.link.pool_up, p.link.pool_up.base + ((size_t)(p.link.pool_up.rows + 1) * pool_out.W + (x >> 1)) * 4, c0, o);
+                                tc::store16_fmt<FMT>(p.link.pool_up, p.link.pool_up.base + ((size_t)(p.link.pool_up.rows + 1) * pool_out.W + (x >> 1)) * 4, c0, o);
                             if ((y >> 1) == pool_out.rows - 1 && p.link.pool_down.base)
-                                tc::store16(p.link.pool_down, p.link.pool_down.base + (size_t)(x >> 1) * 4, c0, o);
+                                tc::store16_fmt<FMT>(p.link.pool_down, p.link.pool_down.base + (size_t)(x >> 1) * 4, c0, o);
                         }
                     }
                 }
@@ -720,6 +733,19 @@ static ptd_status tc_make_map_act(CUtensorMap* map, const DnTensor& t) {
 }
 
 inline void tc_plan_destroy(TcConvPlan& plan) { plan.valid = 0; }
+
+// kernel variants: (operand type, output format) in {tf32 -> fp32, tf32 -> fp32 hi/lo, f16 -> fp32, f16 -> fp16, f16 -> fp16 hi/lo} x linked
+typedef void (*TcKernel)(const TcParams);
+static TcKernel tc_kernel_variant(int combo, int linked) {
+    switch (combo * 2 + linked) {
+        case 0: return conv_tc_kernel<false, false, 0>; case 1: return conv_tc_kernel<false, true, 0>;
+        case 2: return conv_tc_kernel<false, false, 2>; case 3: return conv_tc_kernel<false, true, 2>;
+        case 4: return conv_tc_kernel<true, false, 0>;  case 5: return conv_tc_kernel<true, true, 0>;
+        case 6: return conv_tc_kernel<true, false, 1>;  case 7: return conv_tc_kernel<true, true, 1>;
+        case 8: return conv_tc_kernel<true, false, 3>;  default: return conv_tc_kernel<true, true, 3>;
+    }
+}
+static int tc_kernel_combo(bool half, int fmt) { return half ? (fmt == 0 ? 2 : (fmt == 1 ? 3 : 4)) : (fmt == 0 ? 0 : 1); }
 
 // w9: [9][cinp][coutp] fp32 (padded, zero-filled); builds the packed tf32 weights, the tensor maps and the launch shape.
 inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& w9, int cinp, TcConvPlan& plan, std::vector<void*>& allocs) {
@@ -845,19 +871,19 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     plan.grid = p.total_items < sms ? p.total_items : sms;
     plan.smem = (size_t)p.stages * TC_A_BYTES + ((b_bytes + 15) & ~(size_t)15) + 1024 + 512 + TC_ACC_COLS * 16;
-    if (cudaFuncSetAttribute(conv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess ||
-        cudaFuncSetAttribute(conv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess)
-        PTD_FAIL(PTD_ERR_CUDA, "tc conv: cannot reserve shared memory: %s", cudaGetErrorString(cudaGetLastError()));
+    for (int v = 0; v < 10; ++v)
+        if (cudaFuncSetAttribute(tc_kernel_variant(v >> 1, v & 1), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(220 * 1024)) != cudaSuccess)
+            PTD_FAIL(PTD_ERR_CUDA, "tc conv: cannot reserve shared memory: %s", cudaGetErrorString(cudaGetLastError()));
     plan.valid = 1;
     return PTD_OK;
 }
 
 inline ptd_status tc_conv_launch(TcConvPlan& plan, cudaStream_t st, int* launches, bool* pooled) {
     if (!plan.valid) PTD_FAIL(PTD_ERR_STATE, "tc conv: plan not built");
-    void (*kern)(const TcParams) = plan.p.half ? (plan.p.linked ? conv_tc_kernel<true, true> : conv_tc_kernel<true, false>)
-                                               : (plan.p.linked ? conv_tc_kernel<false, true> : conv_tc_kernel<false, false>);
+    const int fmt = tc::tensor_format(plan.p.out);
+    if (plan.p.pool_out.base && tc::tensor_format(plan.p.pool_out) != fmt) PTD_FAIL(PTD_ERR_STATE, "tc conv: output and pooled output differ in storage format");
+    if ((plan.p.half && fmt == 2) || (!plan.p.half && (fmt == 1 || fmt == 3))) PTD_FAIL(PTD_ERR_STATE, "tc conv: operand type / output format combination not built");
+    TcKernel kern = tc_kernel_variant(tc_kernel_combo(plan.p.half != 0, fmt), plan.p.linked);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
     cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = plan.smem; cfg.stream = st;
