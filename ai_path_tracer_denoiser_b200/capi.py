@@ -36,7 +36,7 @@ ptd_dn_forward_host ptd_dn_create_strip ptd_dn_padded_size ptd_dn_dump_hidden pt
 ptd_pt_launches_last_render ptd_dn_profile ptd_dn_launch_times ptd_dn_launch_name ptd_pt_profile
 ptd_pt_launch_times ptd_dn_strip_partition ptd_dn_strip_info_size ptd_dn_strip_export ptd_dn_strip_connect
 ptd_dn_forward_group ptd_pt_create_strip ptd_pt_strip_info_size ptd_pt_strip_export ptd_pt_strip_connect
-ptd_pt_render_group ptd_frame_host ptd_frame_submit ptd_frame_wait ptd_bvh_probe ptd_bvh_probe_order""".split()
+ptd_pt_render_group ptd_frame_host ptd_frame_submit ptd_frame_wait ptd_frame_timer ptd_bvh_probe ptd_bvh_probe_order""".split()
 
 
 class PtdError(RuntimeError):
@@ -79,6 +79,7 @@ def lib():
         L.ptd_pt_render_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ptd_frame_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_frame_wait.argtypes = [C.c_void_p]
+        L.ptd_frame_timer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
         L.ptd_frame_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_bvh_probe_order.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_double)]
         L.ptd_bvh_probe.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_double)]
@@ -291,6 +292,14 @@ class PathTracer:
 
     def frame_wait(self):
         check(lib().ptd_frame_wait(self.h), "ptd_frame_wait")
+
+    def frame_timer_start(self):
+        check(lib().ptd_frame_timer(self.h, 0, None), "ptd_frame_timer")
+
+    def frame_timer_stop(self):
+        ms = C.c_float()
+        check(lib().ptd_frame_timer(self.h, 1, C.byref(ms)), "ptd_frame_timer")
+        return ms.value
 
     def render(self, gbuf_dev_ptr, cam=None, iter=1, stream=None):
         camp = None

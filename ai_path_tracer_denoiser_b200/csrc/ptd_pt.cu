@@ -710,7 +710,7 @@ struct ptd_pt {
     int W = 0, H = 0, P = 0, depth = 0, ngeoms = 0, nmaterials = 0, nfaces = 0, ntiles = 0;   // P: pixels of this handle (frame or strip)
     int Pfull = 0, row0 = 0, rows = 0;                        // whole-frame pixels; this handle's image rows [row0, row0 + rows)
     int rank = 0, nranks = 1; unsigned epoch = 0;
-    unsigned long long* d_mail = nullptr;                     // [depth + 1][PT_MAX_RANKS], written by the strips above (peer stores)
+    unsigned long long* d_mail = nullptr;                     // [2][depth + 1][PT_MAX_RANKS], written by the strips above (peer stores)
     unsigned long long* peer_mail[PT_MAX_RANKS] = {nullptr}; bool peer_ipc[PT_MAX_RANKS] = {false};
     ptd_camera cam;
     ptd_aabb mesh_box;
@@ -738,6 +738,7 @@ struct ptd_pt {
     cudaEvent_t fr_ev_pt[2] = {nullptr, nullptr}, fr_ev_done[2] = {nullptr, nullptr}, fr_ev_gcopy[2] = {nullptr, nullptr};
     bool fr_has_gcopy[2] = {false, false};
     long long fr_submitted = 0, fr_waited = 0;
+    cudaEvent_t fr_ev_t0 = nullptr, fr_ev_t1 = nullptr; bool fr_timer_armed = false; cudaStream_t fr_last_dn = nullptr;   // ptd_frame_timer
     bool wide_lookback = false;                              // PTD_PT_WIDE_LOOKBACK=1
     bool smem_stack = false;                                 // PTD_PT_SMEM_STACK=1
     // PTD_PT_RAY_SORT
@@ -863,8 +864,11 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
         ALLOC(h->d_bin_order, sizeof(int) * P);
     }
     ALLOC(h->d_ctl, h->ctl_bytes);
-    ALLOC(h->d_mail, sizeof(unsigned long long) * (size_t)(h->depth + 1) * PT_MAX_RANKS);
-    cudaMemset(h->d_mail, 0, sizeof(unsigned long long) * (size_t)(h->depth + 1) * PT_MAX_RANKS);
+    // two mailboxes, used alternately by frame parity: with at most two frames in flight per rank (ptd_frame_submit) a strip above that
+    // already renders frame k + 1 writes the other box, and cannot reach frame k + 2 before every strip has read frame k's counts (its
+    // denoiser of frame k, which gates the slot, depends on every other strip's denoiser of frame k and so on their path trace of frame k)
+    ALLOC(h->d_mail, sizeof(unsigned long long) * 2 * (size_t)(h->depth + 1) * PT_MAX_RANKS);
+    cudaMemset(h->d_mail, 0, sizeof(unsigned long long) * 2 * (size_t)(h->depth + 1) * PT_MAX_RANKS);
     h->d_counts = (int*)(h->d_ctl + off_counts); h->d_ticket = (int*)(h->d_ctl + off_ticket); h->d_status = (unsigned long long*)(h->d_ctl + off_status);
     if (flags & PTD_PT_RAY_SORT) h->d_bin_hist = (int*)(h->d_ctl + off_bins);
     if (sort) {
@@ -914,8 +918,7 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
     p.mesh_box = h->mesh_box;
     p.cam = cam ? *cam : h->cam;
     p.W = h->W; p.P = h->P; p.iter = iter; p.trace_depth = h->depth;
-    p.Pfull = h->Pfull; p.pix0 = h->row0 * h->W; p.rank = h->rank; p.nranks = h->nranks; p.mail = h->d_mail;
-    for (int r = 0; r < PT_MAX_RANKS; ++r) p.peer_mail[r] = h->peer_mail[r];
+    p.Pfull = h->Pfull; p.pix0 = h->row0 * h->W; p.rank = h->rank; p.nranks = h->nranks;
     p.counts = h->d_counts; p.gbuf = gbuf; p.image = h->d_image; p.dead = h->d_dead;
     p.sort_keys = h->d_keys; p.trace_paths = h->d_trace_paths;
     size_t smem = p.geoms_in_smem ? (sizeof(ptd_geom) + sizeof(ptd_aabb)) * h->ngeoms : 0;
@@ -935,6 +938,9 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
         mark();
     }
     p.epoch = h->epoch;
+    const size_t mail_box = (size_t)(h->epoch & 1u) * (size_t)(h->depth + 1) * PT_MAX_RANKS;          // this frame's mailbox (see pt_create)
+    p.mail = h->d_mail + mail_box;
+    for (int r = 0; r < PT_MAX_RANKS; ++r) p.peer_mail[r] = h->peer_mail[r] ? h->peer_mail[r] + mail_box : nullptr;
     for (int b = first; b < last && b < h->depth; ++b) {
         const int cur = h->cur, nxt = (cur + 1) % (sort ? 3 : 2);
         p.bounce = b;
@@ -965,7 +971,7 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
         else pt_trace<false><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
         mark();
         if (b > 0 && h->rank > 0 && (h->flags & PTD_PT_GATED_MAIL)) {     // (timed together with the shade kernel it gates)
-            pt_mail_gate<<<1, 32, 0, st>>>(h->d_mail, b, h->rank, h->epoch);
+            pt_mail_gate<<<1, 32, 0, st>>>(p.mail, b, h->rank, h->epoch);
             h->launches += 1;
         }
         // the next bounce is binned: this pt_shade also writes its survivors' keys and the next histogram
@@ -1166,10 +1172,14 @@ static ptd_status frame_ring_init(ptd_pt* h) {
     return PTD_OK;
 }
 extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host) {
-    if (!h || !dn || !rgb_host || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_submit: bad argument");
+    if (!h || !dn || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_submit: bad argument");
+    // the first-hit planes 3..9 are written by iteration 1 only (pathtrace.cu:295, :379) and live in the slot's G-buffer: accumulating further
+    // iterations would need them carried from slot to slot - use ptd_frame_host / ptd_pt_render for iter > 1
+    if (iter != 1) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_frame_submit: only iter == 1 (one sample per pixel per frame, as runCuda() renders); use ptd_frame_host for accumulation");
     int dn_device = 0, dn_H = 0, dn_W = 0, dn_strip = 0;
     ptd_dn_describe(dn, &dn_device, &dn_H, &dn_W, &dn_strip);
-    if (h->nranks > 1 || h->rows != h->H || dn_strip) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_frame_submit: row-strip handles take device pointers (ptd_pt_render + ptd_dn_forward)");
+    const bool strip = h->nranks > 1 || h->rows != h->H;
+    if (strip != (dn_strip != 0)) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_submit: path tracer and denoiser handles must both cover the frame or both be row strips");
     if (dn_device != h->device || dn_H != h->H || dn_W != h->W) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_submit: the denoiser handle is for %dx%d on device %d, the path tracer for %dx%d on device %d", dn_W, dn_H, dn_device, h->W, h->H, h->device);
     if (h->fr_submitted - h->fr_waited >= 2) PTD_FAIL(PTD_ERR_STATE, "ptd_frame_submit: two frames are in flight - call ptd_frame_wait first");
     CUDA_TRY(cudaSetDevice(h->device));
@@ -1177,21 +1187,31 @@ extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* 
     if (rc != PTD_OK) return rc;
     const int i = h->fr_submitted & 1;                                  // this slot's previous frame (two submissions ago) has been waited for
     const size_t plane = sizeof(float) * (size_t)h->Pfull;
-    cudaStream_t s_pt = h->fr_stream[0], s_dn = h->fr_stream[1], s_cp = h->fr_stream[2];
+    // Row strips: a frame's kernels wait for other GPUs (halo rows, live counts).  With the path trace of frame k + 1 on its own stream,
+    // a kernel that spins while it holds an SM can starve the kernel it waits for; PTD_PT_GATED_MAIL moves the path tracer's only wait
+    // into a one-warp gate kernel, so only handles created with it overlap the two - the others run a frame's
+    // path trace and denoiser on one stream (submission is still asynchronous, the host copies still overlap the next frame).
+    const bool two_streams = !strip || (h->flags & PTD_PT_GATED_MAIL);
+    cudaStream_t s_pt = h->fr_stream[0], s_dn = two_streams ? h->fr_stream[1] : h->fr_stream[0], s_cp = h->fr_stream[2];
+    if (h->fr_timer_armed) { CUDA_TRY(cudaEventRecord(h->fr_ev_t0, s_pt)); h->fr_timer_armed = false; }
+    if (two_streams && h->fr_submitted >= 2) CUDA_TRY(cudaStreamWaitEvent(s_pt, h->fr_ev_done[i], 0));   // the slot's G-buffer is free once frame k - 2 was denoised
     rc = pt_run(h, cam, iter, h->fr_gbuf[i], s_pt, 0, h->depth);
-    if (rc != PTD_OK) return rc;
+    if (rc != PTD_OK) { cudaStreamSynchronize(s_pt); return rc; }
     CUDA_TRY(cudaEventRecord(h->fr_ev_pt[i], s_pt));
+    // the rows this handle renders: the whole frame, or its strip of every plane ([planes][H][W] on both sides)
+    const size_t row_off = (size_t)h->row0 * h->W, row_bytes = sizeof(float) * (size_t)h->rows * h->W;
     h->fr_has_gcopy[i] = host_tensor != nullptr;
     if (host_tensor) {
         CUDA_TRY(cudaStreamWaitEvent(s_cp, h->fr_ev_pt[i], 0));
-        CUDA_TRY(cudaMemcpyAsync(host_tensor, h->fr_gbuf[i], 10 * plane, cudaMemcpyDeviceToHost, s_cp));
+        CUDA_TRY(cudaMemcpy2DAsync(host_tensor + row_off, plane, h->fr_gbuf[i] + row_off, plane, row_bytes, 10, cudaMemcpyDeviceToHost, s_cp));
         CUDA_TRY(cudaEventRecord(h->fr_ev_gcopy[i], s_cp));
     }
-    CUDA_TRY(cudaStreamWaitEvent(s_dn, h->fr_ev_pt[i], 0));
+    if (two_streams) CUDA_TRY(cudaStreamWaitEvent(s_dn, h->fr_ev_pt[i], 0));
     rc = ptd_dn_forward(dn, h->fr_gbuf[i], h->fr_rgb[i], reset_hidden, s_dn);
-    if (rc != PTD_OK) return rc;
-    CUDA_TRY(cudaMemcpyAsync(rgb_host, h->fr_rgb[i], 3 * plane, cudaMemcpyDeviceToHost, s_dn));
+    if (rc != PTD_OK) { cudaStreamSynchronize(s_pt); cudaStreamSynchronize(s_dn); return rc; }
+    if (rgb_host) CUDA_TRY(cudaMemcpy2DAsync(rgb_host + row_off, plane, h->fr_rgb[i] + row_off, plane, row_bytes, 3, cudaMemcpyDeviceToHost, s_dn));
     CUDA_TRY(cudaEventRecord(h->fr_ev_done[i], s_dn));
+    h->fr_last_dn = s_dn;
     h->fr_submitted += 1;
     return PTD_OK;
 }
@@ -1200,9 +1220,25 @@ extern "C" ptd_status ptd_frame_wait(ptd_pt* h) {
     if (h->fr_waited == h->fr_submitted) PTD_FAIL(PTD_ERR_STATE, "ptd_frame_wait: no frame in flight");
     CUDA_TRY(cudaSetDevice(h->device));
     const int i = h->fr_waited & 1;
+    h->fr_waited += 1;                                                  // whatever happens below, this frame is no longer in flight
     CUDA_TRY(cudaEventSynchronize(h->fr_ev_done[i]));
     if (h->fr_has_gcopy[i]) CUDA_TRY(cudaEventSynchronize(h->fr_ev_gcopy[i]));
-    h->fr_waited += 1;
+    return PTD_OK;
+}
+// Device time of a run of submitted frames: op 0 arms the timer (the next ptd_frame_submit records the start event on the path-trace
+// stream before its first launch); op 1 records the stop event behind the last submitted frame's denoiser, waits for it and returns
+// the milliseconds in between (every frame in flight is complete afterwards, but still has to be taken with ptd_frame_wait).
+extern "C" ptd_status ptd_frame_timer(ptd_pt* h, int op, float* ms) {
+    if (!h || (op == 1 && !ms)) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_timer: bad argument");
+    CUDA_TRY(cudaSetDevice(h->device));
+    ptd_status rc = frame_ring_init(h);
+    if (rc != PTD_OK) return rc;
+    if (!h->fr_ev_t0) { CUDA_TRY(cudaEventCreate(&h->fr_ev_t0)); CUDA_TRY(cudaEventCreate(&h->fr_ev_t1)); }
+    if (op == 0) { h->fr_timer_armed = true; return PTD_OK; }
+    if (h->fr_timer_armed || !h->fr_last_dn) PTD_FAIL(PTD_ERR_STATE, "ptd_frame_timer: no frame was submitted since the timer was armed");
+    CUDA_TRY(cudaEventRecord(h->fr_ev_t1, h->fr_last_dn));
+    CUDA_TRY(cudaEventSynchronize(h->fr_ev_t1));
+    CUDA_TRY(cudaEventElapsedTime(ms, h->fr_ev_t0, h->fr_ev_t1));
     return PTD_OK;
 }
 

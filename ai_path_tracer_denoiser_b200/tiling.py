@@ -42,7 +42,7 @@ def neighbours(blobs, rank):
 class StripPipeline:
     """Path tracer + denoiser of this rank's strip, connected to the other ranks' strips."""
 
-    def __init__(self, scene, weights_path, rank, world, device, dist=None, dn_flags=capi.DN_TF32):
+    def __init__(self, scene, weights_path, rank, world, device, dist=None, dn_flags=capi.DN_TF32, gated=None):
         cam = scene.camera[0]
         self.W, self.H = int(cam["res"][0]), int(cam["res"][1])
         self.rank, self.world = rank, world
@@ -53,7 +53,7 @@ class StripPipeline:
             return
         # PTD_STRIP_PIPELINE=1 (same value on every rank): the two-stream frame loop in strip mode.  It needs the gated live-count
         # mail - with it no path-trace block ever spins on another GPU, which is what made the two-stream loop deadlock (FrameLoop)
-        self.two_stream_ok = os.environ.get("PTD_STRIP_PIPELINE", "0") == "1"
+        self.two_stream_ok = os.environ.get("PTD_STRIP_PIPELINE", "0") == "1" if gated is None else bool(gated)
         self.pt = capi.PathTracer(scene, device=device, strip=self.pt_rows, flags=capi.PT_GATED_MAIL if self.two_stream_ok else 0)
         self.dn = capi.Denoiser(weights_path, self.H, self.W, device=device, flags=dn_flags, strip=self.dn_rows)
         pt_blobs = exchange_blobs(self.pt.export_info(), dist, world)

@@ -168,9 +168,18 @@ ptd_status ptd_frame_host(ptd_pt*, ptd_dn*, const ptd_camera* cam, int iter, int
  * ptd_frame_wait blocks until the OLDEST submitted frame has reached its host buffers.  Submit frame k + 1 before waiting for frame k
  * and the path trace of k + 1 overlaps the denoiser and the PCIe copies of k.  At most two frames in flight; frames complete in
  * submission order (so the recurrent state is carried in that order); the host buffers of a frame must stay valid, and should be
- * pinned, until its ptd_frame_wait returns.  Results are bit-identical to ptd_frame_host / the two-call path. */
+ * pinned, until its ptd_frame_wait returns.  Results are bit-identical to ptd_frame_host / the two-call path.
+ * iter must be 1 (one sample per pixel per frame, what runCuda() renders; PTD_ERR_UNSUPPORTED otherwise).  Both host pointers are optional:
+ * with rgb_host == NULL the denoised frame stays on the device (the frame loop itself, nothing copied).
+ * Row-strip handles (ptd_pt_create_strip + ptd_dn_create_strip, connected): every rank submits the same frames; host_tensor / rgb_host are
+ * still FULL-FRAME [10][H][W] / [3][H][W] buffers of which this rank fills its rows - over all ranks the same bytes reach the host as with
+ * one GPU.  A strip's path trace overlaps its denoiser only for handles created with PTD_PT_GATED_MAIL. */
 ptd_status ptd_frame_submit(ptd_pt*, ptd_dn*, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host);
 ptd_status ptd_frame_wait(ptd_pt*);
+/* Device time of a run of submitted frames (CUDA events on the streams ptd_frame_submit launches on): op 0 arms the timer - the next
+ * ptd_frame_submit records the start event ahead of its first launch; op 1 records the stop event behind the last submitted frame's
+ * denoiser, waits for it and returns the elapsed milliseconds. */
+ptd_status ptd_frame_timer(ptd_pt*, int op, float* ms);
 /* ---- row-strip mode: the denoiser of ONE frame tiled over several GPUs ----------------------------
  * A strip handle owns padded rows [row0, row0 + rows) (multiples of 32) of the frame.  Its convs store their first / last
  * output row directly into the neighbour strips' halo rows over NVLink (peer pointers) and raise a flag there; the

@@ -159,6 +159,24 @@ def test_multi_process_strips_bit_exact_when_two_gpus():
     assert r.stdout.count("BIT-EXACT") == 2
 
 
+@pytest.mark.parametrize("gated", ["1", "0"], ids=["two-streams-gated-mail", "one-stream"])
+def test_multi_process_frame_submit_on_strips_when_two_gpus(gated):
+    """ptd_frame_submit / ptd_frame_wait on row-strip handles, one process per GPU (tools/check_frame_strips.py): every rank's rows of the
+    G-buffer and of the denoised frame reach its host buffers bit-identical to the untiled frames, in the contract mode, with the path
+    trace of frame k + 1 overlapping the denoiser of frame k (gated live-count mail) and without.  Needs >= 2 GPUs."""
+    capi = _capi()
+    if capi.device_count() < 2:
+        pytest.skip("needs two GPUs (runs under `gpurun --gpus 2`)")
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                        "--master-port", "29541", os.path.join(root, "tools", "check_frame_strips.py"), "320", "250", "7", "2xf16", gated],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert r.stdout.count("BIT-EXACT") == 2
+
+
 @pytest.mark.parametrize("mode", ["fp32", "tf32"])
 @pytest.mark.parametrize("H,W", [(1, 1), (33, 31), (40, 200)])
 def test_edge_sizes(H, W, mode, wfile):

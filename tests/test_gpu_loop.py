@@ -96,3 +96,18 @@ def test_frame_submit_wait_equals_the_two_host_calls(tmp_path, mode):
             assert gb[k - 1].tobytes() == ref[k - 1][0].tobytes(), k - 1
     pt_b.frame_wait()
     assert rgb[n - 1].tobytes() == ref[n - 1][1].tobytes()
+    # a frame may stay on the device (no host pointer at all), and the device timer brackets a run of frames
+    pt_b.frame_timer_start()
+    for k in range(3):
+        pt_b.frame_submit(dn_b, None, None, cam=cams[k], reset=(k == 0))
+        if k:
+            pt_b.frame_wait()
+    ms = pt_b.frame_timer_stop()
+    pt_b.frame_wait()
+    assert 0.0 < ms < 5000.0
+    # accumulation (iter > 1) needs the first-hit planes of iteration 1, which live in the other slot: reported, not silently wrong
+    with pytest.raises(capi.PtdError, match="iter == 1"):
+        pt_b.frame_submit(dn_b, rgb[0], None, cam=cams[0], iter=2)
+    g3, rgb3 = pt_b.frame_host(dn_b, cam=cams[3], reset=True)           # the blocking call still works afterwards
+    g_ref = pt_a.render_host(cams[3])
+    assert g3.tobytes() == g_ref.tobytes() and rgb3.tobytes() == dn_a.forward_host(g_ref, reset=True).tobytes()
