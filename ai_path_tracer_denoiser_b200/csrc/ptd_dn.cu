@@ -313,8 +313,8 @@ static ptd_status read_ptdw(const char* path, std::map<std::string, std::vector<
 // 28 convs, 3 % of the FLOPs) are computed IN FULL by every strip: encoder 3's fused max-pool stores its rows of the level-3 input
 // into every strip's full-height tensor ("gather": peer stores to all strips + one flag per source strip), the 13 convs then run
 // without any exchange, and decoder 3 reads its rows of the replicated level-3 tensors back into the strip (src_yoff).
-// Opt-in for now: environment PTD_DN_REPL_LEVEL=3 at ptd_dn_create_strip time on every rank (default 6 = every level tiled);
-// validated bit-identical to the untiled run (tests, 8 processes at 720p), not yet re-timed under the serial frame loop.
+// Default for strip handles; PTD_DN_REPL_LEVEL=6 at ptd_dn_create_strip time (same value on every rank) tiles every level instead.
+// Both are bit-identical to the untiled run (tests/test_gpu_dn.py, tests/test_gpu_pt.py; multi-process: tools/check_frame_strips.py).
 #define DN_MAX_TENSORS 48
 #define DN_MAX_RANKS 8
 #define DN_REPL_LEVEL 3                       /* the level replication starts at when enabled */
@@ -364,7 +364,7 @@ struct ptd_dn {
     bool has_peer[2] = {false, false};                     // a strip above / below exists
     size_t gflags_off = 0;
     bool pdl = false;                                      // PTD_DN_PDL=1: convs launched with programmatic stream serialization
-    int repl_level = 6;                                    // levels >= this are replicated on every strip (6 = none)
+    int repl_level = 6;                                    // levels >= this are replicated on every strip (6 = none; strips default to DN_REPL_LEVEL)
     int t_gather = -1;                                     // the gathered tensor (pooled output of encoder repl_level, full height)
     std::vector<int> tensor_level; std::vector<char> tensor_full;
     uint32_t epoch = 0;
@@ -408,6 +408,7 @@ static ptd_status dn_create(const char* weights_path, int H, int W, int row0, in
     ptd_dn* h = new ptd_dn();
     h->device = device; h->flags = flags; h->H = H; h->W = W; h->Hp = Hp; h->Wp = Wp; h->row0 = row0; h->rows = rows; h->strip = strip;
     if (const char* e = getenv("PTD_DN_PDL")) h->pdl = atoi(e) > 0;
+    if (strip) h->repl_level = DN_REPL_LEVEL;             // PTD_DN_REPL_LEVEL=6 (same on every rank): tile every level instead
     if (const char* e = getenv("PTD_DN_REPL_LEVEL")) { const int v = atoi(e); if (v >= 3 && v <= 6) h->repl_level = v; }
     auto fail = [&](ptd_status code) { ptd_dn_destroy(h); return code; };
     auto dalloc = [&](size_t floats) -> float* {

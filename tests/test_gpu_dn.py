@@ -108,11 +108,11 @@ def test_full_size_720p_properties(mode, wfile):
 
 @pytest.fixture(params=["tiled", "replicated"])
 def repl_levels(request, monkeypatch):
-    """All levels tiled (default) or levels >= 1/8 resolution replicated on every strip (PTD_DN_REPL_LEVEL=3, read at create)."""
+    """All levels tiled (PTD_DN_REPL_LEVEL=6) or levels >= 1/8 resolution replicated on every strip (3, the default; read at create)."""
     if request.param == "replicated":
         monkeypatch.setenv("PTD_DN_REPL_LEVEL", "3")
     else:
-        monkeypatch.delenv("PTD_DN_REPL_LEVEL", raising=False)
+        monkeypatch.setenv("PTD_DN_REPL_LEVEL", "6")                 # every level tiled
     return request.param
 
 

@@ -311,7 +311,7 @@ def test_strip_pipeline_equals_full_pipeline(tmp_path, repl, monkeypatch):
     if repl:
         monkeypatch.setenv("PTD_DN_REPL_LEVEL", repl)          # levels >= 1/8 resolution replicated on every strip
     else:
-        monkeypatch.delenv("PTD_DN_REPL_LEVEL", raising=False)
+        monkeypatch.setenv("PTD_DN_REPL_LEVEL", "6")                 # every level tiled
     wfile = weights.save_weights(weights.synthetic_state_dict(1234), str(tmp_path / "w.ptdw"))
     W, H, n = 96, 80, 3
     sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
