@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libptd.so")
+LIB_PATH = os.environ.get("PTD_LIBPTD") or os.path.join(HERE, "libptd.so")     # (PTD_LIBPTD: an alternative build, for A/B timing)
 
 # record layouts of Inference/src/sceneStructs.h == include/ptd.h
 PATH_DT = np.dtype([("o", "<f4", 3), ("d", "<f4", 3), ("color", "<f4", 3), ("pix", "<i4"), ("rb", "<i4")])

@@ -125,6 +125,9 @@ struct __align__(64) TcParams {
     // the hi x hi chain into nseg pieces - tcgen05.mma truncates on every accumulate (tools/microbench/umma_accum), so one long chain loses
     // ~10x the accuracy the operand split buys; the epilogue adds the pieces in fp32 (round to nearest).
     int nseg, nbuf, buf_cols;
+    int fused;                           // split modes: hi x hi and hi x lo of a chunk in ONE MMA of N = 2 * coutp (see mma_role); else three passes
+    uint32_t corr_mask;                  // bit a: accumulator a (columns [a * coutp, (a + 1) * coutp) of a buffer) holds cross terms
+    uint32_t b_load_bytes;               // streamed weights: bytes of B a stage carries (b_stage_bytes, or twice that when fused)
     uint32_t seg_start;                  // bit c: chunk c starts the next main accumulator
     float corr_scale;                    // the correction accumulator's scale: 1 (3xTF32) or 2^-11 (2xF16: lo operands are stored x 2^11)
     int nissue;                          // MMA issuer warps in use (2 when the stage ring splits into two rings of >= 2 stages and nbuf is even)
@@ -321,11 +324,16 @@ __device__ __forceinline__ void store16(const DnTensor& t, float* row, int c0, c
 // One chunk (one shared-memory stage): NTAPS taps x (TWO ? 2 : 1) K steps into one accumulator.  Every descriptor is the stage's base plus
 // a compile-time constant (padded Cout, tap geometry and K-step pitch are template parameters), so an MMA costs two uniform adds and
 // the UTCHMMA itself.  a_base already carries the phase's tap origin and the LBO field, b_cur the LBO field.
-template <int NTAPS, bool HALF, int COUTP, bool TWO>
-__device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_base, uint32_t b_cur, uint32_t idesc, uint32_t accumulate) {
+// NCOLS = the MMA's N (accumulator columns written), BROWS = rows of the weight slab per k vector (its LBO / 16): coutp for both, except in
+// the fused split scheme, where a slab holds the hi rows followed by the lo rows (BROWS = 2 * coutp) and one MMA of NCOLS = 2 * coutp
+// computes hi x hi | hi x lo at once.
+template <int NTAPS, bool HALF, int NCOLS, int BROWS, bool TWO>
+__device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_base, uint32_t b_cur, uint32_t accumulate) {
+    constexpr uint32_t fmt = HALF ? 0u : 2u;                                      // D = f32, A = B = tf32 (format 2) or f16 (format 0), both K-major, M = 128
+    constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(NCOLS >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t a_hi = (uint32_t)(TC_ROW_PITCH >> 4) | (1u << 14);          // SBO = halo row pitch
     constexpr uint32_t b_hi = (uint32_t)(128 >> 4) | (1u << 14);                  // SBO = next 8 output channels
-    constexpr uint32_t b_kstep = (uint32_t)COUTP * 2u;                            // (coutp * 32 B) >> 4: one K step
+    constexpr uint32_t b_kstep = (uint32_t)BROWS * 2u;                            // (rows * 32 B) >> 4: one K step
 #pragma unroll
     for (int t = 0; t < NTAPS; ++t) {
         // tap origin inside the halo tile in 16-byte units: 3x3 taps (dy, dx) = (t / 3 - 1, t % 3 - 1) from the tile's (1, 1); the 2x2 taps of an
@@ -344,18 +352,23 @@ __device__ __forceinline__ void issue_chunk(uint32_t d_tmem, uint32_t a_base, ui
 // dozen instructions more per 18 MMAs cost 7 cycles per MMA).  Hence: nested loops instead of div/mod, every parameter hoisted into
 // registers, compile-time descriptor offsets (issue_chunk), and TWO issuing warps that take the CTA's tiles alternately, so that one's
 // bookkeeping (barrier polls - slow while the tensor core owns the shared-memory pipe -, loop control) hides behind the other's MMAs.
-template <int NTAPS, bool HALF, int COUTP>
+// SCHEME: 0 = one pass per chunk (tf32 / f16), 1 = split operands in three passes, 2 = split operands fused (two passes) - a template
+// parameter because every instruction of the per-chunk code below is on the kernel's critical path.
+template <int NTAPS, bool HALF, int COUTP, int SCHEME>
 __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uint8_t* smem_b, uint64_t* full, uint64_t* empty,
                                          uint64_t* tmem_full, uint64_t* tmem_empty, uint32_t tmem_base, int issuer) {
-    // instruction descriptor: D = f32, A = B = tf32 (format 2) or f16 (format 0), both K-major, N = coutp, M = 128
-    constexpr uint32_t fmt = HALF ? 0u : 2u;
-    constexpr uint32_t idesc = (1u << 4) | (fmt << 7) | (fmt << 10) | ((uint32_t)(COUTP >> 3) << 17) | ((128u >> 4) << 24);
     constexpr uint32_t a_lbo = (uint32_t)(TC_QUAD_PITCH >> 4) << 16;              // LBO = next channel quad
-    constexpr uint32_t b_lbo = (uint32_t)COUTP << 16;                             // (coutp * 16 B) >> 4: next k quad of the same tap
-    const int nchunks = p.n0 + p.n1, npass = p.x3 ? 3 : 1, nphases = p.nphases, total = p.total_items, stages = p.stages;
-    const bool resident = p.resident != 0, x3 = p.x3 != 0;
+    const bool resident = p.resident != 0;
+    constexpr bool x3 = SCHEME != 0, fused = SCHEME == 2;
+    // fused split scheme: per chunk one stage with the hi activations - MMAs of N = 2 * coutp against slabs [hi rows | lo rows]: hi x hi into the
+    // main accumulator and hi x lo into the correction accumulator right behind it, the A operand read from shared memory once for both
+    // (A is 4 KB of the 5 KB an N = 32 MMA fetches) - and one stage with the lo activations: lo x hi (N = coutp, the slab's hi rows) into the
+    // same correction accumulator.  Unfused: three passes hi x hi, hi x lo, lo x hi over separate hi / lo weight blocks.
+    constexpr uint32_t b_lbo = (uint32_t)(fused ? 2 * COUTP : COUTP) << 16;      // (rows * 16 B) >> 4: next k vector of the same tap
+    constexpr int npass = fused ? 2 : (x3 ? 3 : 1);
+    const int nchunks = p.n0 + p.n1, nphases = p.nphases, total = p.total_items, stages = p.stages;
     const uint32_t sa0 = (smem_u32(smem_a) >> 4) | a_lbo, sb0 = (smem_u32(smem_b) >> 4) | b_lbo;
-    const uint32_t b_stage16 = p.b_stage_bytes >> 4, a_stage16 = TC_A_BYTES >> 4;
+    const uint32_t b_stage16 = p.b_stage_bytes >> 4, a_stage16 = TC_A_BYTES >> 4, b_slot16 = p.b_load_bytes >> 4;
     const uint32_t b_chunk16 = b_stage16 * (x3 ? 2u : 1u);                    // resident weights: blocks of one chunk (hi [, lo])
     const uint32_t d_tmem0 = __shfl_sync(0xffffffffu, tmem_base, 0);          // provably warp-uniform
     // chunks whose source holds only two channel vectors there (one K step; the other two vectors are TMA zero fill): bit c
@@ -388,21 +401,33 @@ __device__ __forceinline__ void mma_role(const TcParams& p, uint8_t* smem_a, uin
         uint32_t started = 0, seg = 0;                                        // accumulators of this buffer that hold a partial sum already
         for (int c = 0; c < nchunks; ++c) {
             const bool two = !((one_step >> c) & 1u);
-            if (c && ((seg_start >> c) & 1u)) ++seg;
+            if (x3 && c && ((seg_start >> c) & 1u)) ++seg;
+#pragma unroll
             for (int pass = 0; pass < npass; ++pass) {
                 mbar_wait(&full[stage0 + stage], phase);
                 fence_after_sync();
-                // resident weights: block (phase, chunk) [x3: hi block, lo block]; passes 0 and 2 use the hi block, pass 1 the lo block
-                const uint32_t b_cur = resident ? b_base + (pass == 1 ? b_stage16 : 0u) : sb0 + (uint32_t)(stage0 + stage) * b_stage16;
+                // resident weights: block (phase, chunk): [hi block, lo block] (passes 0 and 2 use the hi block, pass 1 the lo block) or one fused slab
+                const uint32_t b_cur = resident ? b_base + ((!fused && pass == 1) ? b_stage16 : 0u) : sb0 + (uint32_t)(stage0 + stage) * b_slot16;
                 const bool last = c == nchunks - 1 && pass == npass - 1;
-                // hi x hi -> main accumulator `seg`; the cross terms (passes 1, 2) -> the correction accumulator behind the mains
-                const uint32_t ai = pass == 0 ? seg : (uint32_t)nseg;
-                const uint32_t d_tmem = d_buf + ai * (uint32_t)COUTP;
-                const uint32_t accumulate = (started >> ai) & 1u;
-                started |= 1u << ai;
+                // accumulator: unfused - hi x hi -> main `seg`, cross terms -> the correction accumulator behind the mains; fused - pairs [main | correction]
+                uint32_t d_tmem = d_buf, accumulate = c ? 1u : 0u;
+                if (x3) {
+                    const uint32_t ai = fused ? 2u * seg + (uint32_t)pass : (pass == 0 ? seg : (uint32_t)nseg);
+                    d_tmem = d_buf + ai * (uint32_t)COUTP;
+                    accumulate = (started >> ai) & 1u;
+                    started |= (fused && pass == 0) ? (3u << ai) : (1u << ai);
+                }
                 if (elect_one()) {
-                    if (two) issue_chunk<NTAPS, HALF, COUTP, true>(d_tmem, a_base, b_cur, idesc, accumulate);
-                    else issue_chunk<NTAPS, HALF, COUTP, false>(d_tmem, a_base, b_cur, idesc, accumulate);
+                    if (fused && pass == 0) {
+                        if (two) issue_chunk<NTAPS, HALF, 2 * COUTP, 2 * COUTP, true>(d_tmem, a_base, b_cur, accumulate);
+                        else issue_chunk<NTAPS, HALF, 2 * COUTP, 2 * COUTP, false>(d_tmem, a_base, b_cur, accumulate);
+                    } else if (fused) {
+                        if (two) issue_chunk<NTAPS, HALF, COUTP, 2 * COUTP, true>(d_tmem, a_base, b_cur, accumulate);
+                        else issue_chunk<NTAPS, HALF, COUTP, 2 * COUTP, false>(d_tmem, a_base, b_cur, accumulate);
+                    } else {
+                        if (two) issue_chunk<NTAPS, HALF, COUTP, COUTP, true>(d_tmem, a_base, b_cur, accumulate);
+                        else issue_chunk<NTAPS, HALF, COUTP, COUTP, false>(d_tmem, a_base, b_cur, accumulate);
+                    }
                     mma_commit(&empty[stage0 + stage]);                       // frees the smem stage when the MMAs retire
                     if (last) mma_commit(&tmem_full[buf]);                    // accumulators complete -> epilogue
                 }
@@ -427,7 +452,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     uint8_t* smem = (uint8_t*)(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* smem_a = smem;
     uint8_t* smem_b = smem + (size_t)p.stages * TC_A_BYTES;
-    const size_t b_bytes = p.resident ? (size_t)p.w_total_bytes : (size_t)p.stages * p.b_stage_bytes;
+    const size_t b_bytes = p.resident ? (size_t)p.w_total_bytes : (size_t)p.stages * p.b_load_bytes;
     uint64_t* full = (uint64_t*)(smem_b + ((b_bytes + 15) & ~(size_t)15));
     uint64_t* empty = full + TC_MAX_STAGES;
     uint64_t* tmem_full = empty + TC_MAX_STAGES;
@@ -494,8 +519,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
         __syncwarp();
         if (p.pdl) asm volatile("griddepcontrol.wait;" ::: "memory");     // the previous launch has completed and its stores are visible
-        const uint32_t stage_tx = TC_A_BYTES + (p.resident ? 0u : p.b_stage_bytes);
-        const int npass = p.x3 ? 3 : 1, n0 = p.n0, nissue = p.nissue, ring_stages = p.stages / nissue;
+        const uint32_t stage_tx = TC_A_BYTES + (p.resident ? 0u : p.b_load_bytes);
+        const int fused = p.fused, npass = fused ? 2 : (p.x3 ? 3 : 1), n0 = p.n0, nissue = p.nissue, ring_stages = p.stages / nissue;
         // One stage ring per MMA issuer; the CTA's tiles alternate between the issuers, and the producer feeds the `nissue` tiles in flight
         // unit by unit in turn, so that both issuers always have operands staged (feeding tile after tile would starve the second issuer
         // whenever a tile has more units than a ring has stages).
@@ -522,11 +547,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                         else if (tc::elect_one()) {
                             tc::mbar_expect_tx(&full[sidx], stage_tx);
                             // halo tile origin: pixel (x0 - 1, y0 - 1) = buffer row y0 (apron offset +1); x < 0 / x >= W are zero filled
-                            const CUtensorMap* map = c < n0 ? (pass == 2 ? &p.mapA0lo : &p.mapA0) : (pass == 2 ? &p.mapA1lo : &p.mapA1);
+                            const bool lo = pass == (fused ? 1 : 2);                     // the pass that multiplies the lo activations
+                            const CUtensorMap* map = c < n0 ? (lo ? &p.mapA0lo : &p.mapA0) : (lo ? &p.mapA1lo : &p.mapA1);
                             tc::tma_load_3d(smem_a + (size_t)sidx * TC_A_BYTES, map, &full[sidx], (x0[r] - 1) * (HALF ? 8 : 4), y0[r], (c < n0 ? c : c - n0) * 4);
                             if (!p.resident) {
-                                const size_t blk = p.x3 ? (size_t)((ph[r] * nchunks + c) * 2 + (pass == 1 ? 1 : 0)) : (size_t)(ph[r] * nchunks + c);
-                                tc::bulk_load(smem_b + (size_t)sidx * p.b_stage_bytes, (const uint8_t*)p.wpack + blk * p.b_stage_bytes, p.b_stage_bytes, &full[sidx]);
+                                // unfused split: blocks (hi, lo) per chunk, pass 1 takes the lo block; fused: the chunk's slab [hi rows | lo rows] for both passes
+                                const size_t blk = fused ? (size_t)(ph[r] * nchunks + c) * 2 : (p.x3 ? (size_t)((ph[r] * nchunks + c) * 2 + (pass == 1 ? 1 : 0)) : (size_t)(ph[r] * nchunks + c));
+                                tc::bulk_load(smem_b + (size_t)sidx * p.b_load_bytes, (const uint8_t*)p.wpack + blk * p.b_stage_bytes, p.b_load_bytes, &full[sidx]);
                             }
                         }
                         __syncwarp();
@@ -540,10 +567,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         //       one elected lane issues.  One tcgen05.mma costs a handful of uniform-datapath adds here - issued from divergent
         //       code the same loop cost ~135 cycles per MMA (R2UR + ELECT sequences) and was the kernel's bottleneck.
         if (p.resident) { tc::mbar_wait(wfull, 0); tc::fence_after_sync(); }
-#define TC_ROLE(C) case C: if (p.ntaps == 9) tc::mma_role<9, HALF, C>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, warp - TC_WARP_MMA); \
-                            else tc::mma_role<4, HALF, C>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, warp - TC_WARP_MMA); break;
+        // the scheme follows from the kernel variant's output format except for the last layer (fp32 output from split sources): SPLIT says
+        // whether this variant can see split sources at all, which keeps the plain variants free of the split roles' code
+#define TC_ROLE2(C, S) if (p.ntaps == 9) tc::mma_role<9, HALF, C, S>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, warp - TC_WARP_MMA); \
+                       else tc::mma_role<4, HALF, C, S>(p, smem_a, smem_b, full, empty, tmem_full, tmem_empty, tmem_base, warp - TC_WARP_MMA);
+#define TC_ROLE(C) case C: if (!p.x3) { TC_ROLE2(C, 0) } else if (p.fused) { TC_ROLE2(C, 2) } else { TC_ROLE2(C, 1) } break;
         switch (p.coutp) { TC_ROLE(16) TC_ROLE(32) TC_ROLE(48) TC_ROLE(64) TC_ROLE(80) TC_ROLE(96) TC_ROLE(112) TC_ROLE(128) default: break; }
 #undef TC_ROLE
+#undef TC_ROLE2
     } else if (warp < TC_EPI_WARPS) {
         // ===== epilogue: TMEM -> registers -> bias/BN/LeakyReLU -> CHW4 ============================================
         // Two warps per SM sub-partition run this loop; with the N = 32 layers' MMAs at ~750 (f16) .. 1500 (tf32) cycles per tile it has
@@ -554,7 +585,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         const int m = q * 32 + lane;                               // pixel of the tile == TMEM lane
         const int ty = m >> 3, tx = m & 7;
         const int coutp = p.coutp, nphases = p.nphases, tiles_x = p.tiles_x, Ws = p.Ws, Hs = p.Hs, out_mul = p.out_mul, total = p.total_items;
-        const int nbuf = p.nbuf, nacc = p.nseg + (p.x3 ? 1 : 0), x3 = p.x3;
+        const int nbuf = p.nbuf, nacc = p.buf_cols / p.coutp;
+        const uint32_t corr_mask = p.corr_mask;
         const uint32_t buf_cols = (uint32_t)p.buf_cols;
         const float corr_scale = p.corr_scale;
         const bool round_out = !HALF && p.round_out && !p.x3;     // fp16 storage rounds in the conversion, the split modes split in store16
@@ -588,32 +620,35 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             for (int c0 = half * 16; c0 < coutp; c0 += 32) {
                 float acc[16];
                 {
+                    // the buffer's accumulators, summed in fp32 (round to nearest): the cross-term accumulators first (scaled), then the main segments
                     uint32_t r[16];
-                    int a = nacc - 1;
-                    if (x3) {                                      // correction accumulator (scaled) + the last main accumulator
-                        uint32_t r2[16];
-                        tc::tmem_ld16(taddr + (uint32_t)(a * coutp + c0), r);
-                        tc::tmem_ld16(taddr + (uint32_t)((a - 1) * coutp + c0), r2);
-                        tc::tmem_ld_wait();
+                    if (nacc == 1) {
+                        if (p.dbg & 4) {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[j] = fmaf(__uint_as_float(r[j]), corr_scale, __uint_as_float(r2[j]));
-                        a -= 2;
-                    } else if (p.dbg & 4) {
-#pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[j] = (float)(j + c0);
-                        a = -1;
-                    } else {
-                        tc::tmem_ld16(taddr + (uint32_t)(a * coutp + c0), r);
-                        tc::tmem_ld_wait();
+                            for (int j = 0; j < 16; ++j) r[j] = (uint32_t)(j + c0);
+                        } else {
+                            tc::tmem_ld16(taddr + (uint32_t)c0, r);
+                            tc::tmem_ld_wait();
+                        }
 #pragma unroll
                         for (int j = 0; j < 16; ++j) acc[j] = __uint_as_float(r[j]);
-                        a -= 1;
-                    }
-                    for (; a >= 0; --a) {
-                        tc::tmem_ld16(taddr + (uint32_t)(a * coutp + c0), r);
-                        tc::tmem_ld_wait();
+                    } else {
 #pragma unroll
-                        for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+                        for (int j = 0; j < 16; ++j) acc[j] = 0.0f;
+                        for (int a = 0; a < nacc; ++a) {
+                            if (!((corr_mask >> a) & 1u)) continue;
+                            tc::tmem_ld16(taddr + (uint32_t)(a * coutp + c0), r);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) acc[j] = fmaf(__uint_as_float(r[j]), corr_scale, acc[j]);
+                        }
+                        for (int a = nacc - 1; a >= 0; --a) {
+                            if ((corr_mask >> a) & 1u) continue;
+                            tc::tmem_ld16(taddr + (uint32_t)(a * coutp + c0), r);
+                            tc::tmem_ld_wait();
+#pragma unroll
+                            for (int j = 0; j < 16; ++j) acc[j] += __uint_as_float(r[j]);
+                        }
                     }
                 }
                 float o[16];
@@ -775,23 +810,46 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     p.total_items = p.tiles_x * p.tiles_y * p.nphases;
     p.x3 = d.src0.lo_off ? 1 : 0;
     if (p.x3 && d.src1.base && !d.src1.lo_off) PTD_FAIL(PTD_ERR_ARG, "tc conv: split-operand modes need hi/lo copies of both sources");
-    // accumulators (see TcParams): buffers of nseg main accumulators [+ the correction accumulator], at least two buffers in 512 columns
+    if (nch > 32) PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: %d channel chunks (> 32)", nch);
+    const int nblk = p.x3 ? 2 : 1;                           // weight blocks per (phase, chunk): hi [, lo]
+    p.b_stage_bytes = (uint32_t)(p.ntaps * coutp * 64);
+    p.w_total_bytes = (uint32_t)(p.nphases * nch * nblk) * p.b_stage_bytes;
+    // shared memory plan: resident weights when they leave room for >= 4 A stages; the split modes fuse hi x hi | hi x lo into one MMA
+    // (see mma_role) whenever a stage can carry a chunk's whole [hi | lo] slab and still leave three stages
+    const size_t budget = TC_SMEM_BUDGET;
+    p.b_load_bytes = p.b_stage_bytes;
+    p.fused = 0;
+    if ((size_t)p.w_total_bytes + 4 * TC_A_BYTES <= budget) {
+        p.resident = 1;
+        p.stages = (int)std::min<size_t>(TC_MAX_STAGES, (budget - p.w_total_bytes) / TC_A_BYTES);
+        p.fused = p.x3;
+    } else {
+        p.resident = 0;
+        if (p.x3 && 2 * coutp <= 256 && budget / (TC_A_BYTES + 2 * (size_t)p.b_stage_bytes) >= 3) { p.fused = 1; p.b_load_bytes = 2 * p.b_stage_bytes; }
+        p.stages = (int)std::min<size_t>(TC_MAX_STAGES, budget / (TC_A_BYTES + p.b_load_bytes));
+        if (p.stages < 2) PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: a stage of %u B does not fit twice in shared memory", TC_A_BYTES + p.b_load_bytes);
+    }
+    if (const char* e = getenv("PTD_DN_NO_FUSED_SPLIT")) { if (atoi(e) > 0 && p.fused) { p.fused = 0; if (!p.resident) { p.b_load_bytes = p.b_stage_bytes; p.stages = (int)std::min<size_t>(TC_MAX_STAGES, budget / (TC_A_BYTES + p.b_load_bytes)); } } }
+    // accumulators (see TcParams): buffers of nseg main accumulators + (split modes) the correction accumulator(s), at least two buffers in 512 columns
     {
         const int max_accs = (TC_TMEM_COLS / 2) / coutp;
-        p.nseg = p.x3 ? std::max(1, std::min(std::min(TC_MAX_SEGS, max_accs - 1), nch)) : 1;
-        p.buf_cols = (p.nseg + p.x3) * coutp;
+        if (p.fused) {                                        // pairs [main | correction]
+            p.nseg = std::max(1, std::min(std::min(2, max_accs / 2), nch));
+            p.buf_cols = 2 * p.nseg * coutp;
+            p.corr_mask = 0xaaaaaaaau & ((1u << (2 * p.nseg)) - 1u);
+        } else {
+            p.nseg = p.x3 ? std::max(1, std::min(std::min(TC_MAX_SEGS, max_accs - 1), nch)) : 1;
+            p.buf_cols = (p.nseg + p.x3) * coutp;
+            p.corr_mask = p.x3 ? 1u << p.nseg : 0u;
+        }
         p.nbuf = std::min(TC_MAX_BUFS, TC_TMEM_COLS / p.buf_cols);
-        if (p.nbuf < 2) PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: %d accumulators of %d columns do not fit twice in tensor memory", p.nseg + p.x3, coutp);
+        if (p.nbuf < 2) PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: %d columns of accumulators do not fit twice in tensor memory", p.buf_cols);
         p.seg_start = 0;
         for (int c = 1; c < nch; ++c)
             if ((c * p.nseg) / nch != ((c - 1) * p.nseg) / nch) p.seg_start |= 1u << c;
         p.corr_scale = half ? 1.0f / 2048.0f : 1.0f;
         if (const char* e = getenv("PTD_DN_DEBUG")) p.dbg = atoi(e);
-        if (nch > 32) PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: %d channel chunks (> 32)", nch);
     }
-    const int nblk = p.x3 ? 2 : 1;                           // weight blocks per (phase, chunk): hi [, lo]
-    p.b_stage_bytes = (uint32_t)(p.ntaps * coutp * 64);
-    p.w_total_bytes = (uint32_t)(p.nphases * nch * nblk) * p.b_stage_bytes;
     // packed weights: [phase][chunk][tap][kstep j][k vector][n][16 bytes = 4 tf32 / 8 fp16]  (see make_desc_nosw); built as 16-bit
     // or 32-bit words in one byte buffer
     std::vector<float> pack((size_t)p.w_total_bytes / 4, 0.f);
@@ -819,15 +877,19 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
                     // position of padded-concat channel c: source, chunk of that source, K step, vector, element
                     const int cl = c < c0p ? c : c - c0p, chunk = (c < c0p ? 0 : p.n0) + cl / CH, r = cl % CH;
                     const int epv = CH / 4, kstep = r / (2 * epv), kq = (r % (2 * epv)) / epv, ke = r % epv;
-                    const size_t off = (((((size_t)((ph * nch + chunk) * nblk) * p.ntaps + t) * 2 + kstep) * 2 + kq) * (size_t)coutp + (size_t)n) * epv + ke;
+                    // unfused: [phase][chunk][hi | lo block][tap][kstep][k vector][n]; fused split: [phase][chunk][tap][kstep][k vector][hi n .. | lo n ..]
+                    const size_t slab = (size_t)((t * 2 + kstep) * 2 + kq);
+                    const size_t off = p.fused ? (((size_t)(ph * nch + chunk) * p.ntaps * 4 + slab) * (size_t)(2 * coutp) + (size_t)n) * epv + ke
+                                               : (((size_t)((ph * nch + chunk) * nblk) * p.ntaps * 4 + slab) * (size_t)coutp + (size_t)n) * epv + ke;
+                    const size_t lo_off = p.fused ? (size_t)coutp * epv : (size_t)p.b_stage_bytes / (half ? 2 : 4);      // elements from a weight's hi to its lo copy
                     if (half) {
                         const __half hi = __float2half_rn(s);
                         pack_h[off] = hi;
-                        if (p.x3) pack_h[off + (size_t)p.b_stage_bytes / 2] = __float2half_rn((s - __half2float(hi)) * 2048.0f);   // lo block, scaled like the activations' lo copy
+                        if (p.x3) pack_h[off + lo_off] = __float2half_rn((s - __half2float(hi)) * 2048.0f);   // lo copy, scaled like the activations' lo copy
                     } else {
                         const float hi = host_round_tf32(s);
                         pack[off] = hi;
-                        if (p.x3) pack[off + (size_t)p.b_stage_bytes / 4] = host_round_tf32(s - hi);   // the lo block follows the hi block
+                        if (p.x3) pack[off + lo_off] = host_round_tf32(s - hi);
                     }
                 }
         }
@@ -851,21 +913,11 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
         if (rc != PTD_OK) return rc;
         if (p.n1) { t = d.src1; t.base += t.lo_off; rc = tc_make_map_act(&p.mapA1lo, t); if (rc != PTD_OK) return rc; }
     }
-    // shared memory plan: resident weights when they leave room for >= 4 A stages
-    const size_t budget = TC_SMEM_BUDGET;
-    if ((size_t)p.w_total_bytes + 4 * TC_A_BYTES <= budget) {
-        p.resident = 1;
-        p.stages = (int)std::min<size_t>(TC_MAX_STAGES, (budget - p.w_total_bytes) / TC_A_BYTES);
-    } else {
-        p.resident = 0;
-        p.stages = (int)std::min<size_t>(TC_MAX_STAGES, budget / (TC_A_BYTES + p.b_stage_bytes));
-        if (p.stages < 2) PTD_FAIL(PTD_ERR_UNSUPPORTED, "tc conv: a stage of %u B does not fit twice in shared memory", TC_A_BYTES + p.b_stage_bytes);
-    }
     // two MMA issuers need a stage ring each (>= 2 stages) and an even number of accumulator buffers (see mma_role)
     p.nissue = (p.stages >= 4 && p.nbuf >= 2) ? TC_MMA_WARPS : 1;
     if (const char* e = getenv("PTD_DN_ISSUERS")) { if (atoi(e) == 1) p.nissue = 1; }
     if (p.nissue == 2) { p.stages &= ~1; p.nbuf &= ~1; }
-    const size_t b_bytes = p.resident ? (size_t)p.w_total_bytes : (size_t)p.stages * p.b_stage_bytes;
+    const size_t b_bytes = p.resident ? (size_t)p.w_total_bytes : (size_t)p.stages * p.b_load_bytes;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

@@ -8,7 +8,7 @@ mkdir -p "$OUT"
 if [ -n "$KEXPR" ]; then timeout 400 python -m pytest tests -m gpu -q -x --timeout=120 -k "$KEXPR" > "$OUT/pytest.log" 2>&1; else timeout 400 python -m pytest tests/test_gpu_dn.py tests/test_gpu_at_size.py -m gpu -q -s -x --timeout=120 > "$OUT/pytest.log" 2>&1; fi
 echo "pytest rc=$?"; tail -5 "$OUT/pytest.log"; grep "max-abs / rel-L2" "$OUT/pytest.log"
 for m in f16 tf32 2xf16 3xtf32; do
-  timeout 150 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-autotune --mode $m > "$OUT/bench_$m.json" 2> "$OUT/bench_$m.err"; echo "$m rc=$?"
+  timeout 150 python bench.py --steps 40 --warmup 5 --no-cpu-baseline --no-side-modes --mode $m > "$OUT/bench_$m.json" 2> "$OUT/bench_$m.err"; echo "$m rc=$?"
 done
 python - "$OUT" <<'PY'
 import glob, json, os, sys
