@@ -735,8 +735,8 @@ struct ptd_pt {
     // ptd_frame_submit / ptd_frame_wait: two frame slots, three streams (path trace, denoise + frame copy, G-buffer copy)
     cudaStream_t fr_stream[3] = {nullptr, nullptr, nullptr};
     float* fr_gbuf[2] = {nullptr, nullptr}; float* fr_rgb[2] = {nullptr, nullptr};
-    cudaEvent_t fr_ev_pt[2] = {nullptr, nullptr}, fr_ev_done[2] = {nullptr, nullptr}, fr_ev_gcopy[2] = {nullptr, nullptr};
-    bool fr_has_gcopy[2] = {false, false};
+    cudaEvent_t fr_ev_pt[2] = {nullptr, nullptr}, fr_ev_done[2] = {nullptr, nullptr}, fr_ev_gcopy[2] = {nullptr, nullptr}, fr_ev_rcopy[2] = {nullptr, nullptr};
+    bool fr_has_gcopy[2] = {false, false}, fr_has_rcopy[2] = {false, false};
     long long fr_submitted = 0, fr_waited = 0;
     cudaEvent_t fr_ev_t0 = nullptr, fr_ev_t1 = nullptr; bool fr_timer_armed = false; cudaStream_t fr_last_dn = nullptr;   // ptd_frame_timer
     bool wide_lookback = false;                              // PTD_PT_WIDE_LOOKBACK=1
@@ -768,6 +768,7 @@ extern "C" void ptd_pt_destroy(ptd_pt* h) {
         cudaFree(h->fr_gbuf[i]); cudaFree(h->fr_rgb[i]);
         if (h->fr_ev_pt[i]) cudaEventDestroy(h->fr_ev_pt[i]);
         if (h->fr_ev_done[i]) cudaEventDestroy(h->fr_ev_done[i]);
+        if (h->fr_ev_rcopy[i]) cudaEventDestroy(h->fr_ev_rcopy[i]);
         if (h->fr_ev_gcopy[i]) cudaEventDestroy(h->fr_ev_gcopy[i]);
     }
     for (cudaEvent_t e : h->events) cudaEventDestroy(e);
@@ -1167,6 +1168,7 @@ static ptd_status frame_ring_init(ptd_pt* h) {
         CUDA_TRY(cudaEventCreateWithFlags(&h->fr_ev_pt[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->fr_ev_done[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&h->fr_ev_gcopy[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->fr_ev_rcopy[i], cudaEventDisableTiming));
     }
     CUDA_TRY(cudaDeviceSynchronize());                                  // the memsets ran on the legacy stream
     return PTD_OK;
@@ -1209,8 +1211,13 @@ extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* 
     if (two_streams) CUDA_TRY(cudaStreamWaitEvent(s_dn, h->fr_ev_pt[i], 0));
     rc = ptd_dn_forward(dn, h->fr_gbuf[i], h->fr_rgb[i], reset_hidden, s_dn);
     if (rc != PTD_OK) { cudaStreamSynchronize(s_pt); cudaStreamSynchronize(s_dn); return rc; }
-    if (rgb_host) CUDA_TRY(cudaMemcpy2DAsync(rgb_host + row_off, plane, h->fr_rgb[i] + row_off, plane, row_bytes, 3, cudaMemcpyDeviceToHost, s_dn));
     CUDA_TRY(cudaEventRecord(h->fr_ev_done[i], s_dn));
+    h->fr_has_rcopy[i] = rgb_host != nullptr;
+    if (rgb_host) {                                                     // on the copy stream: the denoiser stream goes straight on to the next frame
+        CUDA_TRY(cudaStreamWaitEvent(s_cp, h->fr_ev_done[i], 0));
+        CUDA_TRY(cudaMemcpy2DAsync(rgb_host + row_off, plane, h->fr_rgb[i] + row_off, plane, row_bytes, 3, cudaMemcpyDeviceToHost, s_cp));
+        CUDA_TRY(cudaEventRecord(h->fr_ev_rcopy[i], s_cp));
+    }
     h->fr_last_dn = s_dn;
     h->fr_submitted += 1;
     return PTD_OK;
@@ -1223,6 +1230,7 @@ extern "C" ptd_status ptd_frame_wait(ptd_pt* h) {
     h->fr_waited += 1;                                                  // whatever happens below, this frame is no longer in flight
     CUDA_TRY(cudaEventSynchronize(h->fr_ev_done[i]));
     if (h->fr_has_gcopy[i]) CUDA_TRY(cudaEventSynchronize(h->fr_ev_gcopy[i]));
+    if (h->fr_has_rcopy[i]) CUDA_TRY(cudaEventSynchronize(h->fr_ev_rcopy[i]));
     return PTD_OK;
 }
 // Device time of a run of submitted frames: op 0 arms the timer (the next ptd_frame_submit records the start event on the path-trace
