@@ -370,6 +370,7 @@ struct ptd_dn {
     uint32_t epoch = 0;
     uint32_t* d_pack_done = nullptr;
     int parity = 0;
+    int inflight = 0;                                      // frames enqueued by ptd_frame_submit and not yet taken by ptd_frame_wait (they own this handle's state)
     int launches = 0;
     bool profiling = false;
     std::vector<cudaEvent_t> events;          // events[i], events[i+1] bracket launch i
@@ -791,8 +792,16 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
     return PTD_OK;
 }
 
+// While frames submitted with ptd_frame_submit are in flight they own the recurrent state, the parity and the arena on streams of their
+// own; any other entry point would race with them, so it reports PTD_ERR_STATE instead.
+#define DN_NOT_INFLIGHT(h, what) do { if ((h)->inflight > 0) PTD_FAIL(PTD_ERR_STATE, what ": %d frame(s) submitted with ptd_frame_submit are still in flight - call ptd_frame_wait first", (h)->inflight); } while (0)
+ptd_status ptd_dn_forward_frame(ptd_dn* h, const float* gbuf, float* rgb, int reset_hidden, void* stream) {       // ptd_frame_* only (ptd_pt.cu)
+    return dn_run(h, gbuf, rgb, reset_hidden, (cudaStream_t)stream, -1, (int)h->layers.size() + 1);
+}
+void ptd_dn_mark_inflight(ptd_dn* h, int delta) { h->inflight += delta; if (h->inflight < 0) h->inflight = 0; }
 extern "C" ptd_status ptd_dn_forward(ptd_dn* h, const float* gbuf, float* rgb, int reset_hidden, void* stream_) {
     if (!h || !gbuf || !rgb) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_forward: null argument");
+    DN_NOT_INFLIGHT(h, "ptd_dn_forward");
     return dn_run(h, gbuf, rgb, reset_hidden, (cudaStream_t)stream_, -1, (int)h->layers.size() + 1);
 }
 
@@ -812,6 +821,7 @@ extern "C" ptd_status ptd_dn_forward_group(ptd_dn** hs, int n, const float* cons
 extern "C" ptd_status ptd_dn_forward_host(ptd_dn* h, const float* gbuf_host, float* rgb_host, int reset_hidden) {
     if (!h || !gbuf_host || !rgb_host) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_forward_host: null argument");
     if (h->strip) PTD_FAIL(PTD_ERR_UNSUPPORTED, "ptd_dn_forward_host: a row-strip handle takes device pointers (ptd_dn_forward)");
+    DN_NOT_INFLIGHT(h, "ptd_dn_forward_host");
     CUDA_TRY(cudaSetDevice(h->device));
     const size_t P = (size_t)h->H * h->W;
     CUDA_TRY(cudaMemcpy(h->d_gbuf, gbuf_host, P * 40, cudaMemcpyHostToDevice));          // main.cpp:104-105
@@ -834,7 +844,9 @@ extern "C" ptd_status ptd_dn_padded_size(const ptd_dn* h, int* Hp, int* Wp) {
 
 extern "C" ptd_status ptd_dn_dump_hidden(ptd_dn* h, int level, float* host, size_t cap, int* C, int* H, int* W) {
     if (!h || !host || level < 0 || level > 5) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_dump_hidden: bad argument");
+    DN_NOT_INFLIGHT(h, "ptd_dn_dump_hidden");
     CUDA_TRY(cudaSetDevice(h->device));
+    CUDA_TRY(cudaDeviceSynchronize());                                  // the last forward may have run on a non-blocking stream
     const DnTensor& t = h->tensors[h->t_hidden[level][h->parity]];       // the state the NEXT forward will read
     const int c = h->hidden_c[level], hh = t.rows, ww = t.W;
     const size_t n = (size_t)c * hh * ww;

@@ -95,6 +95,9 @@ void ptd_geom_bounds(const std::vector<ptd_geom>& geoms, std::vector<ptd_aabb>& 
 
 // what ptd_frame_host (ptd_pt.cu) needs to know about a denoiser handle (ptd_dn.cu)
 void ptd_dn_describe(const ptd_dn* h, int* device, int* H, int* W, int* strip);
+// ptd_frame_submit / ptd_frame_wait (ptd_pt.cu) drive the denoiser through these: the frames in flight own the handle's state
+ptd_status ptd_dn_forward_frame(ptd_dn* h, const float* gbuf, float* rgb, int reset_hidden, void* stream);
+void ptd_dn_mark_inflight(ptd_dn* h, int delta);
 
 // camera helpers shared with the CLI
 void ptd_camera_derive(ptd_camera& cam, float fovy_deg);

@@ -738,6 +738,7 @@ struct ptd_pt {
     cudaEvent_t fr_ev_pt[2] = {nullptr, nullptr}, fr_ev_done[2] = {nullptr, nullptr}, fr_ev_gcopy[2] = {nullptr, nullptr}, fr_ev_rcopy[2] = {nullptr, nullptr};
     bool fr_has_gcopy[2] = {false, false}, fr_has_rcopy[2] = {false, false};
     long long fr_submitted = 0, fr_waited = 0;
+    ptd_dn* fr_dn[2] = {nullptr, nullptr};                   // the denoiser handle of the frame in each slot (its in-flight count is ours to drop)
     cudaEvent_t fr_ev_t0 = nullptr, fr_ev_t1 = nullptr; bool fr_timer_armed = false; cudaStream_t fr_last_dn = nullptr;   // ptd_frame_timer
     bool wide_lookback = false;                              // PTD_PT_WIDE_LOOKBACK=1
     bool smem_stack = false;                                 // PTD_PT_SMEM_STACK=1
@@ -1010,8 +1011,10 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
     return PTD_OK;
 }
 
+#define PT_NOT_INFLIGHT(h, what) do { if ((h)->fr_waited < (h)->fr_submitted) PTD_FAIL(PTD_ERR_STATE, what ": frame(s) submitted with ptd_frame_submit are still in flight - call ptd_frame_wait first"); } while (0)
 extern "C" ptd_status ptd_pt_render(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf, void* stream_) {
     if (!h || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_render: bad argument");
+    PT_NOT_INFLIGHT(h, "ptd_pt_render");
     return pt_run(h, cam, iter, gbuf, (cudaStream_t)stream_, 0, h->depth);
 }
 
@@ -1209,7 +1212,7 @@ extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* 
         CUDA_TRY(cudaEventRecord(h->fr_ev_gcopy[i], s_cp));
     }
     if (two_streams) CUDA_TRY(cudaStreamWaitEvent(s_dn, h->fr_ev_pt[i], 0));
-    rc = ptd_dn_forward(dn, h->fr_gbuf[i], h->fr_rgb[i], reset_hidden, s_dn);
+    rc = ptd_dn_forward_frame(dn, h->fr_gbuf[i], h->fr_rgb[i], reset_hidden, (void*)s_dn);
     if (rc != PTD_OK) { cudaStreamSynchronize(s_pt); cudaStreamSynchronize(s_dn); return rc; }
     CUDA_TRY(cudaEventRecord(h->fr_ev_done[i], s_dn));
     h->fr_has_rcopy[i] = rgb_host != nullptr;
@@ -1219,6 +1222,8 @@ extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* 
         CUDA_TRY(cudaEventRecord(h->fr_ev_rcopy[i], s_cp));
     }
     h->fr_last_dn = s_dn;
+    h->fr_dn[i] = dn;
+    ptd_dn_mark_inflight(dn, +1);
     h->fr_submitted += 1;
     return PTD_OK;
 }
@@ -1228,6 +1233,7 @@ extern "C" ptd_status ptd_frame_wait(ptd_pt* h) {
     CUDA_TRY(cudaSetDevice(h->device));
     const int i = h->fr_waited & 1;
     h->fr_waited += 1;                                                  // whatever happens below, this frame is no longer in flight
+    if (h->fr_dn[i]) { ptd_dn_mark_inflight(h->fr_dn[i], -1); h->fr_dn[i] = nullptr; }
     CUDA_TRY(cudaEventSynchronize(h->fr_ev_done[i]));
     if (h->fr_has_gcopy[i]) CUDA_TRY(cudaEventSynchronize(h->fr_ev_gcopy[i]));
     if (h->fr_has_rcopy[i]) CUDA_TRY(cudaEventSynchronize(h->fr_ev_rcopy[i]));
@@ -1262,6 +1268,8 @@ extern "C" ptd_status ptd_pt_export_rgba8(ptd_pt* h, int iter, unsigned char* pb
 extern "C" ptd_status ptd_pt_live_counts(ptd_pt* h, int* counts, int capacity, int* bounces_run) {
     if (!h || !counts || capacity < h->depth) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_live_counts: need capacity >= trace depth %d", h ? h->depth : 0);
     CUDA_TRY(cudaSetDevice(h->device));
+    PT_NOT_INFLIGHT(h, "ptd_pt_live_counts");
+    CUDA_TRY(cudaDeviceSynchronize());                                  // the last render may have run on a non-blocking stream
     std::vector<int> c(h->depth + 1);
     CUDA_TRY(cudaMemcpy(c.data(), h->d_counts, sizeof(int) * (h->depth + 1), cudaMemcpyDeviceToHost));
     c[0] = h->P;
@@ -1280,6 +1288,8 @@ extern "C" ptd_status ptd_pt_dump_paths(ptd_pt* h, int bounce, ptd_path_segment*
     if (!h || !host || !n) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_dump_paths: null argument");
     if (!h->d_trace_paths) PTD_FAIL(PTD_ERR_STATE, "ptd_pt_dump_paths: handle was created without PTD_PT_TRACE");
     CUDA_TRY(cudaSetDevice(h->device));
+    PT_NOT_INFLIGHT(h, "ptd_pt_dump_paths");
+    CUDA_TRY(cudaDeviceSynchronize());                                  // the last render may have run on a non-blocking stream
     ptd_status rc = bounce_count(h, bounce, n);
     if (rc != PTD_OK) return rc;
     if (*n > capacity) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_dump_paths: capacity %d < %d", capacity, *n);
@@ -1290,6 +1300,8 @@ extern "C" ptd_status ptd_pt_dump_intersections(ptd_pt* h, int bounce, ptd_inter
     if (!h || !host || !n) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_dump_intersections: null argument");
     if (!h->d_trace_isx) PTD_FAIL(PTD_ERR_STATE, "ptd_pt_dump_intersections: handle was created without PTD_PT_TRACE");
     CUDA_TRY(cudaSetDevice(h->device));
+    PT_NOT_INFLIGHT(h, "ptd_pt_dump_intersections");
+    CUDA_TRY(cudaDeviceSynchronize());                                  // the last render may have run on a non-blocking stream
     ptd_status rc = bounce_count(h, bounce, n);
     if (rc != PTD_OK) return rc;
     if (*n > capacity) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_dump_intersections: capacity %d < %d", capacity, *n);
@@ -1300,12 +1312,16 @@ extern "C" ptd_status ptd_pt_dump_final_paths(ptd_pt* h, ptd_path_segment* host,
     if (!h || !host || capacity < h->P) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_dump_final_paths: bad argument");
     if (!h->d_dead) PTD_FAIL(PTD_ERR_STATE, "ptd_pt_dump_final_paths: handle was created without PTD_PT_KEEP_TERMINATED");
     CUDA_TRY(cudaSetDevice(h->device));
+    PT_NOT_INFLIGHT(h, "ptd_pt_dump_final_paths");
+    CUDA_TRY(cudaDeviceSynchronize());                                  // the last render may have run on a non-blocking stream
     CUDA_TRY(cudaMemcpy(host, h->d_dead, sizeof(ptd_path_segment) * (size_t)h->P, cudaMemcpyDeviceToHost));
     return PTD_OK;
 }
 extern "C" ptd_status ptd_pt_dump_image(ptd_pt* h, float* host_rgb) {
     if (!h || !host_rgb) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_dump_image: null argument");
     CUDA_TRY(cudaSetDevice(h->device));
+    PT_NOT_INFLIGHT(h, "ptd_pt_dump_image");
+    CUDA_TRY(cudaDeviceSynchronize());                                  // the last render may have run on a non-blocking stream
     CUDA_TRY(cudaMemcpy(host_rgb, h->d_image, sizeof(float) * 3 * (size_t)h->P, cudaMemcpyDeviceToHost));
     return PTD_OK;
 }

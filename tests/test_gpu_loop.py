@@ -85,6 +85,13 @@ def test_frame_submit_wait_equals_the_two_host_calls(tmp_path, mode):
     rgb = [np.zeros((3, 96, 160), np.float32) for _ in range(n)]
     gb = [np.zeros((10, 96, 160), np.float32) if k % 3 != 2 else None for k in range(n)]
     pt_b.frame_submit(dn_b, rgb[0], gb[0], cam=cams[0], reset=True)
+    # while a frame is in flight it owns both handles' state: every other entry point reports that instead of racing with it
+    with pytest.raises(capi.PtdError, match="in flight"):
+        dn_b.forward_host(ref[0][0], reset=False)
+    with pytest.raises(capi.PtdError, match="in flight"):
+        pt_b.live_counts()
+    with pytest.raises(capi.PtdError, match="in flight"):
+        dn_b.dump_hidden(0)
     for k in range(1, n):
         pt_b.frame_submit(dn_b, rgb[k], gb[k], cam=cams[k])
         if k == 1:
