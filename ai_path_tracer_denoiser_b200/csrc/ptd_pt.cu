@@ -357,19 +357,78 @@ __device__ __forceinline__ void st_status(unsigned long long* p, unsigned long l
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-// ---- kernel 2 of a bounce: shadeMaterial (:333-390) + thrust::partition (:505) + finalGather / copy_data for the paths that end here
+// ---- -DPTD_SHADE_PROF: per-phase globaltimer sums of the shade kernels (tools/shade_prof.py), compiled out of the product ----------------
+#ifdef PTD_SHADE_PROF
+__device__ unsigned long long g_shade_prof[16];
+__device__ __forceinline__ unsigned long long prof_now() { unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t; }
+#define SH_PROF_BEGIN() unsigned long long prof_t = prof_now()
+#define SH_PROF(k) do { if (threadIdx.x == 0) { const unsigned long long t_ = prof_now(); atomicAdd(&g_shade_prof[k], t_ - prof_t); prof_t = t_; } } while (0)
+#define SH_PROF_TILE() do { if (threadIdx.x == 0) atomicAdd(&g_shade_prof[15], 1ull); } while (0)
+extern "C" int ptd_debug_shade_prof(unsigned long long* out16, int reset) {
+    if (out16) cudaMemcpyFromSymbol(out16, g_shade_prof, sizeof(unsigned long long) * 16);
+    if (reset) { unsigned long long z[16] = {}; cudaMemcpyToSymbol(g_shade_prof, z, sizeof z); }
+    return 0;
+}
+#else
+#define SH_PROF_BEGIN() do {} while (0)
+#define SH_PROF(k) do {} while (0)
+#define SH_PROF_TILE() do {} while (0)
+#endif
+
+// ---- shadeMaterial (pathtrace.cu:333-390) + finalGather (:393-402) + copy_data (:81-94) for ONE path ---------------------------------
+// `seed_index` is the path's index in the frame-wide compacted array (what the reference seeds its RNG with, :351).  Returns whether the
+// path lives on; a path that ends here adds its throughput to the accumulation image and emits the radiance planes - every segment
+// terminates exactly once per iteration, so the two extra passes over P the reference makes are not needed.
+template <bool FIRST>
+__device__ __forceinline__ bool shade_path(const PtKernelParams& p, int seed_index, float isx_t, v3 isx_n, int isx_mat, v3 ip,
+                                           Ray& ray, v3& color, int pixelIndex, int& rb) {
+    const bool hit = isx_t >= 0;
+    const int col = pixelIndex % p.W, row = pixelIndex / p.W;
+    const size_t mirrored = (size_t)(p.W - col - 1) + (size_t)row * p.W;              // x-mirror of copy_data / :297-299
+    if (isx_t > 0.0f) {
+        Rng rng = make_rng(p.iter, seed_index, rb);
+        const ptd_material m = p.materials[isx_mat];
+        if (m.emittance > 0.0f) {
+            rb = 0;
+            color = muls(mulv(color, m.color), m.emittance);
+        } else {
+            scatterRay(ray, color, ip, isx_n, m, rng);
+            --rb;
+        }
+    } else {
+        color = V(0, 0, 0);
+        rb = 0;
+    }
+    if (FIRST && p.iter == 1) {                                                         // :379-387
+        p.gbuf[(size_t)p.Pfull * 7 + mirrored] = hit ? color.x : 0.f;
+        p.gbuf[(size_t)p.Pfull * 8 + mirrored] = hit ? color.y : 0.f;
+        p.gbuf[(size_t)p.Pfull * 9 + mirrored] = hit ? color.z : 0.f;
+    }
+    if (rb > 0) return true;
+    float* img = p.image + (size_t)(pixelIndex - p.pix0) * 3;
+    v3 acc = add(p.iter != 1 ? V(img[0], img[1], img[2]) : V(0.f, 0.f, 0.f), color);
+    img[0] = acc.x; img[1] = acc.y; img[2] = acc.z;
+    const float fi = (float)p.iter;
+    p.gbuf[mirrored] = __fdiv_rn(acc.x, fi);
+    p.gbuf[(size_t)p.Pfull + mirrored] = __fdiv_rn(acc.y, fi);
+    p.gbuf[(size_t)p.Pfull * 2 + mirrored] = __fdiv_rn(acc.z, fi);
+    return false;
+}
+
+// ---- kernel 2 of a bounce, one tile per block (PTD_PT_SHADE_TILED=1; round 1's kernel, kept for A/B): shadeMaterial (:333-390) + thrust::partition (:505) + finalGather / copy_data for the paths that end here
 // WIDE (PTD_PT_WIDE_LOOKBACK=1, opt-in): the decoupled look-back reads PT_BLOCK predecessor states per trip with the whole block
 // instead of 32 with one warp.  With ~300 tiles in flight the one-warp walk is ~10 dependent L2 round trips per tile while the other
 // 15 warps sit at the barrier (ncu: stall_barrier dominates pt_shade); one block-wide trip covers every tile in flight.
 // KEYS (PTD_PT_RAY_SORT, next bounce binned): every survivor's bin key is written at its compacted index and counted into the next
 // bounce's histogram here, where the new ray is still in registers - the separate ray_bin_hist pass (a 40 MB re-read) is not needed.
 template <bool FIRST, bool WIDE = false, bool KEYS = false>
-__global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
+__global__ void __launch_bounds__(PT_BLOCK) pt_shade_tiled(const PtKernelParams p) {
     __shared__ __align__(16) uint32_t s_words[PT_BLOCK * PT_WORDS];                  // 5632 B staging (loads, then compacted stores)
     __shared__ __align__(16) uint32_t s_isx[PT_BLOCK * 9];                           // 4608 B: the tile's ShadeableIntersections
     __shared__ int s_tile, s_warp_kept[PT_BLOCK / 32], s_excl, s_goff;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    SH_PROF_BEGIN();
     const int n = FIRST ? p.P : p.counts[p.bounce];
     if (tid == 0) s_tile = atomicAdd(p.ticket2, 1);                      // dynamic tile id: look-back predecessors are always scheduled
     __syncthreads();
@@ -402,6 +461,7 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
         }
         s_goff = goff;                                                    // read after the next __syncthreads
     }
+    SH_PROF(0);                                                            // ticket + mail
     const int valid = min(PT_BLOCK, n - base);
     const int idx = base + tid;
     const bool active = tid < valid;
@@ -449,6 +509,7 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
         isx_t = w[0]; isx_n = V(w[1], w[2], w[3]); isx_mat = __float_as_int(w[4]); ip = V(w[6], w[7], w[8]);
     }
     __syncthreads();                                                       // staging buffer is reused for the stores below
+    SH_PROF(1);                                                            // loads
     if (p.trace_paths && active) {
         ptd_path_segment ps;
         ps.ray.origin = ray.o; ps.ray.direction = ray.d; ps.color = color; ps.pixelIndex = pixelIndex; ps.remainingBounces = rb;
@@ -457,49 +518,17 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
 
     bool keep = false;
     if (active) {
-        const bool hit = isx_t >= 0;
         if (p.sort_keys) p.sort_keys[idx] = isx_mat;                                   // key of the UN-compacted slot (:509 quirk)
-        const int col = pixelIndex % p.W, row = pixelIndex / p.W;
-        const size_t mirrored = (size_t)(p.W - col - 1) + (size_t)row * p.W;          // x-mirror of copy_data / :297-299
-        // ---- 2. shade (shadeMaterial, pathtrace.cu:333-390) -------------------------------------------------
-        if (isx_t > 0.0f) {
-            Rng rng = make_rng(p.iter, s_goff + idx, rb);                           // frame-wide compacted index
-            const ptd_material m = p.materials[isx_mat];
-            if (m.emittance > 0.0f) {
-                rb = 0;
-                color = muls(mulv(color, m.color), m.emittance);
-            } else {
-                scatterRay(ray, color, ip, isx_n, m, rng);
-                --rb;
-            }
-        } else {
-            color = V(0, 0, 0);
-            rb = 0;
-        }
-        if (FIRST && p.iter == 1) {                                                     // :379-387
-            p.gbuf[(size_t)p.Pfull * 7 + mirrored] = hit ? color.x : 0.f;
-            p.gbuf[(size_t)p.Pfull * 8 + mirrored] = hit ? color.y : 0.f;
-            p.gbuf[(size_t)p.Pfull * 9 + mirrored] = hit ? color.z : 0.f;
-        }
-        keep = rb > 0;
-        if (!keep) {
-            // finalGather (:393-402) + copy_data (:81-94): every segment terminates exactly once per iteration, so its
-            // throughput is accumulated and the radiance planes are emitted here instead of in two extra passes over P.
-            float* img = p.image + (size_t)(pixelIndex - p.pix0) * 3;
-            v3 acc = add(p.iter != 1 ? V(img[0], img[1], img[2]) : V(0.f, 0.f, 0.f), color);
-            img[0] = acc.x; img[1] = acc.y; img[2] = acc.z;
-            const float fi = (float)p.iter;
-            p.gbuf[mirrored] = __fdiv_rn(acc.x, fi);
-            p.gbuf[(size_t)p.Pfull + mirrored] = __fdiv_rn(acc.y, fi);
-            p.gbuf[(size_t)p.Pfull * 2 + mirrored] = __fdiv_rn(acc.z, fi);
-        }
+        keep = shade_path<FIRST>(p, s_goff + idx, isx_t, isx_n, isx_mat, ip, ray, color, pixelIndex, rb);
     }
 
+    SH_PROF(2);                                                            // shade
     // ---- 3. stable stream compaction (thrust::partition, :505) -----------------------------------------------
     const unsigned ballot = __ballot_sync(0xffffffffu, keep);
     const int lane_rank = __popc(ballot & ((1u << lane) - 1u));
     if (lane == 0) s_warp_kept[warp] = __popc(ballot);
     __syncthreads();
+    SH_PROF(3);                                                            // the block's slowest warp
     int warp_off = 0, block_kept = 0;
 #pragma unroll
     for (int w = 0; w < PT_BLOCK / 32; ++w) { if (w < warp) warp_off += s_warp_kept[w]; block_kept += s_warp_kept[w]; }
@@ -592,6 +621,7 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
         w[6] = color.x; w[7] = color.y; w[8] = color.z; w[9] = __int_as_float(pixelIndex); w[10] = __int_as_float(rb);
     }
     __syncthreads();
+    SH_PROF(4);                                                            // look-back
     const int excl = s_excl;
     {
         uint32_t* dst = reinterpret_cast<uint32_t*>(p.dst) + (size_t)excl * PT_WORDS;
@@ -611,6 +641,273 @@ __global__ void __launch_bounds__(PT_BLOCK) pt_shade(const PtKernelParams p) {
         ps.ray.origin = ray.o; ps.ray.direction = ray.d; ps.color = color; ps.pixelIndex = pixelIndex; ps.remainingBounces = rb;
         p.dead[(size_t)(n - 1 - rej_before)] = ps;
     }
+    SH_PROF(5);                                                            // stores issued
+    SH_PROF_TILE();
+}
+
+// ---- kernel 2 of a bounce, pipelined (the default) ---------------------------------------------------------------------------------
+// Same work, same results, same status / count / mail protocol as pt_shade_tiled, organised as a software pipeline.  Per-tile phase times
+// of the tiled kernel (globaltimer stamps, C3, profiles/r4b_shade_phases.json): 3.6 us waiting for the tile's loads, 1.6 us of shading, 4.2 us
+// in the decoupled look-back, 0.6 us of stores - the block does one of these at a time.  Here a persistent block (2 per SM) keeps three
+// tiles in flight:
+//   * tile k + 1 is fetched by two bulk copies (cp.async.bulk, one mbarrier per buffer) issued before tile k is touched;
+//   * tile k is shaded by 16 warps, its survivors are staged compacted in shared memory and its aggregate is published at once;
+//   * the look-back of tile k runs on a 17th warp while the 16 shade tile k + 1; tile k's survivors are stored when its exclusive prefix
+//     arrives, one iteration later.
+// Buffers: 2 x ShadeableIntersection tile (18 KB), 3 x PathSegment tile (22 KB: being filled / being shaded and staged / waiting for its
+// prefix) = 102 KB per block.  Tile ids are still taken from the bounce's ticket in the order blocks ask for them and every block works
+// through its tiles in increasing order, publishing a tile's aggregate before it waits for anything, so the lowest unpublished tile is
+// always being shaded by a resident block: the look-back cannot deadlock.
+// When the frame-wide index of a dropped path is needed at once (PT_KEEP_TERMINATED's reject array, the ray-sort keys) the block waits for
+// the prefix of the tile it has just shaded instead (`defer` = false); everything else is the same code.
+constexpr int SH_THREADS = PT_BLOCK + 32;
+constexpr int SH_ISX_WORDS = PT_BLOCK * 9, SH_PATH_WORDS = PT_BLOCK * PT_WORDS;
+constexpr int SH_SMEM_BYTES = (3 * SH_PATH_WORDS + 2 * SH_ISX_WORDS) * 4;
+
+__device__ __forceinline__ uint32_t sh_smem(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void sh_mbar_init(uint64_t* b, unsigned count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(sh_smem(b)), "r"(count) : "memory"); }
+__device__ __forceinline__ void sh_mbar_arrive(uint64_t* b) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(sh_smem(b)) : "memory"); }
+__device__ __forceinline__ void sh_mbar_expect(uint64_t* b, unsigned bytes) { asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(sh_smem(b)), "r"(bytes) : "memory"); }
+__device__ __forceinline__ void sh_mbar_wait(uint64_t* b, unsigned parity) {
+    PtdSpinGuard guard;                                                    // traps instead of hanging the GPU
+    for (;;) {
+        unsigned ok;
+        asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}" : "=r"(ok) : "r"(sh_smem(b)), "r"(parity) : "memory");
+        if (ok) return;
+        guard.tick();
+    }
+}
+__device__ __forceinline__ void sh_bulk_load(void* dst, const void* src, unsigned bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sh_smem(dst)), "l"(src), "r"(bytes), "r"(sh_smem(bar)) : "memory");
+}
+__device__ __forceinline__ void sh_bar_shaders() { asm volatile("bar.sync 1, %0;" ::"n"(PT_BLOCK) : "memory"); }   // the 16 shading warps only
+
+template <bool FIRST, bool KEYS = false>
+__global__ void __launch_bounds__(SH_THREADS, 2) pt_shade(const PtKernelParams p) {
+    extern __shared__ __align__(128) uint32_t sh_dyn[];
+    uint32_t* const s_path_buf = sh_dyn;                                   // [3][SH_PATH_WORDS]
+    uint32_t* const s_isx_buf = sh_dyn + 3 * SH_PATH_WORDS;                // [2][SH_ISX_WORDS]
+    __shared__ __align__(8) uint64_t bar_full[2], bar_req[2], bar_done[2];
+    __shared__ int s_next, s_goff, s_warp_kept[PT_BLOCK / 32], s_req_tile[2], s_req_agg[2], s_excl[2];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int n = FIRST ? p.P : p.counts[p.bounce];
+    const bool defer = !(KEYS || p.dead != nullptr);
+    const uint32_t* const g_isx = reinterpret_cast<const uint32_t*>(p.isx);
+    const uint32_t* const g_src = reinterpret_cast<const uint32_t*>(p.src);
+    // a full tile whose two source ranges are 16-byte aligned comes by bulk copy; the last (partial) tile of a bounce is loaded by the block
+    const bool aligned = (reinterpret_cast<uintptr_t>(g_isx) & 15) == 0 && (FIRST || (reinterpret_cast<uintptr_t>(g_src) & 15) == 0);
+    auto bulk_tile = [&](int tile) { return aligned && (tile + 1) * PT_BLOCK <= n; };
+    auto fetch = [&](int tile, int slot2, int slot3) {                     // one thread
+        sh_mbar_expect(&bar_full[slot2], (SH_ISX_WORDS + (FIRST ? 0 : SH_PATH_WORDS)) * 4);
+        sh_bulk_load(s_isx_buf + slot2 * SH_ISX_WORDS, g_isx + (size_t)tile * SH_ISX_WORDS, SH_ISX_WORDS * 4, &bar_full[slot2]);
+        if (!FIRST) sh_bulk_load(s_path_buf + slot3 * SH_PATH_WORDS, g_src + (size_t)tile * SH_PATH_WORDS, SH_PATH_WORDS * 4, &bar_full[slot2]);
+    };
+
+    if (tid == 0) {
+        for (int i = 0; i < 2; ++i) { sh_mbar_init(&bar_full[i], 1); sh_mbar_init(&bar_req[i], 1); sh_mbar_init(&bar_done[i], 1); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        const int t0 = atomicAdd(p.ticket2, 1);                            // dynamic tile ids: look-back predecessors are always scheduled
+        s_next = t0;
+        if (bulk_tile(t0)) fetch(t0, 0, 0);
+        if (n == 0 && t0 == 0) {                                           // nothing alive here: still tell the strips below
+            const unsigned long long m = (unsigned long long)p.epoch << 32;
+            for (int r = p.rank + 1; r < p.nranks; ++r)
+                if (p.peer_mail[r]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_mail[r] + (size_t)(p.bounce + 1) * PT_MAX_RANKS + p.rank), "l"(m) : "memory");
+        }
+        // Row-strip mode: the reference seeds its RNG with the index in the frame-wide compacted array (pathtrace.cu:351).  Strips are
+        // contiguous pixel ranges and compaction is stable, so that index is (live paths of the strips above) + local index; the strips
+        // above published their live counts of this bounce into our mailbox (peer stores) when they compacted.
+        int goff = FIRST ? p.pix0 : 0;
+        if (!FIRST && (t0 * PT_BLOCK < n)) {
+            PtdSpinGuard guard;
+            for (int r = 0; r < p.rank; ++r) {
+                unsigned long long m;
+                for (;;) {
+                    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(m) : "l"(p.mail + (size_t)p.bounce * PT_MAX_RANKS + r) : "memory");
+                    if ((unsigned)(m >> 32) == p.epoch) break;
+                    guard.tick();
+                }
+                goff += (int)(unsigned)m;
+            }
+        }
+        s_goff = goff;
+    }
+    __syncthreads();
+
+    if (warp == PT_BLOCK / 32) {
+        // ---- the look-back warp: one request per tile of this block, in order; (tile < 0) ends it --------------------------------------
+        for (int q = 0;; ++q) {
+            const int slot = q & 1;
+            sh_mbar_wait(&bar_req[slot], (q >> 1) & 1);
+            const int tile = s_req_tile[slot], agg = s_req_agg[slot];
+            if (tile < 0) break;
+            // decoupled look-back, one warp wide: state 1 = tile aggregate, 2 = inclusive prefix (value in the low 32 bits); each trip reads
+            // 32 predecessors' states at once
+            int excl = 0;
+            if (tile > 0) {
+                PtdSpinGuard guard;
+                int j = tile - 1;                                          // nearest predecessor of this window
+                for (;;) {
+                    const int t = j - lane;
+                    const unsigned long long sv = t >= 0 ? ld_status(&p.status[t]) : (2ull << 32);   // before tile 0: prefix 0
+                    const unsigned st = (unsigned)(sv >> 32);
+                    const unsigned has_prefix = __ballot_sync(0xffffffffu, st == 2u);
+                    const unsigned not_ready = __ballot_sync(0xffffffffu, st == 0u);
+                    const int first_prefix = has_prefix ? __ffs(has_prefix) - 1 : 31;
+                    const unsigned needed = first_prefix == 31 ? 0xffffffffu : ((2u << first_prefix) - 1u);   // lanes 0 .. first_prefix
+                    if (not_ready & needed) { guard.tick(); continue; }    // a predecessor has not published yet: look again
+                    int v = lane <= first_prefix ? (int)(unsigned)sv : 0;
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+                    excl += v;
+                    if (has_prefix) break;
+                    j -= 32;
+                }
+                if (lane == 0) st_status(&p.status[tile], (2ull << 32) | (unsigned)(excl + agg));
+            }
+            if (lane == 0) {
+                if ((tile + 1) * PT_BLOCK >= n) {                          // last tile publishes the live count ...
+                    p.counts[p.bounce + 1] = excl + agg;
+                    const unsigned long long m = ((unsigned long long)p.epoch << 32) | (unsigned)(excl + agg);
+                    for (int r = p.rank + 1; r < p.nranks; ++r)            // ... and mails it to the strips below (NVLink peer stores)
+                        if (p.peer_mail[r]) asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p.peer_mail[r] + (size_t)(p.bounce + 1) * PT_MAX_RANKS + p.rank), "l"(m) : "memory");
+                }
+                s_excl[slot] = excl;
+                sh_mbar_arrive(&bar_done[slot]);
+            }
+            __syncwarp();
+        }
+        return;
+    }
+
+    // ---- the 16 shading warps -----------------------------------------------------------------------------------------------------------
+    auto store_tile = [&](const uint32_t* words, int kept, int excl) {     // contiguous, 128 B per warp store
+        uint32_t* dst = reinterpret_cast<uint32_t*>(p.dst) + (size_t)excl * PT_WORDS;
+        const int nwords = kept * PT_WORDS;
+        for (int i = tid; i < nwords; i += PT_BLOCK) dst[i] = words[i];
+    };
+    int cur = s_next, k = 0, prev_kept = 0;
+    SH_PROF_BEGIN();
+    for (;; ++k) {
+        const int base = cur * PT_BLOCK;
+        if (base >= n) break;
+        const int valid = min(PT_BLOCK, n - base);
+        const int idx = base + tid;
+        const bool active = tid < valid;
+        const int i2 = k & 1, i3 = k % 3;
+        uint32_t* const s_isx = s_isx_buf + i2 * SH_ISX_WORDS;
+        uint32_t* const s_words = s_path_buf + i3 * SH_PATH_WORDS;
+
+        // ---- A. next tile id; its data starts to move now --------------------------------------------------------------------------
+        if (tid == 0) {
+            const int nx = atomicAdd(p.ticket2, 1);
+            s_next = nx;
+            if (bulk_tile(nx)) fetch(nx, i2 ^ 1, (k + 1) % 3);
+        }
+        SH_PROF(0);                                                        // ticket + prefetch issue (+ the previous iteration's closing barrier)
+        // ---- B. this tile's path segments and intersections ------------------------------------------------------------------------
+        if (bulk_tile(cur)) {
+            sh_mbar_wait(&bar_full[i2], (k >> 1) & 1);
+        } else {
+            const uint32_t* a = g_isx + (size_t)base * 9;
+            for (int i = tid; i < valid * 9; i += PT_BLOCK) s_isx[i] = a[i];
+            if (!FIRST) {
+                const uint32_t* b = g_src + (size_t)base * PT_WORDS;
+                for (int i = tid; i < valid * PT_WORDS; i += PT_BLOCK) s_words[i] = b[i];
+            }
+            sh_bar_shaders();
+        }
+        SH_PROF(1);                                                        // wait for the tile's data
+        Ray ray; v3 color; int pixelIndex = 0, rb = 0;
+        ray.o = ray.d = color = V(0, 0, 0);
+        float isx_t = -1.0f; v3 isx_n = V(0, 0, 0), ip = V(0, 0, 0); int isx_mat = 0;
+        if (active) {
+            if (FIRST) {
+                ray = camera_ray(p.cam, p.W, p.iter, p.pix0 + idx);
+                color = V(1.0f, 1.0f, 1.0f);
+                pixelIndex = p.pix0 + idx;
+                rb = p.trace_depth;
+            } else {
+                const float* w = reinterpret_cast<const float*>(s_words) + tid * PT_WORDS;   // stride 11 words: conflict free
+                ray.o = V(w[0], w[1], w[2]); ray.d = V(w[3], w[4], w[5]); color = V(w[6], w[7], w[8]);
+                pixelIndex = __float_as_int(w[9]); rb = __float_as_int(w[10]);
+            }
+            const float* w = reinterpret_cast<const float*>(s_isx) + tid * 9;                // stride 9 words: conflict free
+            isx_t = w[0]; isx_n = V(w[1], w[2], w[3]); isx_mat = __float_as_int(w[4]); ip = V(w[6], w[7], w[8]);
+        }
+        sh_bar_shaders();                                                  // s_words becomes the staging buffer of this tile's survivors
+        const int nxt = s_next;
+        if (p.trace_paths && active) {
+            ptd_path_segment ps;
+            ps.ray.origin = ray.o; ps.ray.direction = ray.d; ps.color = color; ps.pixelIndex = pixelIndex; ps.remainingBounces = rb;
+            p.trace_paths[(size_t)p.bounce * p.P + idx] = ps;
+        }
+        // ---- C. shade ------------------------------------------------------------------------------------------------------------------
+        bool keep = false;
+        if (active) {
+            if (p.sort_keys) p.sort_keys[idx] = isx_mat;                   // key of the UN-compacted slot (:509 quirk)
+            keep = shade_path<FIRST>(p, s_goff + idx, isx_t, isx_n, isx_mat, ip, ray, color, pixelIndex, rb);
+        }
+        SH_PROF(2);                                                        // registers, barrier, shade
+        // ---- D. stable stream compaction (thrust::partition, :505): ranks inside the tile, aggregate out at once ----------------------
+        const unsigned ballot = __ballot_sync(0xffffffffu, keep);
+        const int lane_rank = __popc(ballot & ((1u << lane) - 1u));
+        if (lane == 0) s_warp_kept[warp] = __popc(ballot);
+        sh_bar_shaders();
+        int warp_off = 0, block_kept = 0;
+#pragma unroll
+        for (int w = 0; w < PT_BLOCK / 32; ++w) { if (w < warp) warp_off += s_warp_kept[w]; block_kept += s_warp_kept[w]; }
+        if (tid == 0) {
+            st_status(&p.status[cur], ((cur == 0 ? 2ull : 1ull) << 32) | (unsigned)block_kept);
+            s_req_tile[i2] = cur; s_req_agg[i2] = block_kept;
+            sh_mbar_arrive(&bar_req[i2]);
+        }
+        const int local_rank = warp_off + lane_rank;
+        if (keep) {
+            float* w = reinterpret_cast<float*>(s_words) + local_rank * PT_WORDS;
+            w[0] = ray.o.x; w[1] = ray.o.y; w[2] = ray.o.z; w[3] = ray.d.x; w[4] = ray.d.y; w[5] = ray.d.z;
+            w[6] = color.x; w[7] = color.y; w[8] = color.z; w[9] = __int_as_float(pixelIndex); w[10] = __int_as_float(rb);
+        }
+        SH_PROF(3);                                                        // slowest warp, scan, publish, stage
+        // ---- E. stores: the tile before this one (its prefix has had a whole iteration to arrive), or this one when it cannot wait -------
+        if (defer) {
+            if (k > 0) {
+                sh_mbar_wait(&bar_done[i2 ^ 1], ((k - 1) >> 1) & 1);
+                SH_PROF(4);                                                // wait for the previous tile's prefix
+                store_tile(s_path_buf + ((k + 2) % 3) * SH_PATH_WORDS, prev_kept, s_excl[i2 ^ 1]);
+            }
+        } else {
+            sh_bar_shaders();                                              // this tile's staging is complete
+            sh_mbar_wait(&bar_done[i2], (k >> 1) & 1);
+            const int excl = s_excl[i2];
+            store_tile(s_words, block_kept, excl);
+            if (KEYS && keep) {
+                const float w6[6] = {ray.o.x, ray.o.y, ray.o.z, ray.d.x, ray.d.y, ray.d.z};
+                const unsigned key = ray_bin(w6, p.bin_box, p.bin_bits);
+                p.bin_keys[excl + local_rank] = key;
+                atomicAdd(&p.bin_hist_next[key], 1);
+            }
+            if (p.dead && active && !keep) {
+                // rejected items end up behind the survivors in REVERSE order (thrust CUDA back end) and are never moved again
+                const int rej_before = base - excl + (tid - local_rank);
+                ptd_path_segment ps;
+                ps.ray.origin = ray.o; ps.ray.direction = ray.d; ps.color = color; ps.pixelIndex = pixelIndex; ps.remainingBounces = rb;
+                p.dead[(size_t)(n - 1 - rej_before)] = ps;
+            }
+        }
+        prev_kept = block_kept;
+        SH_PROF(5);                                                        // stores issued
+        SH_PROF_TILE();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // our reads / writes of the buffers before the next bulk copies into them
+        sh_bar_shaders();
+        cur = nxt;
+    }
+    if (defer && k > 0) {
+        sh_mbar_wait(&bar_done[(k - 1) & 1], ((k - 1) >> 1) & 1);
+        store_tile(s_path_buf + ((k - 1) % 3) * SH_PATH_WORDS, prev_kept, s_excl[(k - 1) & 1]);
+    }
+    if (tid == 0) { s_req_tile[k & 1] = -1; sh_mbar_arrive(&bar_req[k & 1]); }   // ends the look-back warp
 }
 
 // ---- PTD_PT_RAY_SORT: coherent scheduling of the secondary rays ---------------------------------------------------------
@@ -735,12 +1032,17 @@ struct ptd_pt {
     // ptd_frame_submit / ptd_frame_wait: two frame slots, three streams (path trace, denoise + frame copy, G-buffer copy)
     cudaStream_t fr_stream[3] = {nullptr, nullptr, nullptr};
     float* fr_gbuf[2] = {nullptr, nullptr}; float* fr_rgb[2] = {nullptr, nullptr};
+#ifdef PTD_FRAME_SPANS
+    cudaEvent_t sp_ev[2][4] = {};                            // debug build: PT start / end, DN start / end of the slot's frame (timing events)
+#endif
     cudaEvent_t fr_ev_pt[2] = {nullptr, nullptr}, fr_ev_done[2] = {nullptr, nullptr}, fr_ev_gcopy[2] = {nullptr, nullptr}, fr_ev_rcopy[2] = {nullptr, nullptr};
     bool fr_has_gcopy[2] = {false, false}, fr_has_rcopy[2] = {false, false};
     long long fr_submitted = 0, fr_waited = 0;
     ptd_dn* fr_dn[2] = {nullptr, nullptr};                   // the denoiser handle of the frame in each slot (its in-flight count is ours to drop)
     cudaEvent_t fr_ev_t0 = nullptr, fr_ev_t1 = nullptr; bool fr_timer_armed = false; cudaStream_t fr_last_dn = nullptr;   // ptd_frame_timer
-    bool wide_lookback = false;                              // PTD_PT_WIDE_LOOKBACK=1
+    bool wide_lookback = false;                              // PTD_PT_WIDE_LOOKBACK=1 (tiled shade kernel only)
+    bool shade_tiled = false;                                // PTD_PT_SHADE_TILED=1: one tile per block (round 1's kernel) instead of the pipelined one
+    int shade_blocks = 296;                                  // persistent blocks of the pipelined shade kernel (2 per SM)
     bool smem_stack = false;                                 // PTD_PT_SMEM_STACK=1
     // PTD_PT_RAY_SORT
     bool bin_fused = true;
@@ -804,6 +1106,8 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
     if (!(sc->faces.size() > 0) || (flags & PTD_PT_NO_BVH)) flags &= ~(unsigned)PTD_PT_RAY_SORT;      // binning only pays for BVH traversal
     h->device = device; h->flags = flags;
     if (const char* e = getenv("PTD_PT_WIDE_LOOKBACK")) h->wide_lookback = atoi(e) > 0;
+    if (const char* e = getenv("PTD_PT_SHADE_TILED")) h->shade_tiled = atoi(e) > 0;
+    if (h->wide_lookback) h->shade_tiled = true;
     if (const char* e = getenv("PTD_PT_SMEM_STACK")) h->smem_stack = atoi(e) > 0;
     h->cam = sc->camera; h->mesh_box = sc->mesh_box;
     h->W = sc->camera.res_x; h->H = sc->camera.res_y; h->Pfull = h->W * h->H; h->depth = sc->trace_depth;
@@ -892,6 +1196,14 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pt_trace<false>, TR_BLOCK, geom_smem);
         if (const char* e = getenv("PTD_TRACE_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // tuning knob: leave room for a concurrent kernel
         h->trace_blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (h->P + TR_BLOCK - 1) / TR_BLOCK));   // persistent: every resident warp pulls rays
+        CUDA_TRY(cudaFuncSetAttribute(pt_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(pt_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(pt_shade<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_BYTES));
+        CUDA_TRY(cudaFuncSetAttribute(pt_shade<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_BYTES));
+        int sh_per_sm = 2;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sh_per_sm, pt_shade<false>, SH_THREADS, SH_SMEM_BYTES);
+        if (const char* e = getenv("PTD_SHADE_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < sh_per_sm) sh_per_sm = v; }
+        h->shade_blocks = sms * std::max(sh_per_sm, 1);
     }
     CUDA_TRY(cudaDeviceSynchronize());
     *out = h;
@@ -979,18 +1291,28 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
         // the next bounce is binned: this pt_shade also writes its survivors' keys and the next histogram
         const bool keys = bin_fused && (h->flags & PTD_PT_RAY_SORT) && b + 1 >= h->bin_from && b + 1 < h->depth;
         if (keys) { p.bin_box = h->bin_box; p.bin_bits = h->bin_bits; p.bin_keys = h->d_bin_keys; p.bin_hist_next = h->d_bin_hist + (size_t)(b + 1) * h->nbins; }
-        if (keys && h->wide_lookback) {
-            if (b == 0) pt_shade<true, true, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
-            else pt_shade<false, true, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
-        } else if (keys) {
-            if (b == 0) pt_shade<true, false, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
-            else pt_shade<false, false, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
-        } else if (h->wide_lookback) {
-            if (b == 0) pt_shade<true, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
-            else pt_shade<false, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+        if (h->shade_tiled) {
+            if (keys && h->wide_lookback) {
+                if (b == 0) pt_shade_tiled<true, true, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+                else pt_shade_tiled<false, true, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+            } else if (keys) {
+                if (b == 0) pt_shade_tiled<true, false, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+                else pt_shade_tiled<false, false, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+            } else if (h->wide_lookback) {
+                if (b == 0) pt_shade_tiled<true, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+                else pt_shade_tiled<false, true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+            }
+            else if (b == 0) pt_shade_tiled<true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+            else pt_shade_tiled<false><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
+        } else {
+            const int blocks = std::min(h->ntiles, h->shade_blocks);
+            if (keys) {
+                if (b == 0) pt_shade<true, true><<<blocks, SH_THREADS, SH_SMEM_BYTES, st>>>(p);
+                else pt_shade<false, true><<<blocks, SH_THREADS, SH_SMEM_BYTES, st>>>(p);
+            }
+            else if (b == 0) pt_shade<true><<<blocks, SH_THREADS, SH_SMEM_BYTES, st>>>(p);
+            else pt_shade<false><<<blocks, SH_THREADS, SH_SMEM_BYTES, st>>>(p);
         }
-        else if (b == 0) pt_shade<true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
-        else pt_shade<false><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
         h->launches += 2;
         mark();
         h->cur = nxt;
@@ -1200,7 +1522,14 @@ extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* 
     cudaStream_t s_pt = h->fr_stream[0], s_dn = two_streams ? h->fr_stream[1] : h->fr_stream[0], s_cp = h->fr_stream[2];
     if (h->fr_timer_armed) { CUDA_TRY(cudaEventRecord(h->fr_ev_t0, s_pt)); h->fr_timer_armed = false; }
     if (two_streams && h->fr_submitted >= 2) CUDA_TRY(cudaStreamWaitEvent(s_pt, h->fr_ev_done[i], 0));   // the slot's G-buffer is free once frame k - 2 was denoised
+#ifdef PTD_FRAME_SPANS
+    for (int e = 0; e < 4; ++e) if (!h->sp_ev[i][e]) cudaEventCreate(&h->sp_ev[i][e]);
+    cudaEventRecord(h->sp_ev[i][0], s_pt);
+#endif
     rc = pt_run(h, cam, iter, h->fr_gbuf[i], s_pt, 0, h->depth);
+#ifdef PTD_FRAME_SPANS
+    cudaEventRecord(h->sp_ev[i][1], s_pt);
+#endif
     if (rc != PTD_OK) { cudaStreamSynchronize(s_pt); return rc; }
     CUDA_TRY(cudaEventRecord(h->fr_ev_pt[i], s_pt));
     // the rows this handle renders: the whole frame, or its strip of every plane ([planes][H][W] on both sides)
@@ -1212,7 +1541,13 @@ extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* 
         CUDA_TRY(cudaEventRecord(h->fr_ev_gcopy[i], s_cp));
     }
     if (two_streams) CUDA_TRY(cudaStreamWaitEvent(s_dn, h->fr_ev_pt[i], 0));
+#ifdef PTD_FRAME_SPANS
+    cudaEventRecord(h->sp_ev[i][2], s_dn);
+#endif
     rc = ptd_dn_forward_frame(dn, h->fr_gbuf[i], h->fr_rgb[i], reset_hidden, (void*)s_dn);
+#ifdef PTD_FRAME_SPANS
+    cudaEventRecord(h->sp_ev[i][3], s_dn);
+#endif
     if (rc != PTD_OK) { cudaStreamSynchronize(s_pt); cudaStreamSynchronize(s_dn); return rc; }
     CUDA_TRY(cudaEventRecord(h->fr_ev_done[i], s_dn));
     h->fr_has_rcopy[i] = rgb_host != nullptr;
@@ -1256,6 +1591,17 @@ extern "C" ptd_status ptd_frame_timer(ptd_pt* h, int op, float* ms) {
     return PTD_OK;
 }
 
+#ifdef PTD_FRAME_SPANS
+// debug build only: [PT start, PT end, DN start, DN end] of the last two submitted frames (older first), ms since the older frame's PT start
+extern "C" int ptd_debug_frame_spans(ptd_pt* h, float* out8) {
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    const int older = h->fr_submitted & 1;
+    for (int f = 0; f < 2; ++f)
+        for (int e = 0; e < 4; ++e) cudaEventElapsedTime(&out8[f * 4 + e], h->sp_ev[older][0], h->sp_ev[older ^ f][e]);
+    return 0;
+}
+#endif
 extern "C" ptd_status ptd_pt_export_rgba8(ptd_pt* h, int iter, unsigned char* pbo, void* stream_) {
     if (!h || !pbo || iter < 1) PTD_FAIL(PTD_ERR_ARG, "ptd_pt_export_rgba8: bad argument");
     CUDA_TRY(cudaSetDevice(h->device));

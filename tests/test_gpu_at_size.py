@@ -57,6 +57,19 @@ def _bit_exact_vs_oracle_a(capi, scene_path, frame, flags=0):
     _same(pt.dump_final_paths(), ref["final_paths"], "final partition layout")
     assert pt.dump_image().tobytes() == ref["image"].tobytes()
     assert tensor.tobytes() == ref["tensor"].tobytes()
+    # Without the reject array (the product configuration) pt_shade stores a tile's survivors one pipeline step later: same frame, bit for bit.
+    del pt
+    pt2 = capi.PathTracer(sc, flags=flags | capi.PT_TRACE)
+    assert pt2.render_host().tobytes() == ref["tensor"].tobytes()
+    assert pt2.live_counts()[0][:run] == counts[:run]
+    for b in range(run):
+        _same(pt2.dump_paths(b), ref["trace"][b]["paths"], "deferred stores, bounce %d paths" % b)
+        _same(pt2.dump_intersections(b), ref["trace"][b]["isx"], "deferred stores, bounce %d intersections" % b)
+    assert pt2.dump_image().tobytes() == ref["image"].tobytes()
+    del pt2
+    pt3 = capi.PathTracer(sc, flags=flags)
+    assert pt3.render_host().tobytes() == ref["tensor"].tobytes()
+    assert pt3.live_counts()[0][:run] == counts[:run]
     return counts[:run], ref["ms"]
 
 
@@ -71,14 +84,15 @@ def test_c2_cornell_720p_bit_exact_vs_reference_kernels(tmp_path):
         assert abs(a - b) <= 0.002 * b
 
 
-@pytest.mark.parametrize("opts", [{}, {"PTD_PT_RAY_SORT": "1", "PTD_PT_SMEM_STACK": "1", "PTD_PT_WIDE_LOOKBACK": "1"}], ids=["default", "all-kernel-options"])
+@pytest.mark.parametrize("opts", [{}, {"PTD_PT_RAY_SORT": "1", "PTD_PT_SMEM_STACK": "1"}, {"PTD_PT_RAY_SORT": "1", "PTD_PT_SMEM_STACK": "1", "PTD_PT_WIDE_LOOKBACK": "1"},
+                                  ], ids=["default", "kernel-options", "kernel-options-tiled-shade"])
 def test_c3_sponza_like_720p_bit_exact_vs_reference_kernels(tmp_path, opts, monkeypatch):
     """BASELINE config C3, frame 7 of the pan: 921 600 camera rays, 6.9 M path-bounces, ~1 800 shade tiles per bounce in the
     decoupled look-back, the BVH deciding which of the 261 k faces get the exact test.  Run with the default kernels and with every
     scheduling option bench.py's autotuner may switch on."""
     capi = _capi()
     from ai_path_tracer_denoiser_b200 import scenegen
-    for k in ("PTD_PT_RAY_SORT", "PTD_PT_SMEM_STACK", "PTD_PT_WIDE_LOOKBACK"):
+    for k in ("PTD_PT_RAY_SORT", "PTD_PT_SMEM_STACK", "PTD_PT_WIDE_LOOKBACK", "PTD_PT_SHADE_TILED"):
         monkeypatch.delenv(k, raising=False)
     for k, v in opts.items():
         monkeypatch.setenv(k, v)

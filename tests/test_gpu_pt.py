@@ -48,6 +48,16 @@ def _render_ours(capi, arrays, cam, flags):
     tensor = pt.render_host()
     counts, run = pt.live_counts()
     trace = [dict(paths=pt.dump_paths(b), isx=pt.dump_intersections(b)) for b in range(run)]
+    # Without the reject array (the product configuration) pt_shade stores a tile's survivors one pipeline step later: same frame, bit for bit.
+    for fl in (flags | capi.PT_TRACE, flags):
+        pt2 = capi.PathTracer(sc, flags=fl)
+        assert pt2.render_host().tobytes() == tensor.tobytes()
+        assert pt2.live_counts()[0][:run] == counts[:run]
+        assert pt2.dump_image().tobytes() == pt.dump_image().tobytes()
+        if fl & capi.PT_TRACE:
+            for b in range(run):
+                _same(pt2.dump_paths(b), trace[b]["paths"], "deferred stores, bounce %d paths" % b)
+                _same(pt2.dump_intersections(b), trace[b]["isx"], "deferred stores, bounce %d intersections" % b)
     return dict(tensor=tensor, counts=counts[:run], trace=trace, final=pt.dump_final_paths(), image=pt.dump_image(), pt=pt)
 
 
@@ -236,25 +246,31 @@ def test_ray_sort_changes_nothing(bits, unfused, monkeypatch):
     assert b[4] == a[4] + (3 if unfused == "1" else 2) * (sc.counts()[3] - 1)   # scan + scatter (+ the key pass when not fused) per bounce >= 1
 
 
-@pytest.mark.parametrize("res", [(160, 96), (800, 600)], ids=["experimental-wide-lookback-30tiles", "experimental-wide-lookback-938tiles"])
-def test_wide_lookback_changes_nothing(res, monkeypatch):
-    """PTD_PT_WIDE_LOOKBACK=1 (opt-in): pt_shade's decoupled look-back reads 512 predecessor tiles per trip with the whole block.
-    The compaction must stay the same stable compaction: identical live counts, PathSegment order and G-buffer - with fewer tiles
-    than one trip covers and with more (second trip)."""
+@pytest.mark.parametrize("res", [(160, 96), (800, 600), (1000, 803)], ids=["30tiles", "938tiles", "1569tiles-ragged"])
+def test_shade_kernel_variants_change_nothing(res, monkeypatch):
+    """pt_shade comes as the pipelined persistent kernel (default: bulk-copy prefetch of the next tile, look-back on its own warp, stores one
+    step later), as one tile per block (PTD_PT_SHADE_TILED=1) and that with a block-wide look-back (PTD_PT_WIDE_LOOKBACK=1).  The compaction
+    must stay the same stable compaction: identical live counts, PathSegment order and G-buffer - with fewer tiles than there are
+    persistent blocks, with several tiles per block, and with a ragged last tile."""
     capi = _capi()
     sc = capi.Scene(path=os.path.join(SCENES, "hall_64x48.txt"))
     sc.set_resolution(*res)
     out = []
-    for wide in ("0", "1"):
-        monkeypatch.setenv("PTD_PT_WIDE_LOOKBACK", wide)
+    for env in ({}, {"PTD_PT_SHADE_TILED": "1"}, {"PTD_PT_WIDE_LOOKBACK": "1"}, {"PTD_SHADE_BLOCKS_PER_SM": "1"}):
+        for k in ("PTD_PT_SHADE_TILED", "PTD_PT_WIDE_LOOKBACK", "PTD_SHADE_BLOCKS_PER_SM"):
+            monkeypatch.delenv(k, raising=False)
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
         pt = capi.PathTracer(sc, flags=capi.PT_TRACE)
-        g = pt.render_host()
+        for rep in range(2):
+            g = pt.render_host()
         counts, run = pt.live_counts()
         out.append((g, counts[:run], [pt.dump_paths(b) for b in range(run)]))
-    a, b = out
-    assert a[1] == b[1] and a[0].tobytes() == b[0].tobytes()
-    for k, (pa, pb) in enumerate(zip(a[2], b[2])):
-        _same(pa, pb, "bounce %d paths" % k)
+    a = out[0]
+    for b in out[1:]:
+        assert a[1] == b[1] and a[0].tobytes() == b[0].tobytes()
+        for k, (pa, pb) in enumerate(zip(a[2], b[2])):
+            _same(pa, pb, "bounce %d paths" % k)
 
 
 @pytest.mark.parametrize("combo", [{"PTD_PT_SMEM_STACK": "1"}, {"PTD_PT_SMEM_STACK": "1", "PTD_PT_RAY_SORT": "1", "PTD_PT_RAY_SORT_FROM": "1"}],
