@@ -683,7 +683,7 @@ __device__ __forceinline__ void sh_bulk_load(void* dst, const void* src, unsigne
 __device__ __forceinline__ void sh_bar_shaders() { asm volatile("bar.sync 1, %0;" ::"n"(PT_BLOCK) : "memory"); }   // the 16 shading warps only
 
 template <bool FIRST, bool KEYS = false>
-__global__ void __launch_bounds__(SH_THREADS, 2) pt_shade(const PtKernelParams p) {
+__global__ void __launch_bounds__(SH_THREADS, 1024 / PT_BLOCK) pt_shade(const PtKernelParams p) {
     extern __shared__ __align__(128) uint32_t sh_dyn[];
     uint32_t* const s_path_buf = sh_dyn;                                   // [3][SH_PATH_WORDS]
     uint32_t* const s_isx_buf = sh_dyn + 3 * SH_PATH_WORDS;                // [2][SH_ISX_WORDS]
@@ -756,7 +756,8 @@ __global__ void __launch_bounds__(SH_THREADS, 2) pt_shade(const PtKernelParams p
                     const unsigned not_ready = __ballot_sync(0xffffffffu, st == 0u);
                     const int first_prefix = has_prefix ? __ffs(has_prefix) - 1 : 31;
                     const unsigned needed = first_prefix == 31 ? 0xffffffffu : ((2u << first_prefix) - 1u);   // lanes 0 .. first_prefix
-                    if (not_ready & needed) { guard.tick(); continue; }    // a predecessor has not published yet: look again
+                    if (not_ready & needed) { guard.tick(); continue; }    // a predecessor has not published yet: look again (64 states per trip, a
+                                                                           // back-off, tile ids taken further ahead: all measured slower)
                     int v = lane <= first_prefix ? (int)(unsigned)sv : 0;
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -801,7 +802,7 @@ __global__ void __launch_bounds__(SH_THREADS, 2) pt_shade(const PtKernelParams p
 
         // ---- A. next tile id; its data starts to move now --------------------------------------------------------------------------
         if (tid == 0) {
-            const int nx = atomicAdd(p.ticket2, 1);
+            const int nx = atomicAdd(p.ticket2, 1);                        // (taking ids further ahead delays everybody's look-back: a held id is an unpublished predecessor)
             s_next = nx;
             if (bulk_tile(nx)) fetch(nx, i2 ^ 1, (k + 1) % 3);
         }
