@@ -712,7 +712,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         // last CTA of the launch: every CTA's stores are ordered before its counter increment, so the flags can be raised
         __threadfence();
         const uint32_t old = atomicAdd(p.link.done, 1u);
-        if ((old + 1u) % gridDim.x == 0u) {
+        if (old + 1u == gridDim.x) {                                     // (the counter restarts for this layer's next launch, whatever its grid will be)
+            *p.link.done = 0u;
             __threadfence_system();
             for (int i = 0; i < 4; ++i)
                 if (p.link.sig[i]) tc::st_release_sys(p.link.sig[i], p.link.epoch);
@@ -930,7 +931,7 @@ inline ptd_status tc_plan_create(const TcConvDesc& d, const std::vector<float>& 
     return PTD_OK;
 }
 
-inline ptd_status tc_conv_launch(TcConvPlan& plan, cudaStream_t st, int* launches, bool* pooled) {
+inline ptd_status tc_conv_launch(TcConvPlan& plan, cudaStream_t st, int* launches, bool* pooled, int sm_limit = 0) {
     if (!plan.valid) PTD_FAIL(PTD_ERR_STATE, "tc conv: plan not built");
     const int fmt = tc::tensor_format(plan.p.out);
     if (plan.p.pool_out.base && tc::tensor_format(plan.p.pool_out) != fmt) PTD_FAIL(PTD_ERR_STATE, "tc conv: output and pooled output differ in storage format");
@@ -938,7 +939,7 @@ inline ptd_status tc_conv_launch(TcConvPlan& plan, cudaStream_t st, int* launche
     TcKernel kern = tc_kernel_variant(tc_kernel_combo(plan.p.half != 0, fmt), plan.p.linked);
     cudaLaunchConfig_t cfg;
     memset(&cfg, 0, sizeof cfg);
-    cfg.gridDim = dim3(plan.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = plan.smem; cfg.stream = st;
+    cfg.gridDim = dim3(sm_limit > 0 && sm_limit < plan.grid ? sm_limit : plan.grid); cfg.blockDim = dim3(TC_THREADS); cfg.dynamicSmemBytes = plan.smem; cfg.stream = st;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;

@@ -242,7 +242,8 @@ __global__ void pack_gbuffer(const float* __restrict__ g, int H, int W, int row0
         __syncthreads();
         if (threadIdx.x == 0) {
             const uint32_t old = atomicAdd(link.done, 1u);
-            if ((old + 1u) % gridDim.x == 0u) {
+            if (old + 1u == gridDim.x) {
+                *link.done = 0u;
                 __threadfence_system();
                 if (link.sig_up) tc::st_release_sys(link.sig_up, link.epoch);
                 if (link.sig_down) tc::st_release_sys(link.sig_down, link.epoch);
@@ -370,6 +371,7 @@ struct ptd_dn {
     uint32_t epoch = 0;
     uint32_t* d_pack_done = nullptr;
     int parity = 0;
+    int sm_limit = 0;                                      // > 0: at most this many conv CTAs per launch (the denoiser's SM partition, ptd_frame_submit)
     int inflight = 0;                                      // frames enqueued by ptd_frame_submit and not yet taken by ptd_frame_wait (they own this handle's state)
     int launches = 0;
     bool profiling = false;
@@ -745,7 +747,7 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
             }
             plan.p.linked = h->nranks > 1 ? 1 : 0;
             plan.p.pdl = (h->pdl && li > 0 && !h->profiling) ? 1 : 0;       // the first conv follows pack_gbuffer, which does not trigger early
-            ptd_status rc = tc_conv_launch(plan, st, &h->launches, nullptr);
+            ptd_status rc = tc_conv_launch(plan, st, &h->launches, nullptr, h->sm_limit);
             if (rc != PTD_OK) return rc;
             mark(L.spec.name.c_str());
         } else {
@@ -798,6 +800,7 @@ static ptd_status dn_run(ptd_dn* h, const float* gbuf, float* rgb, int reset_hid
 ptd_status ptd_dn_forward_frame(ptd_dn* h, const float* gbuf, float* rgb, int reset_hidden, void* stream) {       // ptd_frame_* only (ptd_pt.cu)
     return dn_run(h, gbuf, rgb, reset_hidden, (cudaStream_t)stream, -1, (int)h->layers.size() + 1);
 }
+void ptd_dn_set_sm_limit(ptd_dn* h, int sms) { h->sm_limit = sms; }
 void ptd_dn_mark_inflight(ptd_dn* h, int delta) { h->inflight += delta; if (h->inflight < 0) h->inflight = 0; }
 extern "C" ptd_status ptd_dn_forward(ptd_dn* h, const float* gbuf, float* rgb, int reset_hidden, void* stream_) {
     if (!h || !gbuf || !rgb) PTD_FAIL(PTD_ERR_ARG, "ptd_dn_forward: null argument");

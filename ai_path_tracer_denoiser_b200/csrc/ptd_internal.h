@@ -98,6 +98,7 @@ void ptd_dn_describe(const ptd_dn* h, int* device, int* H, int* W, int* strip);
 // ptd_frame_submit / ptd_frame_wait (ptd_pt.cu) drive the denoiser through these: the frames in flight own the handle's state
 ptd_status ptd_dn_forward_frame(ptd_dn* h, const float* gbuf, float* rgb, int reset_hidden, void* stream);
 void ptd_dn_mark_inflight(ptd_dn* h, int delta);
+void ptd_dn_set_sm_limit(ptd_dn* h, int sms);          /* > 0: conv grids of the following forwards use at most this many CTAs (SM partition) */
 
 // camera helpers shared with the CLI
 void ptd_camera_derive(ptd_camera& cam, float fovy_deg);

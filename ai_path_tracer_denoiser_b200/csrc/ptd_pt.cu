@@ -17,6 +17,7 @@
 // The PathSegment array keeps the reference's 44-byte AoS layout in HBM (so parity dumps are plain copies and the
 // algorithmic bytes are the survey's 44 B read + 44 B written per live path per bounce); coalescing comes from the
 // shared-memory staging, not from a layout change.  No host synchronisation happens inside a frame.
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <unistd.h>
 #include <algorithm>
@@ -1032,6 +1033,9 @@ struct ptd_pt {
     int bvh_nodes = 0, bvh_leaves = 0, bvh_max_leaf = 0, bvh_max_depth = 0;
     // ptd_frame_submit / ptd_frame_wait: two frame slots, three streams (path trace, denoise + frame copy, G-buffer copy)
     cudaStream_t fr_stream[3] = {nullptr, nullptr, nullptr};
+    int fr_sm_pt = 0, fr_sm_dn = 0;                          // PTD_FRAME_SM_SPLIT: SMs of the path-trace / denoiser partition (0 = the whole GPU, shared)
+    void* fr_green[2] = {nullptr, nullptr};                  // the two green contexts (CUgreenCtx)
+    int trace_per_sm = 4, shade_per_sm = 2;
     float* fr_gbuf[2] = {nullptr, nullptr}; float* fr_rgb[2] = {nullptr, nullptr};
 #ifdef PTD_FRAME_SPANS
     cudaEvent_t sp_ev[2][4] = {};                            // debug build: PT start / end, DN start / end of the slot's frame (timing events)
@@ -1058,6 +1062,7 @@ extern "C" int ptd_device_count(void) {
     return n;
 }
 
+static void frame_green_destroy(void* green_ctx);
 extern "C" void ptd_pt_destroy(ptd_pt* h) {
     if (!h) return;
     cudaSetDevice(h->device);
@@ -1068,6 +1073,7 @@ extern "C" void ptd_pt_destroy(ptd_pt* h) {
     for (int r = 0; r < PT_MAX_RANKS; ++r) if (h->peer_mail[r] && h->peer_ipc[r]) cudaIpcCloseMemHandle(h->peer_mail[r]);
     if (h->host_stream[0]) { cudaStreamDestroy(h->host_stream[0]); cudaStreamDestroy(h->host_stream[1]); cudaEventDestroy(h->host_event); }
     for (int i = 0; i < 3; ++i) if (h->fr_stream[i]) { cudaStreamSynchronize(h->fr_stream[i]); cudaStreamDestroy(h->fr_stream[i]); }
+    for (int i = 0; i < 2; ++i) if (h->fr_green[i]) frame_green_destroy(h->fr_green[i]);
     for (int i = 0; i < 2; ++i) {
         cudaFree(h->fr_gbuf[i]); cudaFree(h->fr_rgb[i]);
         if (h->fr_ev_pt[i]) cudaEventDestroy(h->fr_ev_pt[i]);
@@ -1197,6 +1203,7 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
         else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pt_trace<false>, TR_BLOCK, geom_smem);
         if (const char* e = getenv("PTD_TRACE_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < per_sm) per_sm = v; }   // tuning knob: leave room for a concurrent kernel
         h->trace_blocks = std::max(1, std::min(sms * std::max(per_sm, 1), (h->P + TR_BLOCK - 1) / TR_BLOCK));   // persistent: every resident warp pulls rays
+        h->trace_per_sm = std::max(per_sm, 1);
         CUDA_TRY(cudaFuncSetAttribute(pt_shade<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(pt_shade<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_BYTES));
         CUDA_TRY(cudaFuncSetAttribute(pt_shade<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SH_SMEM_BYTES));
@@ -1205,6 +1212,7 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
         cudaOccupancyMaxActiveBlocksPerMultiprocessor(&sh_per_sm, pt_shade<false>, SH_THREADS, SH_SMEM_BYTES);
         if (const char* e = getenv("PTD_SHADE_BLOCKS_PER_SM")) { const int v = atoi(e); if (v >= 1 && v < sh_per_sm) sh_per_sm = v; }
         h->shade_blocks = sms * std::max(sh_per_sm, 1);
+        h->shade_per_sm = std::max(sh_per_sm, 1);
     }
     CUDA_TRY(cudaDeviceSynchronize());
     *out = h;
@@ -1256,6 +1264,10 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
     const size_t mail_box = (size_t)(h->epoch & 1u) * (size_t)(h->depth + 1) * PT_MAX_RANKS;          // this frame's mailbox (see pt_create)
     p.mail = h->d_mail + mail_box;
     for (int r = 0; r < PT_MAX_RANKS; ++r) p.peer_mail[r] = h->peer_mail[r] ? h->peer_mail[r] + mail_box : nullptr;
+    // on the path-trace partition of a split GPU (PTD_FRAME_SM_SPLIT) the persistent grids are sized for that partition
+    const bool part = h->fr_sm_pt > 0 && st == h->fr_stream[0];
+    const int trace_blocks = part ? std::min(h->trace_blocks, h->fr_sm_pt * h->trace_per_sm) : h->trace_blocks;
+    const int shade_blocks = part ? std::min(h->shade_blocks, h->fr_sm_pt * h->shade_per_sm) : h->shade_blocks;
     for (int b = first; b < last && b < h->depth; ++b) {
         const int cur = h->cur, nxt = (cur + 1) % (sort ? 3 : 2);
         p.bounce = b;
@@ -1264,8 +1276,8 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
         p.ticket = h->d_ticket + 2 * b; p.ticket2 = h->d_ticket + 2 * b + 1;
         p.isx = h->d_trace_isx ? h->d_trace_isx + (size_t)b * h->P : h->d_isx;
         if (b == 0) {
-            if (h->smem_stack) pt_trace<true, false, true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
-            else pt_trace<true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+            if (h->smem_stack) pt_trace<true, false, true><<<trace_blocks, TR_BLOCK, smem, st>>>(p);
+            else pt_trace<true><<<trace_blocks, TR_BLOCK, smem, st>>>(p);
         }
         else if ((h->flags & PTD_PT_RAY_SORT) && b >= h->bin_from) {
             // bin the live rays of this bounce, then trace them in bin order (timed together with the trace kernel they serve)
@@ -1278,12 +1290,12 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
             sort_scan<<<1, 1024, 0, st>>>(hist, h->nbins);
             ray_bin_scatter<<<blocks, 256, 0, st>>>(h->d_bin_keys, h->d_counts + b, hist, h->d_bin_order);
             p.order = h->d_bin_order; p.refill = h->bin_refill;
-            if (h->smem_stack) pt_trace<false, true, true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
-            else pt_trace<false, true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+            if (h->smem_stack) pt_trace<false, true, true><<<trace_blocks, TR_BLOCK, smem, st>>>(p);
+            else pt_trace<false, true><<<trace_blocks, TR_BLOCK, smem, st>>>(p);
             h->launches += 2;
         }
-        else if (h->smem_stack) pt_trace<false, false, true><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
-        else pt_trace<false><<<h->trace_blocks, TR_BLOCK, smem, st>>>(p);
+        else if (h->smem_stack) pt_trace<false, false, true><<<trace_blocks, TR_BLOCK, smem, st>>>(p);
+        else pt_trace<false><<<trace_blocks, TR_BLOCK, smem, st>>>(p);
         mark();
         if (b > 0 && h->rank > 0 && (h->flags & PTD_PT_GATED_MAIL)) {     // (timed together with the shade kernel it gates)
             pt_mail_gate<<<1, 32, 0, st>>>(p.mail, b, h->rank, h->epoch);
@@ -1306,7 +1318,7 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
             else if (b == 0) pt_shade_tiled<true><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
             else pt_shade_tiled<false><<<h->ntiles, PT_BLOCK, 0, st>>>(p);
         } else {
-            const int blocks = std::min(h->ntiles, h->shade_blocks);
+            const int blocks = std::min(h->ntiles, shade_blocks);
             if (keys) {
                 if (b == 0) pt_shade<true, true><<<blocks, SH_THREADS, SH_SMEM_BYTES, st>>>(p);
                 else pt_shade<false, true><<<blocks, SH_THREADS, SH_SMEM_BYTES, st>>>(p);
@@ -1482,11 +1494,72 @@ extern "C" ptd_status ptd_frame_host(ptd_pt* h, ptd_dn* dn, const ptd_camera* ca
 // optional G-buffer copy on a third - into one of two buffer slots and returns at once; ptd_frame_wait blocks until the OLDEST
 // submitted frame has reached the caller's host buffers.  With one frame in flight while the next is submitted, the path trace of
 // frame k + 1 overlaps the denoiser and the PCIe copies of frame k (the reference's loop is strictly serial, main.cpp:120-168).
+// PTD_FRAME_SM_SPLIT=<n>: the denoiser stream gets its own partition of >= n SMs, the path-trace stream the rest (CUDA green contexts).
+// Why: the two halves of consecutive frames are meant to overlap, but a conv CTA needs ~61 K of an SM's 64 K registers and a trace block 16 K,
+// so an SM can hold one kind or the other, never both.  When both streams have work the block scheduler spreads each grid over all SMs and the
+// two kernels end up waiting for each other's blocks to drain; with a strip's small grids (multi-GPU mode) neither kernel fills the GPU and the
+// partition lets both run at once.  Untiled frames fill the GPU either way (the split is work-conserving there: no gain).
+#define FRAME_SPLIT_MIN_RANKS 4
+#define FRAME_SPLIT_DN_SMS 32
+#define CU_TRY_DRV(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) PTD_FAIL(PTD_ERR_CUDA, "%s failed with CUresult %d", #call, (int)r_); } while (0)
+template <typename F> static F drv_entry(const char* name) {
+    void* fp = nullptr; cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint(name, &fp, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess) return nullptr;
+    return (F)fp;
+}
+static void frame_green_destroy(void* green_ctx) {
+    typedef CUresult (*F_destroy)(CUgreenCtx);
+    if (F_destroy destroy = drv_entry<F_destroy>("cuGreenCtxDestroy")) destroy((CUgreenCtx)green_ctx);
+}
+static ptd_status frame_sm_split(ptd_pt* h, int sm_dn) {
+    typedef CUresult (*F_getres)(CUdevice, CUdevResource*, CUdevResourceType);
+    typedef CUresult (*F_split)(CUdevResource*, unsigned int*, const CUdevResource*, CUdevResource*, unsigned int, unsigned int);
+    typedef CUresult (*F_desc)(CUdevResourceDesc*, CUdevResource*, unsigned int);
+    typedef CUresult (*F_create)(CUgreenCtx*, CUdevResourceDesc, CUdevice, unsigned int);
+    typedef CUresult (*F_stream)(CUstream*, CUgreenCtx, unsigned int, int);
+    typedef CUresult (*F_devget)(CUdevice*, int);
+    F_getres getres = drv_entry<F_getres>("cuDeviceGetDevResource");
+    F_split splitf = drv_entry<F_split>("cuDevSmResourceSplitByCount");
+    F_desc desc = drv_entry<F_desc>("cuDevResourceGenerateDesc");
+    F_create create = drv_entry<F_create>("cuGreenCtxCreate");
+    F_stream mkstream = drv_entry<F_stream>("cuGreenCtxStreamCreate");
+    F_devget devget = drv_entry<F_devget>("cuDeviceGet");
+    if (!getres || !splitf || !desc || !create || !mkstream || !devget) PTD_FAIL(PTD_ERR_UNSUPPORTED, "PTD_FRAME_SM_SPLIT: this driver has no green contexts");
+    CUdevice dev; CU_TRY_DRV(devget(&dev, h->device));
+    CUdevResource all, part, rest;
+    CU_TRY_DRV(getres(dev, &all, CU_DEV_RESOURCE_TYPE_SM));
+    unsigned int groups = 1;
+    CU_TRY_DRV(splitf(&part, &groups, &all, &rest, 0, (unsigned)sm_dn));
+    if (groups != 1 || rest.sm.smCount < 8) PTD_FAIL(PTD_ERR_ARG, "PTD_FRAME_SM_SPLIT=%d: cannot split %u SMs that way", sm_dn, all.sm.smCount);
+    CUdevResourceDesc d_dn, d_pt;
+    CU_TRY_DRV(desc(&d_dn, &part, 1));
+    CU_TRY_DRV(desc(&d_pt, &rest, 1));
+    CUgreenCtx g_dn, g_pt;
+    CU_TRY_DRV(create(&g_pt, d_pt, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+    CU_TRY_DRV(create(&g_dn, d_dn, dev, CU_GREEN_CTX_DEFAULT_STREAM));
+    CUstream s_pt, s_dn;
+    CU_TRY_DRV(mkstream(&s_pt, g_pt, CU_STREAM_NON_BLOCKING, 0));
+    CU_TRY_DRV(mkstream(&s_dn, g_dn, CU_STREAM_NON_BLOCKING, 0));
+    h->fr_stream[0] = (cudaStream_t)s_pt; h->fr_stream[1] = (cudaStream_t)s_dn;
+    h->fr_green[0] = (void*)g_pt; h->fr_green[1] = (void*)g_dn;
+    h->fr_sm_pt = (int)rest.sm.smCount; h->fr_sm_dn = (int)part.sm.smCount;
+    return PTD_OK;
+}
 // At most two frames may be in flight; frames complete in submission order; the recurrent state is carried in that order.
 static ptd_status frame_ring_init(ptd_pt* h) {
     if (h->fr_stream[0]) return PTD_OK;
     const size_t plane = sizeof(float) * (size_t)h->Pfull;
-    for (int i = 0; i < 3; ++i) CUDA_TRY(cudaStreamCreateWithFlags(&h->fr_stream[i], cudaStreamNonBlocking));
+    // SM partition of the two streams (see frame_sm_split): PTD_FRAME_SM_SPLIT=<SMs of the denoiser> (0 = none); by default 32 for the strips
+    // of a frame tiled over >= 4 GPUs, where neither half fills the GPU (C3, 2xf16: N = 4 514 -> 576 frames/s, N = 8 725 -> 821; with 16 / 40 /
+    // 64 SMs: 600 at N = 8, 549 / 471 at N = 4), none for untiled frames (work-conserving there: 32 SMs 209.5 vs 210.8 frames/s, 48 SMs 185.6).
+    const bool two_streams = (h->nranks == 1 && h->rows == h->H) || (h->flags & PTD_PT_GATED_MAIL);
+    const char* e = getenv("PTD_FRAME_SM_SPLIT");
+    const int split = e ? atoi(e) : (h->nranks >= FRAME_SPLIT_MIN_RANKS ? FRAME_SPLIT_DN_SMS : 0);
+    if (split > 0 && two_streams) {
+        ptd_status rc = frame_sm_split(h, split);
+        if (rc != PTD_OK && e) return rc;                               // asked for explicitly: fail loudly; the default falls back to the shared GPU
+    }
+    for (int i = 0; i < 3; ++i) if (!h->fr_stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&h->fr_stream[i], cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         CUDA_TRY(cudaMalloc((void**)&h->fr_gbuf[i], 10 * plane));
         CUDA_TRY(cudaMalloc((void**)&h->fr_rgb[i], 3 * plane));
@@ -1545,6 +1618,7 @@ extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* 
 #ifdef PTD_FRAME_SPANS
     cudaEventRecord(h->sp_ev[i][2], s_dn);
 #endif
+    ptd_dn_set_sm_limit(dn, two_streams ? h->fr_sm_dn : 0);
     rc = ptd_dn_forward_frame(dn, h->fr_gbuf[i], h->fr_rgb[i], reset_hidden, (void*)s_dn);
 #ifdef PTD_FRAME_SPANS
     cudaEventRecord(h->sp_ev[i][3], s_dn);
