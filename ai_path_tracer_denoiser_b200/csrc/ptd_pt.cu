@@ -1499,7 +1499,7 @@ extern "C" ptd_status ptd_frame_host(ptd_pt* h, ptd_dn* dn, const ptd_camera* ca
 // so an SM can hold one kind or the other, never both.  When both streams have work the block scheduler spreads each grid over all SMs and the
 // two kernels end up waiting for each other's blocks to drain; with a strip's small grids (multi-GPU mode) neither kernel fills the GPU and the
 // partition lets both run at once.  Untiled frames fill the GPU either way (the split is work-conserving there: no gain).
-#define FRAME_SPLIT_MIN_RANKS 4
+#define FRAME_SPLIT_MIN_RANKS 2
 #define FRAME_SPLIT_DN_SMS 32
 #define CU_TRY_DRV(call) do { CUresult r_ = (call); if (r_ != CUDA_SUCCESS) PTD_FAIL(PTD_ERR_CUDA, "%s failed with CUresult %d", #call, (int)r_); } while (0)
 template <typename F> static F drv_entry(const char* name) {
@@ -1550,8 +1550,8 @@ static ptd_status frame_ring_init(ptd_pt* h) {
     if (h->fr_stream[0]) return PTD_OK;
     const size_t plane = sizeof(float) * (size_t)h->Pfull;
     // SM partition of the two streams (see frame_sm_split): PTD_FRAME_SM_SPLIT=<SMs of the denoiser> (0 = none); by default 32 for the strips
-    // of a frame tiled over >= 4 GPUs, where neither half fills the GPU (C3, 2xf16: N = 4 514 -> 576 frames/s, N = 8 725 -> 821; with 16 / 40 /
-    // 64 SMs: 600 at N = 8, 549 / 471 at N = 4), none for untiled frames (work-conserving there: 32 SMs 209.5 vs 210.8 frames/s, 48 SMs 185.6).
+    // of a frame tiled over several GPUs, where neither half fills the GPU (C3, 2xf16: N = 2 340 -> 359 frames/s, N = 4 514 -> 576, N = 8 725 -> 821;
+    // with 16 / 40 / 64 SMs: 600 at N = 8, 549 / 471 at N = 4), none for untiled frames (work-conserving there: 32 SMs 209.5 vs 210.8 frames/s, 48 SMs 185.6).
     const bool two_streams = (h->nranks == 1 && h->rows == h->H) || (h->flags & PTD_PT_GATED_MAIL);
     const char* e = getenv("PTD_FRAME_SM_SPLIT");
     const int split = e ? atoi(e) : (h->nranks >= FRAME_SPLIT_MIN_RANKS ? FRAME_SPLIT_DN_SMS : 0);
