@@ -420,7 +420,9 @@ def main():
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE[args.mode], "data": "synthetic",
            "config": {"workload": "%s: %s" % (args.config, desc), "frames": "camera pan phi_k = phi_0 + 0.002 k, recurrent hidden state carried",
                       "frame_loop": "ptd_frame_submit / ptd_frame_wait (C++): two frame slots, path trace of frame k + 1 overlaps the denoiser of frame k" +
-                                    ("" if world == 1 or gated else " - strips: one stream per rank"),
+                                    ("" if world == 1 or gated else " - strips: one stream per rank") +
+                                    ("; SM partition (green contexts): denoiser stream %s SMs, path-trace stream the rest" % os.environ.get("PTD_FRAME_SM_SPLIT", "32")
+                                     if world > 1 and gated and os.environ.get("PTD_FRAME_SM_SPLIT", "32") != "0" else ""),
                       "triangles": nfaces, "live_paths_per_bounce": live[:run], "denoiser_padded": [Hp, Wp], "weights": "synthetic seed 1234 (no checkpoint ships)",
                       "l2": "per-frame working set (>1.5 GB of activations) exceeds the 126 MB L2; no explicit flush",
                       "parallelism": "1 GPU" if world == 1 else "each frame tiled in %d row strips (path tracer + denoiser), one strip per GPU; halo rows / live counts "

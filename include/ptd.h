@@ -173,7 +173,9 @@ ptd_status ptd_frame_host(ptd_pt*, ptd_dn*, const ptd_camera* cam, int iter, int
  * with rgb_host == NULL the denoised frame stays on the device (the frame loop itself, nothing copied).
  * Row-strip handles (ptd_pt_create_strip + ptd_dn_create_strip, connected): every rank submits the same frames; host_tensor / rgb_host are
  * still FULL-FRAME [10][H][W] / [3][H][W] buffers of which this rank fills its rows - over all ranks the same bytes reach the host as with
- * one GPU.  A strip's path trace overlaps its denoiser only for handles created with PTD_PT_GATED_MAIL. */
+ * one GPU.  A strip's path trace overlaps its denoiser only for handles created with PTD_PT_GATED_MAIL; those also run the two halves on
+ * two SM partitions of the GPU (CUDA green contexts: 32 SMs for the denoiser stream, the rest for the path trace; PTD_FRAME_SM_SPLIT=<n>
+ * in the environment chooses another size, 0 switches the partition off; it falls back to the shared GPU when the driver has none). */
 ptd_status ptd_frame_submit(ptd_pt*, ptd_dn*, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host);
 ptd_status ptd_frame_wait(ptd_pt*);
 /* Device time of a run of submitted frames (CUDA events on the streams ptd_frame_submit launches on): op 0 arms the timer - the next
