@@ -371,7 +371,7 @@ def main():
     else:
         g = trace_bytes / (trace_ms * 1e-3) / 1e9
         roof = dict(bound="hbm", kernel="pt_trace", achieved=g, peak=peaks["hbm"], unit="GB/s", frac=g / peaks["hbm"], traffic=None,
-                    note="BVH traversal is latency / divergence bound (ncu: 59 % of the stall samples are long-scoreboard, 16.8 of 32 lanes active in the node step), "
+                    note="BVH traversal is latency / divergence bound (ncu: 59 % of the stall samples are long-scoreboard, 17.9 of 32 lanes active in the node step), "
                          "not HBM bound: see mrays_per_s in kernels[] and DESIGN.md section 2")
     try:                                                 # DRAM traffic per launch of the dominant kernel, from the committed ncu capture
         tr = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
@@ -387,6 +387,9 @@ def main():
     roof["per_layer_ms"] = {n: round(float(m), 4) for (n, _), m in zip(dn_named, dn_ms)}
     roof["per_bounce_ms"] = {"pt_trace": [round(float(m), 4) for m in pt_ms[0::2]], "pt_shade": [round(float(m), 4) for m in pt_ms[1::2]]}
     roof["kernels"] = kernels
+    # the same figures as flat scalars (a consumer that keeps only the scalar fields of `roofline` still sees every kernel class)
+    roof.update(pt_trace_ms=round(trace_ms, 4), pt_mrays_per_s=kernels[1]["mrays_per_s"], pt_shade_ms=round(shade_ms, 4), pt_shade_hbm_frac=kernels[2]["hbm_frac"],
+                conv_ms=round(conv_ms, 4), conv_executed_tflops=round(conv_tf * executed, 1), conv_tensor_frac=round(conv_tf * executed / tensor_peak, 4))
 
     # ---- the reduced-precision engines beside the contract mode (N = 1; same frame loop, shorter run) ----
     modes = None
@@ -433,10 +436,13 @@ def main():
                    "api": "ptd_frame_submit + ptd_frame_wait with pinned host buffers: camera in; G-buffer (host_tensor) + denoised frame out, every frame" +
                           ("" if world == 1 else "; every rank returns its rows, %d ranks" % world)},
            "roofline": roof, "clocks": clocks}
+    out["config"].update(mode=args.mode, path_bounces_per_frame=int(sum(live[:run])))
     if modes:
         out["modes"] = modes
+        out["config"].update({"side_%s_fps" % m: v["value"] for m, v in modes.items()})      # flat copies of the side figures
     if replicas:
         out["replicas"] = replicas
+        out["config"]["replicas_fps"] = replicas["value"]
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         ref = CpuReference(scene_path, W, H, threads, scale=12 if nfaces else 1)
