@@ -36,7 +36,7 @@ ptd_dn_forward_host ptd_dn_create_strip ptd_dn_padded_size ptd_dn_dump_hidden pt
 ptd_pt_launches_last_render ptd_dn_profile ptd_dn_launch_times ptd_dn_launch_name ptd_pt_profile
 ptd_pt_launch_times ptd_dn_strip_partition ptd_dn_strip_info_size ptd_dn_strip_export ptd_dn_strip_connect
 ptd_dn_forward_group ptd_pt_create_strip ptd_pt_strip_info_size ptd_pt_strip_export ptd_pt_strip_connect
-ptd_pt_render_group ptd_frame_host ptd_frame_submit ptd_frame_wait ptd_frame_timer ptd_bvh_probe ptd_bvh_probe_order""".split()
+ptd_pt_render_group ptd_frame_host ptd_frame_submit ptd_frame_wait ptd_frame_slots ptd_frame_timer ptd_bvh_probe ptd_bvh_probe_order""".split()
 
 
 class PtdError(RuntimeError):
@@ -79,6 +79,8 @@ def lib():
         L.ptd_pt_render_host.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.ptd_frame_submit.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_frame_wait.argtypes = [C.c_void_p]
+        L.ptd_frame_slots.argtypes = []
+        L.ptd_frame_slots.restype = C.c_int
         L.ptd_frame_timer.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_float)]
         L.ptd_frame_host.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.ptd_bvh_probe_order.argtypes = [C.c_void_p, C.c_int, C.c_uint, C.c_int, C.POINTER(C.c_double)]
@@ -125,6 +127,11 @@ def check(rc, what=""):
 
 def device_count():
     return lib().ptd_device_count()
+
+
+def frame_slots():
+    """Frames ptd_frame_submit keeps in flight (3): submit frame k, then wait for frame k - (frame_slots() - 1)."""
+    return lib().ptd_frame_slots()
 
 
 def _view(ptr, dt, n):

@@ -119,6 +119,7 @@ __device__ __forceinline__ Ray camera_ray(const ptd_camera& cam, int W, int iter
 #define TR_MIN_BLOCKS 8
 #endif
 #define PT_SENTINEL 0x76543210
+#define FRAME_SLOTS 3                                   // frames ptd_frame_submit keeps in flight (G-buffer / image slots, mailboxes)
 
 struct TraceOut {
     ptd_intersection* isx; float* gbuf; int P, W, pix0; bool write_gbuf;   // P: pixels of the whole frame
@@ -1009,7 +1010,7 @@ struct ptd_pt {
     int W = 0, H = 0, P = 0, depth = 0, ngeoms = 0, nmaterials = 0, nfaces = 0, ntiles = 0;   // P: pixels of this handle (frame or strip)
     int Pfull = 0, row0 = 0, rows = 0;                        // whole-frame pixels; this handle's image rows [row0, row0 + rows)
     int rank = 0, nranks = 1; unsigned epoch = 0;
-    unsigned long long* d_mail = nullptr;                     // [2][depth + 1][PT_MAX_RANKS], written by the strips above (peer stores)
+    unsigned long long* d_mail = nullptr;                     // [FRAME_SLOTS][depth + 1][PT_MAX_RANKS], written by the strips above (peer stores)
     unsigned long long* peer_mail[PT_MAX_RANKS] = {nullptr}; bool peer_ipc[PT_MAX_RANKS] = {false};
     ptd_camera cam;
     ptd_aabb mesh_box;
@@ -1036,14 +1037,14 @@ struct ptd_pt {
     int fr_sm_pt = 0, fr_sm_dn = 0;                          // PTD_FRAME_SM_SPLIT: SMs of the path-trace / denoiser partition (0 = the whole GPU, shared)
     void* fr_green[2] = {nullptr, nullptr};                  // the two green contexts (CUgreenCtx)
     int trace_per_sm = 4, shade_per_sm = 2;
-    float* fr_gbuf[2] = {nullptr, nullptr}; float* fr_rgb[2] = {nullptr, nullptr};
+    float* fr_gbuf[FRAME_SLOTS] = {}; float* fr_rgb[FRAME_SLOTS] = {};
 #ifdef PTD_FRAME_SPANS
-    cudaEvent_t sp_ev[2][4] = {};                            // debug build: PT start / end, DN start / end of the slot's frame (timing events)
+    cudaEvent_t sp_ev[FRAME_SLOTS][4] = {};                            // debug build: PT start / end, DN start / end of the slot's frame (timing events)
 #endif
-    cudaEvent_t fr_ev_pt[2] = {nullptr, nullptr}, fr_ev_done[2] = {nullptr, nullptr}, fr_ev_gcopy[2] = {nullptr, nullptr}, fr_ev_rcopy[2] = {nullptr, nullptr};
-    bool fr_has_gcopy[2] = {false, false}, fr_has_rcopy[2] = {false, false};
+    cudaEvent_t fr_ev_pt[FRAME_SLOTS] = {}, fr_ev_done[FRAME_SLOTS] = {}, fr_ev_gcopy[FRAME_SLOTS] = {}, fr_ev_rcopy[FRAME_SLOTS] = {};
+    bool fr_has_gcopy[FRAME_SLOTS] = {}, fr_has_rcopy[FRAME_SLOTS] = {};
     long long fr_submitted = 0, fr_waited = 0;
-    ptd_dn* fr_dn[2] = {nullptr, nullptr};                   // the denoiser handle of the frame in each slot (its in-flight count is ours to drop)
+    ptd_dn* fr_dn[FRAME_SLOTS] = {};                   // the denoiser handle of the frame in each slot (its in-flight count is ours to drop)
     cudaEvent_t fr_ev_t0 = nullptr, fr_ev_t1 = nullptr; bool fr_timer_armed = false; cudaStream_t fr_last_dn = nullptr;   // ptd_frame_timer
     bool wide_lookback = false;                              // PTD_PT_WIDE_LOOKBACK=1 (tiled shade kernel only)
     bool shade_tiled = false;                                // PTD_PT_SHADE_TILED=1: one tile per block (round 1's kernel) instead of the pipelined one
@@ -1074,7 +1075,7 @@ extern "C" void ptd_pt_destroy(ptd_pt* h) {
     if (h->host_stream[0]) { cudaStreamDestroy(h->host_stream[0]); cudaStreamDestroy(h->host_stream[1]); cudaEventDestroy(h->host_event); }
     for (int i = 0; i < 3; ++i) if (h->fr_stream[i]) { cudaStreamSynchronize(h->fr_stream[i]); cudaStreamDestroy(h->fr_stream[i]); }
     for (int i = 0; i < 2; ++i) if (h->fr_green[i]) frame_green_destroy(h->fr_green[i]);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FRAME_SLOTS; ++i) {
         cudaFree(h->fr_gbuf[i]); cudaFree(h->fr_rgb[i]);
         if (h->fr_ev_pt[i]) cudaEventDestroy(h->fr_ev_pt[i]);
         if (h->fr_ev_done[i]) cudaEventDestroy(h->fr_ev_done[i]);
@@ -1177,11 +1178,12 @@ static ptd_status pt_create(const ptd_scene* sc, int device, unsigned flags, int
         ALLOC(h->d_bin_order, sizeof(int) * P);
     }
     ALLOC(h->d_ctl, h->ctl_bytes);
-    // two mailboxes, used alternately by frame parity: with at most two frames in flight per rank (ptd_frame_submit) a strip above that
-    // already renders frame k + 1 writes the other box, and cannot reach frame k + 2 before every strip has read frame k's counts (its
-    // denoiser of frame k, which gates the slot, depends on every other strip's denoiser of frame k and so on their path trace of frame k)
-    ALLOC(h->d_mail, sizeof(unsigned long long) * 2 * (size_t)(h->depth + 1) * PT_MAX_RANKS);
-    cudaMemset(h->d_mail, 0, sizeof(unsigned long long) * 2 * (size_t)(h->depth + 1) * PT_MAX_RANKS);
+    // FRAME_SLOTS mailboxes, used in turn (frame number mod FRAME_SLOTS): with at most FRAME_SLOTS frames in flight per rank (ptd_frame_submit)
+    // a strip above that already renders frame k + 1 or k + 2 writes another box, and cannot reach frame k + FRAME_SLOTS before every strip has
+    // read frame k's counts (its denoiser of frame k, which gates the slot, depends on every other strip's denoiser of frame k and so on their
+    // path trace of frame k)
+    ALLOC(h->d_mail, sizeof(unsigned long long) * FRAME_SLOTS * (size_t)(h->depth + 1) * PT_MAX_RANKS);
+    cudaMemset(h->d_mail, 0, sizeof(unsigned long long) * FRAME_SLOTS * (size_t)(h->depth + 1) * PT_MAX_RANKS);
     h->d_counts = (int*)(h->d_ctl + off_counts); h->d_ticket = (int*)(h->d_ctl + off_ticket); h->d_status = (unsigned long long*)(h->d_ctl + off_status);
     if (flags & PTD_PT_RAY_SORT) h->d_bin_hist = (int*)(h->d_ctl + off_bins);
     if (sort) {
@@ -1261,7 +1263,7 @@ static ptd_status pt_run(ptd_pt* h, const ptd_camera* cam, int iter, float* gbuf
         mark();
     }
     p.epoch = h->epoch;
-    const size_t mail_box = (size_t)(h->epoch & 1u) * (size_t)(h->depth + 1) * PT_MAX_RANKS;          // this frame's mailbox (see pt_create)
+    const size_t mail_box = (size_t)(h->epoch % FRAME_SLOTS) * (size_t)(h->depth + 1) * PT_MAX_RANKS;          // this frame's mailbox (see pt_create)
     p.mail = h->d_mail + mail_box;
     for (int r = 0; r < PT_MAX_RANKS; ++r) p.peer_mail[r] = h->peer_mail[r] ? h->peer_mail[r] + mail_box : nullptr;
     // on the path-trace partition of a split GPU (PTD_FRAME_SM_SPLIT) the persistent grids are sized for that partition
@@ -1560,7 +1562,7 @@ static ptd_status frame_ring_init(ptd_pt* h) {
         if (rc != PTD_OK && e) return rc;                               // asked for explicitly: fail loudly; the default falls back to the shared GPU
     }
     for (int i = 0; i < 3; ++i) if (!h->fr_stream[i]) CUDA_TRY(cudaStreamCreateWithFlags(&h->fr_stream[i], cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < FRAME_SLOTS; ++i) {
         CUDA_TRY(cudaMalloc((void**)&h->fr_gbuf[i], 10 * plane));
         CUDA_TRY(cudaMalloc((void**)&h->fr_rgb[i], 3 * plane));
         CUDA_TRY(cudaMemset(h->fr_gbuf[i], 0, 10 * plane));
@@ -1582,11 +1584,11 @@ extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* 
     const bool strip = h->nranks > 1 || h->rows != h->H;
     if (strip != (dn_strip != 0)) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_submit: path tracer and denoiser handles must both cover the frame or both be row strips");
     if (dn_device != h->device || dn_H != h->H || dn_W != h->W) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_submit: the denoiser handle is for %dx%d on device %d, the path tracer for %dx%d on device %d", dn_W, dn_H, dn_device, h->W, h->H, h->device);
-    if (h->fr_submitted - h->fr_waited >= 2) PTD_FAIL(PTD_ERR_STATE, "ptd_frame_submit: two frames are in flight - call ptd_frame_wait first");
+    if (h->fr_submitted - h->fr_waited >= FRAME_SLOTS) PTD_FAIL(PTD_ERR_STATE, "ptd_frame_submit: %d frames are in flight - call ptd_frame_wait first", FRAME_SLOTS);
     CUDA_TRY(cudaSetDevice(h->device));
     ptd_status rc = frame_ring_init(h);
     if (rc != PTD_OK) return rc;
-    const int i = h->fr_submitted & 1;                                  // this slot's previous frame (two submissions ago) has been waited for
+    const int i = (int)(h->fr_submitted % FRAME_SLOTS);                 // this slot's previous frame (FRAME_SLOTS submissions ago) has been waited for
     const size_t plane = sizeof(float) * (size_t)h->Pfull;
     // Row strips: a frame's kernels wait for other GPUs (halo rows, live counts).  With the path trace of frame k + 1 on its own stream,
     // a kernel that spins while it holds an SM can starve the kernel it waits for; PTD_PT_GATED_MAIL moves the path tracer's only wait
@@ -1595,7 +1597,7 @@ extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* 
     const bool two_streams = !strip || (h->flags & PTD_PT_GATED_MAIL);
     cudaStream_t s_pt = h->fr_stream[0], s_dn = two_streams ? h->fr_stream[1] : h->fr_stream[0], s_cp = h->fr_stream[2];
     if (h->fr_timer_armed) { CUDA_TRY(cudaEventRecord(h->fr_ev_t0, s_pt)); h->fr_timer_armed = false; }
-    if (two_streams && h->fr_submitted >= 2) CUDA_TRY(cudaStreamWaitEvent(s_pt, h->fr_ev_done[i], 0));   // the slot's G-buffer is free once frame k - 2 was denoised
+    if (two_streams && h->fr_submitted >= FRAME_SLOTS) CUDA_TRY(cudaStreamWaitEvent(s_pt, h->fr_ev_done[i], 0));   // the slot's G-buffer is free once its previous frame was denoised
 #ifdef PTD_FRAME_SPANS
     for (int e = 0; e < 4; ++e) if (!h->sp_ev[i][e]) cudaEventCreate(&h->sp_ev[i][e]);
     cudaEventRecord(h->sp_ev[i][0], s_pt);
@@ -1637,11 +1639,12 @@ extern "C" ptd_status ptd_frame_submit(ptd_pt* h, ptd_dn* dn, const ptd_camera* 
     h->fr_submitted += 1;
     return PTD_OK;
 }
+extern "C" int ptd_frame_slots(void) { return FRAME_SLOTS; }
 extern "C" ptd_status ptd_frame_wait(ptd_pt* h) {
     if (!h) PTD_FAIL(PTD_ERR_ARG, "ptd_frame_wait: null handle");
     if (h->fr_waited == h->fr_submitted) PTD_FAIL(PTD_ERR_STATE, "ptd_frame_wait: no frame in flight");
     CUDA_TRY(cudaSetDevice(h->device));
-    const int i = h->fr_waited & 1;
+    const int i = (int)(h->fr_waited % FRAME_SLOTS);
     h->fr_waited += 1;                                                  // whatever happens below, this frame is no longer in flight
     if (h->fr_dn[i]) { ptd_dn_mark_inflight(h->fr_dn[i], -1); h->fr_dn[i] = nullptr; }
     CUDA_TRY(cudaEventSynchronize(h->fr_ev_done[i]));
@@ -1671,9 +1674,9 @@ extern "C" ptd_status ptd_frame_timer(ptd_pt* h, int op, float* ms) {
 extern "C" int ptd_debug_frame_spans(ptd_pt* h, float* out8) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    const int older = h->fr_submitted & 1;
+    const int older = (int)((h->fr_submitted + FRAME_SLOTS - 2) % FRAME_SLOTS);
     for (int f = 0; f < 2; ++f)
-        for (int e = 0; e < 4; ++e) cudaEventElapsedTime(&out8[f * 4 + e], h->sp_ev[older][0], h->sp_ev[older ^ f][e]);
+        for (int e = 0; e < 4; ++e) cudaEventElapsedTime(&out8[f * 4 + e], h->sp_ev[older][0], h->sp_ev[(older + f) % FRAME_SLOTS][e]);
     return 0;
 }
 #endif

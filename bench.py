@@ -6,7 +6,7 @@ frame k of a 300-frame pan, then the recurrent denoiser forward (HP-2) with the 
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode 2xf16|f16|tf32|3xtf32|fp32] [--config C2..C5]
 
-Every frame of every leg goes through the C ABI's frame loop, ptd_frame_submit / ptd_frame_wait (include/ptd.h; C++: two frame slots,
+Every frame of every leg goes through the C ABI's frame loop, ptd_frame_submit / ptd_frame_wait (include/ptd.h; C++: three frame slots,
 path trace of frame k + 1 on one stream overlapping the denoiser of frame k on another) - at N = 1 and, on row-strip handles, at N > 1.
 
 Prints ONE JSON line:
@@ -259,25 +259,29 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    SLOTS = capi.frame_slots()                          # frames the C++ loop keeps in flight (3)
+
     def frame_loop(pt_, dn_, first_cam, n, hosts=None, reset_first=False):
-        """n frames through ptd_frame_submit / ptd_frame_wait, frame k + 1 submitted before frame k is awaited; every frame has been
-        waited for on return.  hosts = [(gbuf, rgb)] * 2 pinned tensors, or None (nothing leaves the device)."""
+        """n frames through ptd_frame_submit / ptd_frame_wait, frames k + 1 and k + 2 submitted before frame k is awaited; every frame has been
+        waited for on return.  hosts = [(gbuf, rgb)] * SLOTS pinned tensors, or None (nothing leaves the device)."""
         for k in range(n):
-            g, r = (hosts[k & 1] if hosts else (None, None))
+            g, r = (hosts[k % SLOTS] if hosts else (None, None))
             pt_.frame_submit(dn_, r, g, cam=cams[first_cam + k], reset=(reset_first and k == 0))
-            if k:
+            if k >= SLOTS - 1:
                 pt_.frame_wait()
-        pt_.frame_wait()
+        for _ in range(min(n, SLOTS - 1)):
+            pt_.frame_wait()
 
     def device_timed(pt_, dn_, first_cam, n):
         sync_all()
         pt_.frame_timer_start()
         for k in range(n):
             pt_.frame_submit(dn_, None, None, cam=cams[first_cam + k])
-            if k:
+            if k >= SLOTS - 1:
                 pt_.frame_wait()
         ms = pt_.frame_timer_stop()
-        pt_.frame_wait()
+        for _ in range(min(n, SLOTS - 1)):
+            pt_.frame_wait()
         return allmax(ms)
 
     # ---- warm-up, then K timed steps (device timing, max over ranks) ----
@@ -292,7 +296,7 @@ def main():
     launches_per_step = pt.launches() + dn.launches()
 
     # ---- end to end: the same loop with host buffers (wall clock, max over ranks) ----
-    hosts = [(torch.zeros(10, H, W, dtype=torch.float32).pin_memory(), torch.zeros(3, H, W, dtype=torch.float32).pin_memory()) for _ in range(2)]
+    hosts = [(torch.zeros(10, H, W, dtype=torch.float32).pin_memory(), torch.zeros(3, H, W, dtype=torch.float32).pin_memory()) for _ in range(SLOTS)]
     frame_loop(pt, dn, 0, 3, hosts)
     sync_all()
     t0 = time.perf_counter()
@@ -422,7 +426,7 @@ def main():
     out = {"metric": METRIC, "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": DTYPE[args.mode], "data": "synthetic",
            "config": {"workload": "%s: %s" % (args.config, desc), "frames": "camera pan phi_k = phi_0 + 0.002 k, recurrent hidden state carried",
-                      "frame_loop": "ptd_frame_submit / ptd_frame_wait (C++): two frame slots, path trace of frame k + 1 overlaps the denoiser of frame k" +
+                      "frame_loop": "ptd_frame_submit / ptd_frame_wait (C++): %d frame slots, path trace of frame k + 1 overlaps the denoiser of frame k" % SLOTS +
                                     ("" if world == 1 or gated else " - strips: one stream per rank") +
                                     ("; SM partition (green contexts): denoiser stream %s SMs, path-trace stream the rest" % os.environ.get("PTD_FRAME_SM_SPLIT", "32")
                                      if world > 1 and gated and os.environ.get("PTD_FRAME_SM_SPLIT", "32") != "0" else ""),

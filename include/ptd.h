@@ -166,7 +166,8 @@ ptd_status ptd_dn_forward_host(ptd_dn*, const float* gbuffer_host, float* rgb_ho
 ptd_status ptd_frame_host(ptd_pt*, ptd_dn*, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host);
 /* The same frame asynchronously.  ptd_frame_submit enqueues path trace + denoise + host copies of one frame and returns at once;
  * ptd_frame_wait blocks until the OLDEST submitted frame has reached its host buffers.  Submit frame k + 1 before waiting for frame k
- * and the path trace of k + 1 overlaps the denoiser and the PCIe copies of k.  At most two frames in flight; frames complete in
+ * and the path trace of k + 1 overlaps the denoiser and the PCIe copies of k.  At most ptd_frame_slots() (3) frames in flight - keep two
+ * ahead of the wait and neither the copies nor the host's submission latency ever leave the GPU idle; frames complete in
  * submission order (so the recurrent state is carried in that order); the host buffers of a frame must stay valid, and should be
  * pinned, until its ptd_frame_wait returns.  Results are bit-identical to ptd_frame_host / the two-call path.
  * iter must be 1 (one sample per pixel per frame, what runCuda() renders; PTD_ERR_UNSUPPORTED otherwise).  Both host pointers are optional:
@@ -178,6 +179,7 @@ ptd_status ptd_frame_host(ptd_pt*, ptd_dn*, const ptd_camera* cam, int iter, int
  * in the environment chooses another size, 0 switches the partition off; it falls back to the shared GPU when the driver has none). */
 ptd_status ptd_frame_submit(ptd_pt*, ptd_dn*, const ptd_camera* cam, int iter, int reset_hidden, float* host_tensor, float* rgb_host);
 ptd_status ptd_frame_wait(ptd_pt*);
+int ptd_frame_slots(void);
 /* Device time of a run of submitted frames (CUDA events on the streams ptd_frame_submit launches on): op 0 arms the timer - the next
  * ptd_frame_submit records the start event ahead of its first launch; op 1 records the stop event behind the last submitted frame's
  * denoiser, waits for it and returns the elapsed milliseconds. */

@@ -22,7 +22,7 @@ class _FakeLib:
         self.real, self.calls = real, []
 
     def __getattr__(self, name):
-        if not name.startswith(("ptd_pt_", "ptd_dn_", "ptd_frame_")) or name == "ptd_dn_strip_partition":     # pure host arithmetic
+        if not name.startswith(("ptd_pt_", "ptd_dn_", "ptd_frame_")) or name in ("ptd_dn_strip_partition", "ptd_frame_slots"):     # pure host arithmetic
             return getattr(self.real, name)
 
         def f(*a):
@@ -46,7 +46,7 @@ def bench_env(monkeypatch):
             self.P, self.depth, self.h, self.flags = self.W * (strip[1] if strip else self.H), scene.counts()[3], 1, flags
             self.inflight = 0
         def frame_submit(self, dn, rgb_out, gbuf_out=None, cam=None, iter=1, reset=False):
-            assert self.inflight < 2
+            assert self.inflight < 3
             self.inflight += 1
             log.append(("submit", rgb_out is not None, gbuf_out is not None, reset))
         def frame_wait(self):

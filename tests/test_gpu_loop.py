@@ -64,7 +64,7 @@ def test_frame_host_equals_the_two_host_calls(tmp_path, mode):
 
 @pytest.mark.parametrize("mode", ["experimental-frame-submit-wait"])
 def test_frame_submit_wait_equals_the_two_host_calls(tmp_path, mode):
-    """ptd_frame_submit / ptd_frame_wait (one frame in flight while the next is submitted) == ptd_pt_render_host + ptd_dn_forward_host,
+    """ptd_frame_submit / ptd_frame_wait (two frames in flight while the next is submitted) == ptd_pt_render_host + ptd_dn_forward_host,
     bit for bit over a recurrent sequence, with and without the host copy of the G-buffer; call-order errors are reported, not ignored."""
     from ai_path_tracer_denoiser_b200 import capi, weights
     if capi.device_count() < 1:
@@ -92,25 +92,38 @@ def test_frame_submit_wait_equals_the_two_host_calls(tmp_path, mode):
         pt_b.live_counts()
     with pytest.raises(capi.PtdError, match="in flight"):
         dn_b.dump_hidden(0)
+    slots = capi.frame_slots()
+    assert slots == 3
+    done = 0
+
+    def wait_and_check():
+        nonlocal done
+        pt_b.frame_wait()                                              # the oldest frame in flight is complete
+        assert rgb[done].tobytes() == ref[done][1].tobytes(), done
+        if gb[done] is not None:
+            assert gb[done].tobytes() == ref[done][0].tobytes(), done
+        done += 1
+
     for k in range(1, n):
         pt_b.frame_submit(dn_b, rgb[k], gb[k], cam=cams[k])
-        if k == 1:
-            with pytest.raises(capi.PtdError):
-                pt_b.frame_submit(dn_b, rgb[k], gb[k], cam=cams[k])   # a third frame in flight
-        pt_b.frame_wait()                                              # frame k - 1 is complete
-        assert rgb[k - 1].tobytes() == ref[k - 1][1].tobytes(), k - 1
-        if gb[k - 1] is not None:
-            assert gb[k - 1].tobytes() == ref[k - 1][0].tobytes(), k - 1
-    pt_b.frame_wait()
-    assert rgb[n - 1].tobytes() == ref[n - 1][1].tobytes()
+        if k == slots - 1:
+            with pytest.raises(capi.PtdError, match="in flight"):
+                pt_b.frame_submit(dn_b, rgb[k], gb[k], cam=cams[k])   # one frame more than there are slots
+        if k >= slots - 1:
+            wait_and_check()
+    while done < n:
+        wait_and_check()
+    with pytest.raises(capi.PtdError):
+        pt_b.frame_wait()
     # a frame may stay on the device (no host pointer at all), and the device timer brackets a run of frames
     pt_b.frame_timer_start()
-    for k in range(3):
+    for k in range(4):
         pt_b.frame_submit(dn_b, None, None, cam=cams[k], reset=(k == 0))
-        if k:
+        if k >= slots - 1:
             pt_b.frame_wait()
     ms = pt_b.frame_timer_stop()
-    pt_b.frame_wait()
+    for _ in range(slots - 1):
+        pt_b.frame_wait()
     assert 0.0 < ms < 5000.0
     # accumulation (iter > 1) needs the first-hit planes of iteration 1, which live in the other slot: reported, not silently wrong
     with pytest.raises(capi.PtdError, match="iter == 1"):

@@ -1,6 +1,6 @@
 """torchrun --nproc-per-node N tools/check_frame_strips.py [W H frames mode gated]
 Multi-process parity check of ptd_frame_submit / ptd_frame_wait on row strips: every rank (a) renders the untiled frames on its own
-GPU through the two reference call sites and (b) submits the same frames through its strip handles with one frame in flight while the
+GPU through the two reference call sites and (b) submits the same frames through its strip handles with two frames in flight while the
 next is submitted, host buffers for the G-buffer and the denoised frame; its rows of both must be bit-identical.  gated = 1 creates the
 path-tracer strips with PTD_PT_GATED_MAIL, i.e. path trace of frame k + 1 and denoiser of frame k on two streams.
 Prints one line per rank; exit code 1 on any mismatch.  Test infrastructure, not product."""
@@ -52,17 +52,27 @@ def check(k):
         print("rank %d frame %d MISMATCH gbuf=%s rgb=%s outside-rows-untouched=%s" % (rank, k, ok_g, ok_y, outside), flush=True)
 
 
-pipe.pt.frame_submit(pipe.dn, hr[0], hg[0], cam=cams[0], reset=True)
-for k in range(1, frames):
-    pipe.pt.frame_submit(pipe.dn, hr[k], hg[k] if k % 3 != 2 else None, cam=cams[k])
+slots = capi.frame_slots()                                     # 3: two frames stay in flight behind the one being submitted
+done = 0
+
+
+def wait_and_check():
+    global bad, done
     pipe.pt.frame_wait()
-    if (k - 1) % 3 != 2 or k - 1 == 0:
-        check(k - 1)
-    elif hr[k - 1].numpy()[:, r0:r0 + nr].tobytes() != refs[k - 1][1][:, r0:r0 + nr].tobytes():
+    k = done
+    if k % 3 != 2:                                             # (every third frame was submitted without a G-buffer pointer)
+        check(k)
+    elif hr[k].numpy()[:, r0:r0 + nr].tobytes() != refs[k][1][:, r0:r0 + nr].tobytes():
         bad += 1
-pipe.pt.frame_wait()
-if hr[frames - 1].numpy()[:, r0:r0 + nr].tobytes() != refs[frames - 1][1][:, r0:r0 + nr].tobytes():
-    bad += 1
+    done += 1
+
+
+for k in range(frames):
+    pipe.pt.frame_submit(pipe.dn, hr[k], hg[k] if k % 3 != 2 else None, cam=cams[k], reset=(k == 0))
+    if k >= slots - 1:
+        wait_and_check()
+while done < frames:
+    wait_and_check()
 t = torch.tensor([bad], device="cuda")
 dist.all_reduce(t)
 print("rank %d/%d rows [%d,%d) mode %s %s: %d frame(s) %s" % (rank, world, r0, r0 + nr, mode, "two streams (gated mail)" if gated else "one stream", frames,

@@ -15,9 +15,10 @@ cams = [capi.frame_camera(sc.camera[0], k) for k in range(40)]
 N = 24
 for k in range(N):
     pt.frame_submit(dn, None, None, cam=cams[k], reset=(k == 0))
-    if k:
+    if k >= capi.frame_slots() - 1:
         pt.frame_wait()
-pt.frame_wait()
+for _ in range(capi.frame_slots() - 1):
+    pt.frame_wait()
 out = (ctypes.c_float * 8)()
 lib.ptd_debug_frame_spans(pt.h, out)
 v = [round(x, 3) for x in out]
