@@ -1032,7 +1032,7 @@ struct ptd_pt {
     std::vector<cudaEvent_t> events;
     int timed_launches = 0;
     int bvh_nodes = 0, bvh_leaves = 0, bvh_max_leaf = 0, bvh_max_depth = 0;
-    // ptd_frame_submit / ptd_frame_wait: two frame slots, three streams (path trace, denoise + frame copy, G-buffer copy)
+    // ptd_frame_submit / ptd_frame_wait: FRAME_SLOTS frame slots, three streams (path trace, denoise + frame copy, G-buffer copy)
     cudaStream_t fr_stream[3] = {nullptr, nullptr, nullptr};
     int fr_sm_pt = 0, fr_sm_dn = 0;                          // PTD_FRAME_SM_SPLIT: SMs of the path-trace / denoiser partition (0 = the whole GPU, shared)
     void* fr_green[2] = {nullptr, nullptr};                  // the two green contexts (CUgreenCtx)
@@ -1547,7 +1547,7 @@ static ptd_status frame_sm_split(ptd_pt* h, int sm_dn) {
     h->fr_sm_pt = (int)rest.sm.smCount; h->fr_sm_dn = (int)part.sm.smCount;
     return PTD_OK;
 }
-// At most two frames may be in flight; frames complete in submission order; the recurrent state is carried in that order.
+// At most FRAME_SLOTS frames may be in flight; frames complete in submission order; the recurrent state is carried in that order.
 static ptd_status frame_ring_init(ptd_pt* h) {
     if (h->fr_stream[0]) return PTD_OK;
     const size_t plane = sizeof(float) * (size_t)h->Pfull;
