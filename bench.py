@@ -196,6 +196,8 @@ def main():
     ap.add_argument("--config", default="C3", choices=["C2", "C3", "C4", "C5"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-side-modes", action="store_true", help="skip the f16 / tf32 side figures")
+    ap.add_argument("--side-configs", default="auto", help="comma-separated BASELINE configs benched briefly beside the main one at N = 1 "
+                    "(config.side_<cfg>_fps); auto = C2,C4,C5 beside a default C3 run, none otherwise")
     ap.add_argument("--one-stream-strips", action="store_true", help="N > 1: path trace and denoiser of a strip on one stream (no gated live-count mail)")
     args = ap.parse_args()
     W, H = {"C2": (1280, 720), "C3": (1280, 720), "C4": (1920, 1080), "C5": (2560, 1440)}[args.config]
@@ -261,22 +263,24 @@ def main():
 
     SLOTS = capi.frame_slots()                          # frames the C++ loop keeps in flight (3)
 
-    def frame_loop(pt_, dn_, first_cam, n, hosts=None, reset_first=False):
+    def frame_loop(pt_, dn_, first_cam, n, hosts=None, reset_first=False, cams_=None):
         """n frames through ptd_frame_submit / ptd_frame_wait, frames k + 1 and k + 2 submitted before frame k is awaited; every frame has been
         waited for on return.  hosts = [(gbuf, rgb)] * SLOTS pinned tensors, or None (nothing leaves the device)."""
+        cams_ = cams if cams_ is None else cams_
         for k in range(n):
             g, r = (hosts[k % SLOTS] if hosts else (None, None))
-            pt_.frame_submit(dn_, r, g, cam=cams[first_cam + k], reset=(reset_first and k == 0))
+            pt_.frame_submit(dn_, r, g, cam=cams_[first_cam + k], reset=(reset_first and k == 0))
             if k >= SLOTS - 1:
                 pt_.frame_wait()
         for _ in range(min(n, SLOTS - 1)):
             pt_.frame_wait()
 
-    def device_timed(pt_, dn_, first_cam, n):
+    def device_timed(pt_, dn_, first_cam, n, cams_=None):
+        cams_ = cams if cams_ is None else cams_
         sync_all()
         pt_.frame_timer_start()
         for k in range(n):
-            pt_.frame_submit(dn_, None, None, cam=cams[first_cam + k])
+            pt_.frame_submit(dn_, None, None, cam=cams_[first_cam + k])
             if k >= SLOTS - 1:
                 pt_.frame_wait()
         ms = pt_.frame_timer_stop()
@@ -413,6 +417,29 @@ def main():
                             tolerance="max-abs <= 2e-2, rel-L2 <= 5e-3 vs the fp32 reference model (measured 3.5e-3 / 3.4e-4 at 720p)")
             del dn2
 
+    # ---- the other BASELINE configs beside the default one (N = 1, contract mode, same frame loop, short runs): C2 Cornell 720p, C4 1080p
+    # reflective mesh with per-face MTL materials, C5 580 k triangles at 2560 x 1440.  A failure here never costs the main line.
+    side_configs = None
+    side_list = [c for c in args.side_configs.split(",") if c] if args.side_configs != "auto" else \
+                (["C2", "C4", "C5"] if args.config == "C3" and args.mode == "2xf16" and not args.no_side_modes else [])
+    if world == 1 and side_list:
+        side_configs = {}
+        for cfg in side_list:
+            try:
+                W2, H2 = {"C2": (1280, 720), "C3": (1280, 720), "C4": (1920, 1080), "C5": (2560, 1440)}[cfg]
+                path2, _ = make_scene(cfg, W2, H2)
+                sc2 = capi.Scene(path=path2)
+                pt2 = capi.PathTracer(sc2, device=local)
+                dn2 = capi.Denoiser(wfile, H2, W2, device=local, flags=FLAGS[args.mode])
+                n2 = min(args.steps, 24)
+                cams2 = [capi.frame_camera(sc2.camera[0], k) for k in range(n2 + 8)]
+                frame_loop(pt2, dn2, 0, 4, reset_first=True, cams_=cams2)
+                ms2 = device_timed(pt2, dn2, 4, n2, cams_=cams2)
+                side_configs[cfg] = round(n2 / (ms2 * 1e-3), 1)
+                del pt2, dn2, sc2
+            except Exception as e:                       # noqa: BLE001 - reported in the line, the C3 figures stand
+                side_configs[cfg] = "failed: %s" % str(e)[:100]
+
     # ---- context for N > 1: the same GPUs as N independent frame sequences (no tiling, no coupling), aggregate frames/s ----
     replicas = None
     if world > 1:
@@ -444,6 +471,8 @@ def main():
     if modes:
         out["modes"] = modes
         out["config"].update({"side_%s_fps" % m: v["value"] for m, v in modes.items()})      # flat copies of the side figures
+    if side_configs:
+        out["config"].update({"side_%s_fps" % c: v for c, v in side_configs.items()})           # frames/s, same metric, N = 1
     if replicas:
         out["replicas"] = replicas
         out["config"]["replicas_fps"] = replicas["value"]

@@ -102,7 +102,7 @@ def _run(bench, capsys, argv):
 
 def test_bench_host_logic_runs_and_keeps_the_json_contract(bench_env, capsys):
     bench, lib, log = bench_env
-    d = _run(bench, capsys, ["--config", "C2", "--steps", "4", "--warmup", "3", "--no-cpu-baseline"])
+    d = _run(bench, capsys, ["--config", "C2", "--steps", "4", "--warmup", "3", "--no-cpu-baseline", "--side-configs", "C2"])
     for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype", "data",
                 "config", "gpu_launches", "e2e", "roofline", "clocks", "modes"):
         assert key in d, key
@@ -113,7 +113,8 @@ def test_bench_host_logic_runs_and_keeps_the_json_contract(bench_env, capsys):
     assert d["e2e"]["api"].startswith("ptd_frame_submit") and d["e2e"]["h2d_bytes_per_step"] == 84 and d["e2e"]["d2h_bytes_per_step"] == 52 * 1280 * 720
     submits = [e for e in log if e[0] == "submit"]
     assert len(submits) == len([e for e in log if e[0] == "wait"])                               # every frame submitted is awaited
-    assert len(submits) == (3 + 4) + (3 + 4) + 2 * (4 + 4)                                        # value leg, e2e leg, two side modes
+    assert len(submits) == (3 + 4) + (3 + 4) + 2 * (4 + 4) + (4 + 4)                              # value leg, e2e leg, two side modes, one side config
+    assert isinstance(d["config"]["side_C2_fps"], float) and d["config"]["side_f16_fps"] == d["modes"]["f16"]["value"]
     assert sum(1 for e in submits if e[1] and e[2]) == 3 + 4                                      # only the e2e leg hands host buffers in
     assert d["gpu_launches"] == (2 * 8 + 30) * 4
 
