@@ -3,7 +3,7 @@
 OUT=gpurun_out/${1:-dbg}; mkdir -p $OUT
 for dbg in 0 1 2 4 3 7; do
   for m in f16 tf32; do
-    PTD_DN_DEBUG=$dbg timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-autotune --no-pipeline --e2e calls --mode $m > $OUT/b_${m}_$dbg.json 2> $OUT/b_${m}_$dbg.err
+    PTD_DN_DEBUG=$dbg timeout 200 python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-side-modes --mode $m > $OUT/b_${m}_$dbg.json 2> $OUT/b_${m}_$dbg.err
     python - $OUT/b_${m}_$dbg.json $m $dbg <<'PY'
 import json,sys
 try:

@@ -9,7 +9,7 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$
 nproc > "$OUT/nproc.txt"
 timeout 120 tools/microbench/umma_rate 2048 > "$OUT/umma_rate.txt" 2>&1; echo "umma_rate rc=$?"; head -60 "$OUT/umma_rate.txt"
 PTD_OPTIN_TESTS=1 timeout 1500 python -m pytest tests -m gpu -q -s --durations=15 > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?"; tail -40 "$OUT/pytest_gpu.log"
-B="--steps 60 --warmup 5 --no-cpu-baseline --no-autotune"
+B="--steps 60 --warmup 5 --no-cpu-baseline"
 run() { name=$1; shift; timeout 300 env "$@" python bench.py $B $EXTRA > "$OUT/bench_$name.json" 2> "$OUT/bench_$name.err"; echo "$name rc=$?"; }
 EXTRA=""
 run default X=1

@@ -14,7 +14,7 @@ for w in $WHAT; do
     smoke)    timeout 600 python -c "import __graft_entry__ as g; g.smoke()" > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?"; tail -2 "$OUT/smoke.log";;
     bench)    timeout 900 python bench.py > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?"; cat "$OUT/bench.json"; tail -3 "$OUT/bench.err";;
     launches) timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file "$OUT/launches.csv" \
-                python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-autotune > "$OUT/launches_bench.log" 2>&1; echo "launches rc=$?";;
+                python bench.py --steps 2 --warmup 3 --no-cpu-baseline > "$OUT/launches_bench.log" 2>&1; echo "launches rc=$?";;
     ncu_conv) timeout 900 ncu --set full --clock-control none --import-source on -k regex:conv_tc -s ${NCU_CONV_SKIP:-28} -c ${NCU_CONV_COUNT:-3} -f -o "$OUT/conv_tc" \
                 python tools/run_frames.py C3 2 tf32 > "$OUT/ncu_conv.log" 2>&1; echo "ncu_conv rc=$?";;
     ncu_pt)   timeout 900 ncu --set full --clock-control none --import-source on -k regex:pt_trace -s ${NCU_PT_SKIP:-9} -c ${NCU_PT_COUNT:-2} -f -o "$OUT/pt_trace" \
